@@ -1,0 +1,375 @@
+"""Checkpoint ingestion: reference ``state_dict`` -> packed device blob.
+
+The reference ships plain ``state_dict`` ``.pth`` files in the *offline* naming
+(``model/dpdfnet.py:642-643``); the streaming model renames a few keys
+(``onnx_model/dpdfnet.py:876-888``) but the arithmetic is the same.  This module
+
+* enumerates the parameter shapes of a checkpoint (``ref_param_shapes``),
+* builds a seeded random checkpoint with **randomised BatchNorm running statistics**
+  (no shipped weights are available offline; fresh BN would hide folding bugs),
+* packs a checkpoint into the engine's blob: eval-BatchNorm folded into the preceding
+  bias-free convolution (eps 1e-5, ``torch.nn.BatchNorm2d`` default), GRU biases pre-summed
+  for the r/z gates, grouped linears stacked ``[G, O/G, I/G]``, and the windowed DFT bases.
+
+Blob format (little endian): ``b"DPDFW001"``, ``int64 n_entries``, then ``n_entries`` records of
+``char name[56]; int64 offset_floats; int64 numel`` followed by the float32 payload.  Offsets
+are relative to the payload start and 32-float (128 B) aligned.
+"""
+from __future__ import annotations
+
+import struct
+from collections import OrderedDict
+from typing import Dict, Mapping, Tuple
+
+import numpy as np
+
+from .spec import CONV_CH, DF_ORDER, GRU_DIM, NB_DF, ModelSpec, vorbis_window
+
+MAGIC = b"DPDFW001"
+NAME_LEN = 56
+ALIGN = 32  # floats
+BN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------
+# reference checkpoint shape table
+# --------------------------------------------------------------------------
+
+def _gl(shapes, prefix: str, groups: int, k: int, n: int):
+    for g in range(groups):
+        shapes[f"{prefix}.layers.{g}.weight"] = (n, k)
+        shapes[f"{prefix}.layers.{g}.bias"] = (n,)
+
+
+def _bn(shapes, prefix: str, ch: int):
+    shapes[f"{prefix}.weight"] = (ch,)
+    shapes[f"{prefix}.bias"] = (ch,)
+    shapes[f"{prefix}.running_mean"] = (ch,)
+    shapes[f"{prefix}.running_var"] = (ch,)
+
+
+def _gru(shapes, prefix: str, inp: int, hid: int, layers: int = 1, reverse: bool = False):
+    for l in range(layers):
+        for suf in ([""] + (["_reverse"] if reverse else [])):
+            shapes[f"{prefix}.weight_ih_l{l}{suf}"] = (3 * hid, inp if l == 0 else hid)
+            shapes[f"{prefix}.weight_hh_l{l}{suf}"] = (3 * hid, hid)
+            shapes[f"{prefix}.bias_ih_l{l}{suf}"] = (3 * hid,)
+            shapes[f"{prefix}.bias_hh_l{l}{suf}"] = (3 * hid,)
+
+
+def ref_param_shapes(spec: ModelSpec) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Learned tensors of a reference checkpoint (offline naming), buffers excluded."""
+    C = CONV_CH
+    s: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+    s["enc.erb_conv0.1.weight"] = (C, 1, 3, 3)
+    _bn(s, "enc.erb_conv0.2", C)
+    for i in (1, 2, 3):
+        s[f"enc.erb_conv{i}.0.weight"] = (C, 1, 1, 3)
+        s[f"enc.erb_conv{i}.1.weight"] = (C, C, 1, 1)
+        _bn(s, f"enc.erb_conv{i}.2", C)
+    s["enc.df_conv0.1.convs.0.weight"] = (C // 2, 1, 3, 3)
+    s["enc.df_conv0.1.convs.1.weight"] = (C // 2, 1, 3, 3)
+    s["enc.df_conv0.2.weight"] = (C, C, 1, 1)
+    _bn(s, "enc.df_conv0.3", C)
+    s["enc.df_conv1.0.weight"] = (C, 1, 1, 3)
+    s["enc.df_conv1.1.weight"] = (C, C, 1, 1)
+    _bn(s, "enc.df_conv1.2", C)
+    for br in ("erb", "df"):
+        for i in range(spec.n_blocks):
+            p = f"enc.dprnn_{br}.blocks.{i}"
+            _gru(s, f"{p}.intra_gru", C, C, reverse=True)
+            s[f"{p}.fc_intra.weight"] = (C, 2 * C)
+            s[f"{p}.fc_intra.bias"] = (C,)
+            s[f"{p}.ln_intra.weight"] = (C,)
+            s[f"{p}.ln_intra.bias"] = (C,)
+            _gru(s, f"{p}.inter_gru", C, C)
+            s[f"{p}.fc_inter.weight"] = (C, C)
+            s[f"{p}.fc_inter.bias"] = (C,)
+            s[f"{p}.ln_inter.weight"] = (C,)
+            s[f"{p}.ln_inter.bias"] = (C,)
+    if spec.hr48:
+        _gl(s, "enc.erb_fc_emb.0", 32, C * spec.fe[3] // 32, 16)
+    _gl(s, "enc.df_fc_emb.0", 32, C * (NB_DF // 2) // 32, 16)
+    _gl(s, "enc.emb_gru.linear_in.0", 16, 64, 16)
+    _gru(s, "enc.emb_gru.gru", GRU_DIM, GRU_DIM)
+    _gl(s, "enc.emb_gru.linear_out.0", 16, 16, 32)
+    s["enc.lsnr_fc.0.weight"] = (1, 512)
+    s["enc.lsnr_fc.0.bias"] = (1,)
+    _gl(s, "erb_dec.emb_gru.linear_in.0", 16, 32, 16)
+    _gru(s, "erb_dec.emb_gru.gru", GRU_DIM, GRU_DIM, layers=2)
+    _gl(s, "erb_dec.emb_gru.linear_out.0", 16, 16, 32)
+    if spec.hr48:
+        _gl(s, "erb_dec.erb_fc_emb.0", 32, 16, C * spec.fe[3] // 32)
+    up3, up2, up1 = spec.dec_up
+    for i, up in ((3, up3), (2, up2), (1, up1)):
+        s[f"erb_dec.conv{i}p.0.weight"] = (C, 1, 1, 1)
+        _bn(s, f"erb_dec.conv{i}p.1", C)
+        if up == 1:
+            s[f"erb_dec.convt{i}.0.weight"] = (C, 1, 1, 3)
+        else:
+            for j in range(up):
+                s[f"erb_dec.convt{i}.0.convs.{j}.weight"] = (C, 1, 1, 3)
+        s[f"erb_dec.convt{i}.1.weight"] = (C, C, 1, 1)
+        _bn(s, f"erb_dec.convt{i}.2", C)
+    s["erb_dec.conv0p.0.weight"] = (C, 1, 1, 1)
+    _bn(s, "erb_dec.conv0p.1", C)
+    s["erb_dec.conv0_out.0.weight"] = (1, C, 1, 3)
+    _bn(s, "erb_dec.conv0_out.1", 1)
+    s["df_dec.df_convp.1.convs.0.weight"] = (DF_ORDER, C // 2, DF_ORDER, 1)
+    s["df_dec.df_convp.1.convs.1.weight"] = (DF_ORDER, C // 2, DF_ORDER, 1)
+    s["df_dec.df_convp.2.weight"] = (2 * DF_ORDER, 2 * DF_ORDER, 1, 1)
+    _bn(s, "df_dec.df_convp.3", 2 * DF_ORDER)
+    _gl(s, "df_dec.df_gru.linear_in.0", 8, 64, 32)       # default linear_groups=8 quirk
+    _gru(s, "df_dec.df_gru.gru", GRU_DIM, GRU_DIM, layers=2)
+    _gl(s, "df_dec.df_skip", 16, 32, 16)
+    _gl(s, "df_dec.df_out.0", 16, 16, NB_DF * 2 * DF_ORDER // 16)
+    return s
+
+
+def random_checkpoint(spec: ModelSpec, seed: int = 0) -> "OrderedDict[str, np.ndarray]":
+    """Deterministic (numpy PCG64) stand-in for a shipped checkpoint, reference naming."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sd: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for name, shape in ref_param_shapes(spec).items():
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "running_var":
+            v = rng.uniform(0.5, 1.5, shape)
+        elif leaf == "running_mean":
+            v = rng.uniform(-0.2, 0.2, shape)
+        elif leaf == "weight" and len(shape) == 1:
+            v = rng.uniform(0.5, 1.5, shape)          # LayerNorm / BatchNorm gamma
+        elif len(shape) == 1:
+            v = rng.uniform(-0.2, 0.2, shape)          # all biases (incl. BN/LN beta, GRU biases)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            if "gru" in name and "linear" not in name:
+                bound = np.sqrt(6.0 / (shape[0] // 3 + shape[1]))   # ~xavier per gate
+            else:
+                bound = np.sqrt(3.0 / fan_in)
+            v = rng.uniform(-bound, bound, shape)
+        sd[name] = np.ascontiguousarray(v, dtype=np.float32)
+    return sd
+
+
+# --------------------------------------------------------------------------
+# packing
+# --------------------------------------------------------------------------
+
+def _bn_affine(sd: Mapping[str, np.ndarray], prefix: str) -> Tuple[np.ndarray, np.ndarray]:
+    g = sd[f"{prefix}.weight"].astype(np.float64)
+    b = sd[f"{prefix}.bias"].astype(np.float64)
+    m = sd[f"{prefix}.running_mean"].astype(np.float64)
+    v = sd[f"{prefix}.running_var"].astype(np.float64)
+    sc = g / np.sqrt(v + BN_EPS)
+    return sc, b - m * sc
+
+
+def _gl_pack(sd, prefix: str, groups: int) -> Tuple[np.ndarray, np.ndarray]:
+    w = np.stack([sd[f"{prefix}.layers.{g}.weight"] for g in range(groups)], 0)   # [G, O/G, I/G]
+    b = np.concatenate([sd[f"{prefix}.layers.{g}.bias"] for g in range(groups)], 0)
+    return w, b
+
+
+def _gru_bias(b_ih: np.ndarray, b_hh: np.ndarray) -> np.ndarray:
+    """[4, H]: (b_ir+b_hr, b_iz+b_hz, b_in, b_hn); gate order r,z,n as torch.nn.GRU."""
+    H = b_ih.shape[0] // 3
+    bi, bh = b_ih.reshape(3, H).astype(np.float64), b_hh.reshape(3, H).astype(np.float64)
+    return np.stack([bi[0] + bh[0], bi[1] + bh[1], bi[2], bh[2]], 0)
+
+
+def dft_bases(spec: ModelSpec) -> Dict[str, np.ndarray]:
+    """Windowed real-DFT bases with ``wnorm`` folded in.
+
+    Analysis (stream.py:119-126 / model/dpdfnet.py:608-613): ``X_k = wnorm * sum_n x_n w_n e^{-2 pi i nk/N}``.
+    Synthesis (stream.py:138-144 / model/dpdfnet.py:615-625): ``y_n = w_n / wnorm * irfft(Y)_n``.
+    """
+    N, F = spec.win, spec.freq_bins
+    w = vorbis_window(N)
+    n = np.arange(N, dtype=np.float64)[:, None]
+    k = np.arange(F, dtype=np.float64)[None, :]
+    ang = 2.0 * np.pi * ((n * k) % N) / N
+    fwd_c = (w[:, None] * np.cos(ang)) * spec.wnorm            # [N, F]
+    fwd_s = (-w[:, None] * np.sin(ang)) * spec.wnorm
+    ck = np.full(F, 2.0)
+    ck[0] = 1.0
+    ck[-1] = 1.0
+    inv_c = (ck[:, None] * np.cos(ang.T)) * (w[None, :] / (N * spec.wnorm))     # [F, N]
+    inv_s = (-ck[:, None] * np.sin(ang.T)) * (w[None, :] / (N * spec.wnorm))
+    inv_s[0, :] = 0.0
+    inv_s[-1, :] = 0.0
+    return {"const.dft_fwd_c": fwd_c, "const.dft_fwd_s": fwd_s,
+            "const.dft_inv_c": inv_c, "const.dft_inv_s": inv_s}
+
+
+def norm_init(spec: ModelSpec) -> Tuple[np.ndarray, np.ndarray]:
+    """(mu0, s0): ErbNorm/SpecNorm linspace inits (layers.py:460-463, 519-522) or the 48 kHz tables."""
+    if spec.hr48:
+        from .data import norm_init_48k
+        return norm_init_48k.MU0.astype(np.float32), norm_init_48k.S0.astype(np.float32)
+    # float32 arithmetic exactly as torch: init0 + arange * step
+    step_mu = np.float32((-90.0 - -60.0) / (spec.fe_feat - 1))
+    mu0 = np.float32(-60.0) + np.arange(spec.fe_feat, dtype=np.float32) * step_mu
+    step_s = np.float32((0.0001 - 0.001) / (NB_DF - 1))
+    s0 = np.float32(0.001) + np.arange(NB_DF, dtype=np.float32) * step_s
+    return mu0.astype(np.float32), s0.astype(np.float32)
+
+
+def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[str, np.ndarray]":
+    """Reference checkpoint -> named float32 tensors in engine layout."""
+    C = CONV_CH
+    sd = {k: np.asarray(v) for k, v in sd.items()}
+    missing = [k for k in ref_param_shapes(spec) if k not in sd]
+    if missing:
+        raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
+    for k, shp in ref_param_shapes(spec).items():
+        if tuple(sd[k].shape) != tuple(shp):
+            raise ValueError(f"{k}: expected shape {shp}, got {tuple(sd[k].shape)}")
+    t: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for k, v in dft_bases(spec).items():
+        t[k] = v
+    mu0, s0 = norm_init(spec)
+    t["const.mu0"], t["const.s0"] = mu0, s0
+
+    def sep(prefix_out: str, dw_keys, pw_key: str, bn_prefix: str):
+        # depthwise [S][3][C] (tap-major, channel contiguous); pointwise [C_out][C_in] with BN scale folded
+        dws = [sd[k][:, 0, 0, :].T for k in dw_keys]                       # [3, C] each
+        sc, sh = _bn_affine(sd, bn_prefix)
+        t[f"{prefix_out}.dw"] = np.stack(dws, 0)
+        t[f"{prefix_out}.pw"] = sd[pw_key][:, :, 0, 0].astype(np.float64) * sc[:, None]
+        t[f"{prefix_out}.b"] = sh
+
+    # --- encoder -----------------------------------------------------------
+    sc, sh = _bn_affine(sd, "enc.erb_conv0.2")
+    w = sd["enc.erb_conv0.1.weight"][:, 0].astype(np.float64) * sc[:, None, None]       # [C,3,3]
+    t["enc.erb_conv0.w"] = w.reshape(C, 9).T                                            # [9, C]
+    t["enc.erb_conv0.b"] = sh
+    for i in (1, 2, 3):
+        sep(f"enc.erb_conv{i}", [f"enc.erb_conv{i}.0.weight"], f"enc.erb_conv{i}.1.weight", f"enc.erb_conv{i}.2")
+    gw = np.concatenate([sd["enc.df_conv0.1.convs.0.weight"][:, 0], sd["enc.df_conv0.1.convs.1.weight"][:, 0]], 0)
+    t["enc.df_conv0.w"] = gw.reshape(C, 9).T                                            # [9, C]; ch<32 <- re, else im
+    sc, sh = _bn_affine(sd, "enc.df_conv0.3")
+    t["enc.df_conv0.pw"] = sd["enc.df_conv0.2.weight"][:, :, 0, 0].astype(np.float64) * sc[:, None]
+    t["enc.df_conv0.b"] = sh
+    sep("enc.df_conv1", ["enc.df_conv1.0.weight"], "enc.df_conv1.1.weight", "enc.df_conv1.2")
+
+    for br in ("erb", "df"):
+        for i in range(spec.n_blocks):
+            p = f"enc.dprnn_{br}.blocks.{i}"
+            q = f"enc.dprnn_{br}.{i}"
+            t[f"{q}.intra.wih"] = np.stack([sd[f"{p}.intra_gru.weight_ih_l0"], sd[f"{p}.intra_gru.weight_ih_l0_reverse"]], 0)
+            t[f"{q}.intra.whh"] = np.stack([sd[f"{p}.intra_gru.weight_hh_l0"], sd[f"{p}.intra_gru.weight_hh_l0_reverse"]], 0)
+            t[f"{q}.intra.bias"] = np.stack([
+                _gru_bias(sd[f"{p}.intra_gru.bias_ih_l0"], sd[f"{p}.intra_gru.bias_hh_l0"]),
+                _gru_bias(sd[f"{p}.intra_gru.bias_ih_l0_reverse"], sd[f"{p}.intra_gru.bias_hh_l0_reverse"])], 0)
+            t[f"{q}.intra.fc_w"] = sd[f"{p}.fc_intra.weight"]
+            t[f"{q}.intra.fc_b"] = sd[f"{p}.fc_intra.bias"]
+            t[f"{q}.intra.ln_g"] = sd[f"{p}.ln_intra.weight"]
+            t[f"{q}.intra.ln_b"] = sd[f"{p}.ln_intra.bias"]
+            t[f"{q}.inter.wih"] = sd[f"{p}.inter_gru.weight_ih_l0"]
+            t[f"{q}.inter.whh"] = sd[f"{p}.inter_gru.weight_hh_l0"]
+            t[f"{q}.inter.bias"] = _gru_bias(sd[f"{p}.inter_gru.bias_ih_l0"], sd[f"{p}.inter_gru.bias_hh_l0"])
+            t[f"{q}.inter.fc_w"] = sd[f"{p}.fc_inter.weight"]
+            t[f"{q}.inter.fc_b"] = sd[f"{p}.fc_inter.bias"]
+            t[f"{q}.inter.ln_g"] = sd[f"{p}.ln_inter.weight"]
+            t[f"{q}.inter.ln_b"] = sd[f"{p}.ln_inter.bias"]
+
+    def gl(out: str, prefix: str, groups: int):
+        t[f"{out}.w"], t[f"{out}.b"] = _gl_pack(sd, prefix, groups)
+
+    def gru(out: str, prefix: str, layers: int):
+        for l in range(layers):
+            t[f"{out}.{l}.wih"] = sd[f"{prefix}.weight_ih_l{l}"]
+            t[f"{out}.{l}.whh"] = sd[f"{prefix}.weight_hh_l{l}"]
+            t[f"{out}.{l}.bias"] = _gru_bias(sd[f"{prefix}.bias_ih_l{l}"], sd[f"{prefix}.bias_hh_l{l}"])
+
+    if spec.hr48:
+        gl("enc.erb_fc_emb", "enc.erb_fc_emb.0", 32)
+    gl("enc.df_fc_emb", "enc.df_fc_emb.0", 32)
+    gl("enc.emb_gru.lin_in", "enc.emb_gru.linear_in.0", 16)
+    gru("enc.emb_gru.gru", "enc.emb_gru.gru", 1)
+    gl("enc.emb_gru.lin_out", "enc.emb_gru.linear_out.0", 16)
+
+    # --- ERB decoder -------------------------------------------------------
+    gl("erb_dec.emb_gru.lin_in", "erb_dec.emb_gru.linear_in.0", 16)
+    gru("erb_dec.emb_gru.gru", "erb_dec.emb_gru.gru", 2)
+    gl("erb_dec.emb_gru.lin_out", "erb_dec.emb_gru.linear_out.0", 16)
+    if spec.hr48:
+        gl("erb_dec.erb_fc_emb", "erb_dec.erb_fc_emb.0", 32)
+    for i, up in zip((3, 2, 1), spec.dec_up):
+        sc, sh = _bn_affine(sd, f"erb_dec.conv{i}p.1")
+        t[f"erb_dec.conv{i}p.a"] = sd[f"erb_dec.conv{i}p.0.weight"].reshape(C).astype(np.float64) * sc
+        t[f"erb_dec.conv{i}p.b"] = sh
+        keys = [f"erb_dec.convt{i}.0.weight"] if up == 1 else [f"erb_dec.convt{i}.0.convs.{j}.weight" for j in range(up)]
+        sep(f"erb_dec.convt{i}", keys, f"erb_dec.convt{i}.1.weight", f"erb_dec.convt{i}.2")
+    sc, sh = _bn_affine(sd, "erb_dec.conv0p.1")
+    t["erb_dec.conv0p.a"] = sd["erb_dec.conv0p.0.weight"].reshape(C).astype(np.float64) * sc
+    t["erb_dec.conv0p.b"] = sh
+    sc, sh = _bn_affine(sd, "erb_dec.conv0_out.1")
+    t["erb_dec.conv0_out.w"] = sd["erb_dec.conv0_out.0.weight"][0, :, 0, :].T.astype(np.float64) * sc[0]   # [3, C]
+    t["erb_dec.conv0_out.b"] = sh
+
+    # --- DF decoder --------------------------------------------------------
+    gw = np.concatenate([sd["df_dec.df_convp.1.convs.0.weight"][..., 0],
+                         sd["df_dec.df_convp.1.convs.1.weight"][..., 0]], 0)            # [10, 32, 5(kt)]
+    t["df_dec.df_convp.w"] = gw.transpose(0, 2, 1)                                       # [10, 5(kt), 32]
+    sc, sh = _bn_affine(sd, "df_dec.df_convp.3")
+    t["df_dec.df_convp.pw"] = sd["df_dec.df_convp.2.weight"][:, :, 0, 0].astype(np.float64) * sc[:, None]
+    t["df_dec.df_convp.b"] = sh
+    gl("df_dec.df_gru.lin_in", "df_dec.df_gru.linear_in.0", 8)
+    gru("df_dec.df_gru.gru", "df_dec.df_gru.gru", 2)
+    gl("df_dec.df_skip", "df_dec.df_skip", 16)
+    gl("df_dec.df_out", "df_dec.df_out.0", 16)
+    return OrderedDict((k, np.ascontiguousarray(v, dtype=np.float32)) for k, v in t.items())
+
+
+def serialize(tensors: Mapping[str, np.ndarray]) -> bytes:
+    names = list(tensors)
+    offsets, cur = [], 0
+    for n in names:
+        offsets.append(cur)
+        cur += (tensors[n].size + ALIGN - 1) // ALIGN * ALIGN
+    head = bytearray(MAGIC + struct.pack("<q", len(names)))
+    for n, off in zip(names, offsets):
+        nb = n.encode()
+        if len(nb) >= NAME_LEN:
+            raise ValueError(f"tensor name too long: {n}")
+        head += nb.ljust(NAME_LEN, b"\0") + struct.pack("<qq", off, tensors[n].size)
+    pad = (-len(head)) % 128
+    head += b"\0" * pad
+    payload = np.zeros(cur, dtype=np.float32)
+    for n, off in zip(names, offsets):
+        payload[off:off + tensors[n].size] = tensors[n].reshape(-1)
+    return bytes(head) + payload.tobytes()
+
+
+def deserialize(blob: bytes) -> "OrderedDict[str, np.ndarray]":
+    if blob[:8] != MAGIC:
+        raise ValueError("not a DPDFNet-B200 weight blob")
+    (n,) = struct.unpack_from("<q", blob, 8)
+    rec = NAME_LEN + 16
+    head = 16 + n * rec
+    head += (-head) % 128
+    payload = np.frombuffer(blob, dtype=np.float32, offset=head)
+    out: "OrderedDict[str, np.ndarray]" = OrderedDict()
+    for i in range(n):
+        base = 16 + i * rec
+        name = blob[base:base + NAME_LEN].split(b"\0", 1)[0].decode()
+        off, numel = struct.unpack_from("<qq", blob, base + NAME_LEN)
+        out[name] = payload[off:off + numel]
+    return out
+
+
+def pack_checkpoint(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> bytes:
+    return serialize(pack_tensors(spec, sd))
+
+
+def load_checkpoint_file(path) -> Dict[str, np.ndarray]:
+    """Load a reference ``.pth`` (plain ``state_dict`` or ``{'state_dict': ...}``) as numpy."""
+    import torch
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception:
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+    if isinstance(obj, dict) and "state_dict" in obj and not any(k.startswith("enc.") for k in obj):
+        obj = obj["state_dict"]
+    return {k: v.detach().cpu().numpy() for k, v in obj.items() if hasattr(v, "detach")}

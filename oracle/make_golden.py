@@ -1,0 +1,78 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference PyTorch modules.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Vectors (weights are regenerated from ``seed`` by dpdfnet_b200.weights.random_checkpoint):
+* ``stream_<model>.npz``  - per-frame ``onnx_model`` DPDFNet.forward(spec, state) behind the
+  ONNX wrapper scaling (export_dpdfnet_to_onnx.py:21-25): inputs ``spec_in [T,F,2]``, reference
+  ``spec_out [T,F,2]`` and the final flat ``state [S]``.
+* ``offline_<model>.npz`` - whole-utterance ``model/dpdfnet.py`` DPDFNet.forward(waveform):
+  ``wave_in [B,n]`` and reference ``wave_out [B,hop*(T-1)]``.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from dpdfnet_b200.spec import get_spec  # noqa: E402
+from dpdfnet_b200.weights import random_checkpoint  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+SEED = 0
+
+
+def test_signal(rng, sr, n, batch):
+    """Seeded white noise + AM-modulated harmonic tones (no speech corpus offline)."""
+    t = np.arange(n) / sr
+    x = 0.05 * rng.standard_normal((batch, n))
+    for b in range(batch):
+        f0 = 140.0 + 60.0 * b
+        for h in (1, 2, 3):
+            x[b] += (0.12 / h) * np.sin(2 * np.pi * f0 * h * t + b) * (0.6 + 0.4 * np.sin(2 * np.pi * (2.0 + h) * t))
+    return np.clip(x, -1, 1).astype(np.float32)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    for name, frames, secs in (("dpdfnet2", 16, 2.0), ("dpdfnet4", 8, 0.5), ("dpdfnet2_48khz_hr", 10, 0.5)):
+        spec = get_spec(name)
+        ck = random_checkpoint(spec, SEED)
+        rng = np.random.default_rng(1234)
+        # ---- streaming, per frame --------------------------------------
+        ref = ref_import.streaming_model(spec, ck)
+        n = spec.hop * (frames + 1)
+        wave = test_signal(rng, spec.sample_rate, n, 1)[0]
+        win = np.sin(0.5 * np.pi * np.sin(0.5 * np.pi * (np.arange(spec.win) + 0.5) / (spec.win / 2)) ** 2)
+        spec_in = np.zeros((frames, spec.freq_bins, 2), np.float32)
+        for t in range(frames):
+            X = np.fft.rfft(wave[t * spec.hop:t * spec.hop + spec.win].astype(np.float64) * win)
+            spec_in[t, :, 0], spec_in[t, :, 1] = X.real, X.imag
+        state = ref.initial_state(dtype=torch.float32)
+        outs = []
+        wn = torch.tensor(float(spec.wnorm), dtype=torch.float32)
+        iwn = torch.tensor(1.0 / float(spec.wnorm), dtype=torch.float32)
+        with torch.no_grad():
+            for t in range(frames):
+                y, state = ref(torch.from_numpy(spec_in[t])[None, None] * wn, state)
+                outs.append((y * iwn).numpy()[0, 0])
+        np.savez_compressed(OUT / f"stream_{name}.npz", seed=SEED, spec_in=spec_in,
+                            spec_out=np.stack(outs).astype(np.float32), state=state.numpy().astype(np.float32))
+        # ---- offline, whole clip ---------------------------------------
+        off = ref_import.offline_model(spec, ck)
+        wave_in = test_signal(rng, spec.sample_rate, int(secs * spec.sample_rate), 2)
+        with torch.no_grad():
+            wave_out, _ = off(torch.from_numpy(wave_in))
+        np.savez_compressed(OUT / f"offline_{name}.npz", seed=SEED, wave_in=wave_in,
+                            wave_out=wave_out.numpy().astype(np.float32))
+        print(name, "stream frames", frames, "offline", wave_in.shape, "->", tuple(wave_out.shape))
+
+
+if __name__ == "__main__":
+    main()
