@@ -1,0 +1,828 @@
+// C ABI of the engine (include/dpdfnet_b200.h): creation from a packed weight blob, the per-hop
+// kernel schedule (optionally replayed as a CUDA graph), host-buffer entry points and the
+// reference-layout state import / export.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "engine.h"
+
+using namespace dpdf;
+
+struct dpdf_engine { Engine e; };
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t err__ = (call);                                                                   \
+    if (err__ != cudaSuccess)                                                                     \
+      return fail(DPDF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* dpdf_last_error(void) { return g_err; }
+extern "C" const char* dpdf_version(void) { return "dpdfnet_b200 0.1 (sm_100a, fp32 FFMA2)"; }
+
+// ---------------------------------------------------------------------------------------------
+// weight blob
+// ---------------------------------------------------------------------------------------------
+static const int NAME_LEN = 56;
+
+static int parse_blob(Engine& e, const void* blob, size_t nbytes, const float** payload, size_t* payload_floats) {
+  const char* p = static_cast<const char*>(blob);
+  if (nbytes < 16 || memcmp(p, "DPDFW001", 8) != 0) return fail(DPDF_ERR_WEIGHTS, "not a DPDFNet-B200 weight blob");
+  long long n;
+  memcpy(&n, p + 8, 8);
+  const size_t rec = NAME_LEN + 16;
+  size_t head = 16 + (size_t)n * rec;
+  head += (128 - head % 128) % 128;
+  if (n <= 0 || head > nbytes) return fail(DPDF_ERR_WEIGHTS, "truncated weight blob header");
+  size_t maxend = 0;
+  for (long long i = 0; i < n; ++i) {
+    const char* r = p + 16 + i * rec;
+    char name[NAME_LEN + 1];
+    memcpy(name, r, NAME_LEN);
+    name[NAME_LEN] = 0;
+    long long off, numel;
+    memcpy(&off, r + NAME_LEN, 8);
+    memcpy(&numel, r + NAME_LEN + 8, 8);
+    if (off < 0 || numel < 0) return fail(DPDF_ERR_WEIGHTS, "corrupt entry %s", name);
+    e.wtable[name] = {(size_t)off, (size_t)numel};
+    if ((size_t)(off + numel) > maxend) maxend = off + numel;
+  }
+  if (head + maxend * sizeof(float) > nbytes) return fail(DPDF_ERR_WEIGHTS, "truncated weight blob payload");
+  *payload = reinterpret_cast<const float*>(p + head);
+  *payload_floats = (nbytes - head) / sizeof(float);
+  return 0;
+}
+
+static int bind_weights(Engine& e) {
+  const char* missing = nullptr;
+  static std::string missing_name;
+  auto W = [&](const std::string& name, size_t expect) -> const float* {
+    auto it = e.wtable.find(name);
+    if (it == e.wtable.end() || it->second.second != expect) {
+      if (!missing) { missing_name = name; missing = missing_name.c_str(); }
+      return nullptr;
+    }
+    return e.weights_dev + it->second.first;
+  };
+  const Dims& d = e.d;
+  Weights& w = e.w;
+  w.dft_fwd = W("const.dft_fwd", (size_t)d.win * d.F * 2);
+  w.dft_inv = W("const.dft_inv", (size_t)d.win * d.F * 2);
+  w.mu0 = W("const.mu0", d.fe_feat);
+  w.s0 = W("const.s0", NDF);
+  w.erb_conv0_w = W("enc.erb_conv0.w", 9 * C);
+  w.erb_conv0_b = W("enc.erb_conv0.b", C);
+  auto sep = [&](const std::string& n, int up) { return SepW{W(n + ".dw", (size_t)up * 3 * C), W(n + ".pw", C * C), W(n + ".b", C)}; };
+  for (int i = 0; i < 3; ++i) w.erb_conv[i] = sep("enc.erb_conv" + std::to_string(i + 1), 1);
+  w.df_conv0_w = W("enc.df_conv0.w", 9 * C);
+  w.df_conv0_pw = W("enc.df_conv0.pw", C * C);
+  w.df_conv0_b = W("enc.df_conv0.b", C);
+  w.df_conv1 = sep("enc.df_conv1", 1);
+  for (int br = 0; br < 2; ++br) {
+    auto& vec = br ? w.dprnn_df : w.dprnn_erb;
+    vec.resize(d.N);
+    for (int i = 0; i < d.N; ++i) {
+      const std::string q = std::string("enc.dprnn_") + (br ? "df." : "erb.") + std::to_string(i);
+      DprnnW& x = vec[i];
+      x.i_wih = W(q + ".intra.wih", 2 * 192 * C);  x.i_whh = W(q + ".intra.whh", 2 * 192 * C);
+      x.i_bias = W(q + ".intra.bias", 2 * 4 * C);
+      x.fc_w = W(q + ".intra.fc_w", C * 2 * C);    x.fc_b = W(q + ".intra.fc_b", C);
+      x.ln_g = W(q + ".intra.ln_g", C);            x.ln_b = W(q + ".intra.ln_b", C);
+      x.r_wih = W(q + ".inter.wih", 192 * C);      x.r_whh = W(q + ".inter.whh", 192 * C);
+      x.r_bias = W(q + ".inter.bias", 4 * C);
+      x.fc2_w = W(q + ".inter.fc_w", C * C);       x.fc2_b = W(q + ".inter.fc_b", C);
+      x.ln2_g = W(q + ".inter.ln_g", C);           x.ln2_b = W(q + ".inter.ln_b", C);
+    }
+  }
+  auto gl = [&](const std::string& n, int G, int Ng, int Kg) { return GLW{W(n + ".w", (size_t)G * Ng * Kg), W(n + ".b", (size_t)G * Ng), G, Ng, Kg}; };
+  auto gru = [&](const std::string& n) { return GRUW{W(n + ".wih", 3 * H * H), W(n + ".whh", 3 * H * H), W(n + ".bias", 4 * H)}; };
+  const int kfc = C * d.fe[3] / 32;
+  if (d.hr48) {
+    w.erb_fc_emb = gl("enc.erb_fc_emb", 32, 16, kfc);
+    w.erbdec_fc = gl("erb_dec.erb_fc_emb", 32, kfc, 16);
+  }
+  w.df_fc_emb = gl("enc.df_fc_emb", 32, 16, 96);
+  w.enc_in = gl("enc.emb_gru.lin_in", 16, 16, 64);
+  w.enc_gru = gru("enc.emb_gru.gru.0");
+  w.enc_out = gl("enc.emb_gru.lin_out", 16, 32, 16);
+  w.erbdec_in = gl("erb_dec.emb_gru.lin_in", 16, 16, 32);
+  w.erb_gru[0] = gru("erb_dec.emb_gru.gru.0");
+  w.erb_gru[1] = gru("erb_dec.emb_gru.gru.1");
+  w.erbdec_out = gl("erb_dec.emb_gru.lin_out", 16, 32, 16);
+  for (int i = 0; i < 3; ++i) {
+    const std::string n = std::to_string(3 - i);
+    w.convp_a[i] = W("erb_dec.conv" + n + "p.a", C);
+    w.convp_b[i] = W("erb_dec.conv" + n + "p.b", C);
+    w.convt[i] = sep("erb_dec.convt" + n, d.up[i]);
+  }
+  w.convp_a[3] = W("erb_dec.conv0p.a", C);
+  w.convp_b[3] = W("erb_dec.conv0p.b", C);
+  w.conv0_out_w = W("erb_dec.conv0_out.w", 3 * C);
+  w.conv0_out_b = W("erb_dec.conv0_out.b", 1);
+  w.dfp_w = W("df_dec.df_convp.w", 10 * ORD * 32);
+  w.dfp_pw = W("df_dec.df_convp.pw", 100);
+  w.dfp_b = W("df_dec.df_convp.b", 10);
+  w.dfdec_in = gl("df_dec.df_gru.lin_in", 8, 32, 64);
+  w.df_gru[0] = gru("df_dec.df_gru.gru.0");
+  w.df_gru[1] = gru("df_dec.df_gru.gru.1");
+  w.df_skip = gl("df_dec.df_skip", 16, 16, 32);
+  w.df_out = gl("df_dec.df_out", 16, 60, 16);
+  if (missing) return fail(DPDF_ERR_WEIGHTS, "weight tensor '%s' missing or of unexpected size", missing);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------------------------
+static int check_spec(const dpdf_spec* s) {
+  if (!s) return fail(DPDF_ERR_INVALID, "spec is NULL");
+  if (s->abi_version != DPDF_ABI_VERSION) return fail(DPDF_ERR_INVALID, "ABI version mismatch: %d vs %d", s->abi_version, DPDF_ABI_VERSION);
+  if (s->win != 2 * s->hop || s->freq_bins != s->win / 2 + 1 || s->win % 4 || s->win > 1024)
+    return fail(DPDF_ERR_INVALID, "unsupported framing win=%d hop=%d bins=%d", s->win, s->hop, s->freq_bins);
+  if (s->n_blocks < 0 || s->n_blocks > 64) return fail(DPDF_ERR_INVALID, "bad n_blocks %d", s->n_blocks);
+  int sum = 0;
+  for (int i = 0; i < 32; ++i) sum += s->erb_widths[i];
+  if (sum != s->freq_bins) return fail(DPDF_ERR_INVALID, "ERB widths sum to %d, expected %d", sum, s->freq_bins);
+  if (s->hr48 ? (s->fe_feat != s->freq_bins || s->fe[0] != s->freq_bins - 1) : (s->fe_feat != 32 || s->fe[0] != 32))
+    return fail(DPDF_ERR_INVALID, "inconsistent feature widths");
+  if ((C * s->fe[3]) % 32) return fail(DPDF_ERR_INVALID, "fe[3] not compatible with 32 linear groups");
+  return 0;
+}
+
+static size_t state_size_of(const Dims& d) {
+  return (size_t)d.fe_feat + NDF + 3 * d.fe_feat + (size_t)d.N * d.fe[3] * C + 3 * 2 * NDF + (size_t)d.N * (NDF / 2) * C +
+         5 * H + (size_t)ORD * C * NDF + 3 * d.F * 2 + 3 * ORD * NDF * 2 + (size_t)ORD * d.F * 2;
+}
+
+extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nbytes, int32_t max_streams,
+                           int32_t device, dpdf_engine** out) {
+  if (!out) return fail(DPDF_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (int rc = check_spec(spec)) return rc;
+  if (!weights) return fail(DPDF_ERR_WEIGHTS, "weights is NULL");
+  if (max_streams <= 0) return fail(DPDF_ERR_INVALID, "max_streams must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(DPDF_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(DPDF_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(DPDF_ERR_CUDA, "device %s is sm_%d%d; the engine is built for sm_100a only", prop.name, prop.major, prop.minor);
+
+  dpdf_engine* h = new dpdf_engine();
+  Engine& e = h->e;
+  e.spec = *spec;
+  e.device = device;
+  e.max_streams = max_streams;
+  e.num_sms = prop.multiProcessorCount;
+  Dims& d = e.d;
+  d.win = spec->win; d.hop = spec->hop; d.F = spec->freq_bins; d.fe_feat = spec->fe_feat;
+  for (int i = 0; i < 4; ++i) d.fe[i] = spec->fe[i];
+  for (int i = 0; i < 3; ++i) { d.stride[i] = spec->erb_strides[i]; d.up[i] = spec->dec_up[i]; }
+  d.N = spec->n_blocks; d.hr48 = spec->hr48;
+  const double wn = 1.0 / ((double)d.win * d.win / (2.0 * d.hop));
+  d.wnorm = (float)wn; d.inv_wnorm = (float)(1.0 / wn);
+  if ((int)state_size_of(d) != spec->state_size) {
+    delete h;
+    return fail(DPDF_ERR_INVALID, "state_size mismatch: spec says %d, layout gives %zu", spec->state_size, state_size_of(d));
+  }
+  auto bail = [&](int rc) { dpdf_destroy(h); return rc; };
+
+  const float* payload = nullptr;
+  size_t payload_floats = 0;
+  if (int rc = parse_blob(e, weights, nbytes, &payload, &payload_floats)) return bail(rc);
+  e.weights_floats = payload_floats;
+  if (cudaMalloc(&e.weights_dev, payload_floats * sizeof(float)) != cudaSuccess) return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(weights) failed"));
+  if (cudaMemcpy(e.weights_dev, payload, payload_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    return bail(fail(DPDF_ERR_CUDA, "weight upload failed"));
+  if (int rc = bind_weights(e)) return bail(rc);
+
+  // band tables
+  {
+    std::vector<int> aux(33 + d.F);
+    std::vector<float> invw(32);
+    int k = 0;
+    for (int b = 0; b < 32; ++b) {
+      aux[b] = k;
+      for (int i = 0; i < spec->erb_widths[b]; ++i) aux[33 + k + i] = b;
+      k += spec->erb_widths[b];
+      invw[b] = (float)(1.0 / spec->erb_widths[b]);
+    }
+    aux[32] = k;
+    float* invw_dev = nullptr;
+    if (cudaMalloc(&e.aux_int, aux.size() * sizeof(int) + 32 * sizeof(float)) != cudaSuccess) return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(aux) failed"));
+    invw_dev = reinterpret_cast<float*>(e.aux_int + aux.size());
+    cudaMemcpy(e.aux_int, aux.data(), aux.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(invw_dev, invw.data(), 32 * sizeof(float), cudaMemcpyHostToDevice);
+    e.w.band_start = e.aux_int;
+    e.w.band_of_bin = e.aux_int + 33;
+    e.w.band_inv_w = invw_dev;
+  }
+
+  // arena: state + scratch, 256-byte aligned sub-allocations
+  {
+    const size_t Bm = max_streams;
+    std::vector<std::pair<float**, size_t>> items;
+    State& s = e.st;
+    Scratch& c = e.sc;
+    auto add = [&](float*& ptr, size_t per) { items.push_back({&ptr, per * Bm}); };
+    add(s.mu, d.fe_feat); add(s.s, NDF); add(s.erb_ring, 3 * d.fe_feat); add(s.df_ring, 3 * 2 * NDF);
+    add(s.inter_erb, (size_t)std::max(d.N, 1) * d.fe[3] * C); add(s.inter_df, (size_t)std::max(d.N, 1) * (NDF / 2) * C);
+    add(s.h_enc, H); add(s.h_erb, 2 * H); add(s.h_df, 2 * H);
+    add(s.c0_ring, (size_t)ORD * NDF * C); add(s.mask_ring, 3 * d.F * 2); add(s.coef_ring, 3 * NDF * 2 * ORD);
+    add(s.dfspec_ring, (size_t)ORD * d.F * 2); add(s.in_hist, d.hop); add(s.ola, d.hop);
+    add(c.e0, (size_t)d.fe[0] * C); add(c.e1, (size_t)d.fe[1] * C); add(c.e2, (size_t)d.fe[2] * C); add(c.e3, (size_t)d.fe[3] * C);
+    add(c.c0, NDF * C); add(c.c1, (NDF / 2) * C); add(c.xe, (size_t)d.fe[3] * C);
+    add(c.hcat_e, (size_t)d.fe[3] * 2 * C); add(c.hcat_d, (NDF / 2) * 2 * C);
+    add(c.emb_e, 512); add(c.cemb, 512); add(c.g0, H); add(c.henc, H); add(c.emb, 512);
+    add(c.x1, H); add(c.herb1, H); add(c.herb2, H); add(c.ed, 512); add(c.ed2, (size_t)d.fe[3] * C);
+    add(c.x2, H); add(c.hdf1, H); add(c.hdf2, H); add(c.cc, H); add(c.co, NDF * 2 * ORD);
+    add(c.d3, (size_t)d.fe[2] * C); add(c.d2, (size_t)d.fe[1] * C); add(c.d1, (size_t)d.fe[0] * C); add(c.m, d.fe[0]);
+    size_t total = 0;
+    for (auto& it : items) total += (it.second * sizeof(float) + 255) / 256 * 256;
+    total += (Bm * sizeof(int) + 255) / 256 * 256;
+    e.arena_bytes = total;
+    if (cudaMalloc(&e.arena, total) != cudaSuccess)
+      return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(%zu MB) for %d streams failed", total >> 20, max_streams));
+    cudaMemset(e.arena, 0, total);
+    char* cur = static_cast<char*>(e.arena);
+    for (auto& it : items) {
+      *it.first = reinterpret_cast<float*>(cur);
+      cur += (it.second * sizeof(float) + 255) / 256 * 256;
+    }
+    s.pos = reinterpret_cast<int*>(cur);
+  }
+  if (cudaMalloc(&e.io_dev, sizeof(IoDesc)) != cudaSuccess || cudaMalloc(&e.slots_dev, max_streams * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&e.flags_dev, max_streams * sizeof(int)) != cudaSuccess)
+    return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(io) failed"));
+  if (cudaStreamCreateWithFlags(&e.own_stream, cudaStreamDefault) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "stream creation failed"));
+  init_frontend_kernels();
+  init_conv_kernels();
+  init_dprnn_kernels();
+  init_dense_kernels();
+  launch_reset(e, nullptr, max_streams, e.own_stream);
+  if (cudaStreamSynchronize(e.own_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    return bail(fail(DPDF_ERR_CUDA, "engine initialisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
+  *out = h;
+  return 0;
+}
+
+extern "C" int dpdf_destroy(dpdf_engine* h) {
+  if (!h) return 0;
+  Engine& e = h->e;
+  cudaSetDevice(e.device);
+  cudaDeviceSynchronize();
+  for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+  for (auto ev : e.tev) cudaEventDestroy(ev);
+  cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_dev);
+  cudaFree(e.slots_dev); cudaFree(e.flags_dev); cudaFree(e.stage_in); cudaFree(e.stage_out);
+  if (e.pinned) cudaFreeHost(e.pinned);
+  if (e.own_stream) cudaStreamDestroy(e.own_stream);
+  delete h;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one hop: kernel schedule
+// ---------------------------------------------------------------------------------------------
+namespace dpdf {
+
+#define RUN(name, call)                                           \
+  do {                                                            \
+    if (e.timing) {                                               \
+      cudaEvent_t ev0, ev1;                                       \
+      cudaEventCreate(&ev0); cudaEventCreate(&ev1);               \
+      cudaEventRecord(ev0, st);                                   \
+      call;                                                       \
+      cudaEventRecord(ev1, st);                                   \
+      e.tev.push_back(ev0); e.tev.push_back(ev1);                 \
+      e.tnames.push_back(name);                                   \
+    } else {                                                      \
+      call;                                                       \
+    }                                                             \
+  } while (0)
+
+void enqueue_step(Engine& e, int B, cudaStream_t st) {
+  const Dims& d = e.d;
+  const Weights& w = e.w;
+  Scratch& c = e.sc;
+  int n = 0;
+  RUN("analysis", launch_analysis(e, B, st)); ++n;
+  RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
+  auto sepp = [&](const SepW& sw, const float* in1, const float* in2, int pidx, float* out, int Fin, int Fout, int stride, int up) {
+    SepProblem q{};
+    q.mode = 0; q.in1 = in1; q.in2 = in2;
+    q.pa = in2 ? w.convp_a[pidx] : nullptr; q.pb = in2 ? w.convp_b[pidx] : nullptr;
+    q.dw = sw.dw; q.pw = sw.pw; q.bias = sw.b; q.out = out; q.Fin = Fin; q.Fout = Fout; q.stride = stride; q.up = up;
+    return q;
+  };
+  {
+    SepProblem pr[2];
+    pr[0] = SepProblem{};
+    pr[0].mode = 1; pr[0].dw = w.df_conv0_w; pr[0].pw = w.df_conv0_pw; pr[0].bias = w.df_conv0_b;
+    pr[0].Fin = NDF; pr[0].Fout = NDF; pr[0].stride = 1; pr[0].up = 1; pr[0].out = c.c0;
+    pr[1] = sepp(w.erb_conv[0], c.e0, nullptr, 0, c.e1, d.fe[0], d.fe[1], d.stride[0], 1);
+    RUN("sepconv", launch_sepconv(e, pr, 2, B, st)); ++n;
+  }
+  {
+    SepProblem pr[2];
+    pr[0] = sepp(w.df_conv1, c.c0, nullptr, 0, c.c1, NDF, NDF / 2, 2, 1);
+    pr[1] = sepp(w.erb_conv[1], c.e1, nullptr, 0, c.e2, d.fe[1], d.fe[2], d.stride[1], 1);
+    RUN("sepconv", launch_sepconv(e, pr, 2, B, st)); ++n;
+    pr[0] = sepp(w.erb_conv[2], c.e2, nullptr, 0, c.e3, d.fe[2], d.fe[3], d.stride[2], 1);
+    RUN("sepconv", launch_sepconv(e, pr, 1, B, st)); ++n;
+  }
+  for (int i = 0; i < d.N; ++i) {
+    RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); ++n;
+    RUN("dprnn_post", launch_dprnn_post(e, i, B, st)); ++n;
+  }
+  const float* xe_final = d.N > 0 ? c.xe : c.e3;
+  auto glp = [&](const GLW& gw, const float* in0, int ld0, float* out, int ldo, int act) {
+    GLProblem q{};
+    q.in0 = in0; q.ld0 = ld0; q.in1 = nullptr; q.ld1 = 0; q.split = 1 << 30; q.w = gw; q.out = out; q.ldo = ldo; q.col0 = 0;
+    q.addend = nullptr; q.lda = 0; q.act = act;
+    return q;
+  };
+  {
+    GLProblem pr[2];
+    int np = 0;
+    pr[np++] = glp(w.df_fc_emb, c.c1, (NDF / 2) * C, c.cemb, 512, 1);
+    if (d.hr48) pr[np++] = glp(w.erb_fc_emb, xe_final, d.fe[3] * C, c.emb_e, 512, 1);
+    RUN("gl", launch_gl(e, pr, np, B, st)); ++n;
+  }
+  {
+    GLProblem q = glp(w.enc_in, d.hr48 ? c.emb_e : xe_final, 512, c.g0, H, 1);
+    q.in1 = c.cemb; q.ld1 = 512; q.split = 512;
+    RUN("gl", launch_gl(e, &q, 1, B, st)); ++n;
+  }
+  {
+    GRUProblem g{c.g0, e.st.h_enc, H, w.enc_gru, c.henc};
+    RUN("gru", launch_gru(e, &g, 1, B, st)); n += 2;
+  }
+  {
+    GLProblem q = glp(w.enc_out, c.henc, H, c.emb, 512, 1);
+    RUN("gl", launch_gl(e, &q, 1, B, st)); ++n;
+  }
+  {
+    GLProblem pr[2] = {glp(w.erbdec_in, c.emb, 512, c.x1, H, 1), glp(w.dfdec_in, c.emb, 512, c.x2, H, 1)};
+    RUN("gl", launch_gl(e, pr, 2, B, st)); ++n;
+  }
+  {
+    GRUProblem g[2] = {{c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1}};
+    RUN("gru", launch_gru(e, g, 2, B, st)); n += 3;
+    GRUProblem g2[2] = {{c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
+    RUN("gru", launch_gru(e, g2, 2, B, st)); n += 3;
+  }
+  {
+    GLProblem pr[2] = {glp(w.erbdec_out, c.herb2, H, c.ed, 512, 1), glp(w.df_skip, c.emb, 512, c.cc, H, 0)};
+    pr[1].addend = c.hdf2; pr[1].lda = H;
+    RUN("gl", launch_gl(e, pr, 2, B, st)); ++n;
+  }
+  {
+    GLProblem pr[2];
+    int np = 0;
+    pr[np++] = glp(w.df_out, c.cc, H, c.co, NDF * 2 * ORD, 2);
+    if (d.hr48) pr[np++] = glp(w.erbdec_fc, c.ed, 512, c.ed2, d.fe[3] * C, 1);
+    RUN("gl", launch_gl(e, pr, np, B, st)); ++n;
+  }
+  {
+    const float* edv = d.hr48 ? c.ed2 : c.ed;
+    SepProblem q = sepp(w.convt[0], edv, c.e3, 0, c.d3, d.fe[3], d.fe[3] * d.up[0], 1, d.up[0]);
+    RUN("sepconv", launch_sepconv(e, &q, 1, B, st)); ++n;
+    q = sepp(w.convt[1], c.d3, c.e2, 1, c.d2, d.fe[2], d.fe[2] * d.up[1], 1, d.up[1]);
+    RUN("sepconv", launch_sepconv(e, &q, 1, B, st)); ++n;
+    q = sepp(w.convt[2], c.d2, c.e1, 2, c.d1, d.fe[1], d.fe[1] * d.up[2], 1, d.up[2]);
+    RUN("sepconv", launch_sepconv(e, &q, 1, B, st)); ++n;
+  }
+  RUN("conv0_out", launch_conv0_out(e, B, st)); ++n;
+  RUN("df_pathway", launch_df_pathway(e, B, st)); ++n;
+  RUN("synthesis", launch_synthesis(e, B, st)); ++n;
+  e.launches = n;
+}
+
+}  // namespace dpdf
+
+// ---------------------------------------------------------------------------------------------
+// step entry points
+// ---------------------------------------------------------------------------------------------
+static int check_batch(Engine& e, int B) {
+  if (B <= 0) return fail(DPDF_ERR_INVALID, "B must be positive");
+  if (B > e.max_streams) return fail(DPDF_ERR_INVALID, "B=%d exceeds max_streams=%d", B, e.max_streams);
+  return 0;
+}
+
+// Launch the kernels of one hop on `st`, through a cached CUDA graph when enabled.
+static int run_step(Engine& e, int B, cudaStream_t st) {
+  if (!e.use_graph || e.timing) {
+    enqueue_step(e, B, st);
+    CU(cudaGetLastError());
+    return 0;
+  }
+  auto it = e.graphs.find(B);
+  if (it == e.graphs.end()) {
+    // capture on the engine's own stream: the caller's stream may be the legacy default stream,
+    // which cannot be captured; the instantiated graph is then launched on the caller's stream.
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(e.own_stream, cudaStreamCaptureModeRelaxed));
+    enqueue_step(e, B, e.own_stream);
+    cudaError_t err = cudaStreamEndCapture(e.own_stream, &graph);
+    if (err != cudaSuccess) return fail(DPDF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
+    cudaGraphExec_t exec = nullptr;
+    err = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (err != cudaSuccess) return fail(DPDF_ERR_CUDA, "graph instantiation failed: %s", cudaGetErrorString(err));
+    it = e.graphs.emplace(B, exec).first;
+  }
+  CU(cudaGraphLaunch(it->second, st));
+  return 0;
+}
+
+static int set_io(Engine& e, const float* in, long long in_stride, float* out, long long out_stride,
+                  const int32_t* slot_ids, const int32_t* flags, int mode, cudaStream_t st) {
+  IoDesc io{};
+  io.in = in; io.out = out; io.in_stride = in_stride; io.out_stride = out_stride;
+  io.slot_ids = slot_ids; io.flags = flags; io.t_in = 0; io.t_out = 0; io.mode = mode;
+  CU(cudaMemcpyAsync(e.io_dev, &io, sizeof(io), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+  return 0;
+}
+
+extern "C" int dpdf_step_spec(dpdf_engine* h, const float* spec_in, float* spec_out, const int32_t* slot_ids,
+                              const int32_t* flags, int32_t B, void* cuda_stream) {
+  if (!h || !spec_in || !spec_out) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  CU(cudaSetDevice(e.device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (int rc = set_io(e, spec_in, 0, spec_out, 0, slot_ids, flags, 1, st)) return rc;
+  e.last_B = B;
+  return run_step(e, B, st);
+}
+
+extern "C" int dpdf_run_pcm(dpdf_engine* h, const float* pcm_in, int64_t in_stride, float* pcm_out, int64_t out_stride,
+                            const int32_t* slot_ids, const int32_t* flags, int32_t B, int32_t T, void* cuda_stream) {
+  if (!h || !pcm_in || !pcm_out) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  if (T <= 0) return fail(DPDF_ERR_INVALID, "T must be positive");
+  if (in_stride < (int64_t)T * e.d.hop || out_stride < (int64_t)T * e.d.hop)
+    return fail(DPDF_ERR_INVALID, "row stride smaller than T*hop");
+  CU(cudaSetDevice(e.device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (int rc = set_io(e, pcm_in, in_stride, pcm_out, out_stride, slot_ids, flags, 0, st)) return rc;
+  e.last_B = B;
+  for (int t = 0; t < T; ++t)
+    if (int rc = run_step(e, B, st)) return rc;
+  return 0;
+}
+
+extern "C" int dpdf_step_pcm(dpdf_engine* h, const float* pcm_in, int64_t in_stride, float* pcm_out, int64_t out_stride,
+                             const int32_t* slot_ids, const int32_t* flags, int32_t B, void* cuda_stream) {
+  return dpdf_run_pcm(h, pcm_in, in_stride, pcm_out, out_stride, slot_ids, flags, B, 1, cuda_stream);
+}
+
+extern "C" int dpdf_prime_pcm(dpdf_engine* h, const float* pcm_in, int64_t in_stride, const int32_t* slot_ids, int32_t B,
+                              void* cuda_stream) {
+  if (!h || !pcm_in) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  CU(cudaSetDevice(e.device));
+  launch_prime(e, pcm_in, in_stride, slot_ids, B, static_cast<cudaStream_t>(cuda_stream));
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dpdf_reset(dpdf_engine* h, const int32_t* slots_host, int32_t n, void* cuda_stream) {
+  if (!h) return fail(DPDF_ERR_INVALID, "NULL engine");
+  Engine& e = h->e;
+  CU(cudaSetDevice(e.device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (!slots_host || n <= 0) {
+    launch_reset(e, nullptr, e.max_streams, st);
+  } else {
+    if (n > e.max_streams) return fail(DPDF_ERR_INVALID, "n=%d exceeds max_streams", n);
+    for (int i = 0; i < n; ++i)
+      if (slots_host[i] < 0 || slots_host[i] >= e.max_streams) return fail(DPDF_ERR_INVALID, "slot %d out of range", slots_host[i]);
+    CU(cudaMemcpyAsync(e.slots_dev, slots_host, n * sizeof(int), cudaMemcpyHostToDevice, st));
+    launch_reset(e, e.slots_dev, n, st);
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ---- host-buffer variants ---------------------------------------------------------------------
+static int ensure_stage(Engine& e, size_t in_floats, size_t out_floats) {
+  if (in_floats > e.stage_in_floats) {
+    cudaFree(e.stage_in);
+    e.stage_in = nullptr;
+    if (cudaMalloc(&e.stage_in, in_floats * sizeof(float)) != cudaSuccess) return fail(DPDF_ERR_NOMEM, "staging alloc failed");
+    e.stage_in_floats = in_floats;
+  }
+  if (out_floats > e.stage_out_floats) {
+    cudaFree(e.stage_out);
+    e.stage_out = nullptr;
+    if (cudaMalloc(&e.stage_out, out_floats * sizeof(float)) != cudaSuccess) return fail(DPDF_ERR_NOMEM, "staging alloc failed");
+    e.stage_out_floats = out_floats;
+  }
+  return 0;
+}
+
+static int host_ids(Engine& e, const int32_t* slot_ids, const int32_t* flags, int B, const int32_t** s_dev,
+                    const int32_t** f_dev, cudaStream_t st) {
+  *s_dev = nullptr;
+  *f_dev = nullptr;
+  if (slot_ids) {
+    for (int i = 0; i < B; ++i)
+      if (slot_ids[i] < 0 || slot_ids[i] >= e.max_streams) return fail(DPDF_ERR_INVALID, "slot %d out of range", slot_ids[i]);
+    CU(cudaMemcpyAsync(e.slots_dev, slot_ids, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    *s_dev = e.slots_dev;
+  }
+  if (flags) {
+    CU(cudaMemcpyAsync(e.flags_dev, flags, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    *f_dev = e.flags_dev;
+  }
+  return 0;
+}
+
+extern "C" int dpdf_step_spec_host(dpdf_engine* h, const float* spec_in, float* spec_out, const int32_t* slot_ids,
+                                   const int32_t* flags, int32_t B) {
+  if (!h || !spec_in || !spec_out) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  CU(cudaSetDevice(e.device));
+  const size_t n = (size_t)B * e.d.F * 2;
+  if (int rc = ensure_stage(e, n, n)) return rc;
+  cudaStream_t st = e.own_stream;
+  const int32_t *s_dev, *f_dev;
+  if (int rc = host_ids(e, slot_ids, flags, B, &s_dev, &f_dev, st)) return rc;
+  CU(cudaMemcpyAsync(e.stage_in, spec_in, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = dpdf_step_spec(h, e.stage_in, e.stage_out, s_dev, f_dev, B, st)) return rc;
+  CU(cudaMemcpyAsync(spec_out, e.stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int dpdf_run_pcm_host(dpdf_engine* h, const float* pcm_in, float* pcm_out, const int32_t* slot_ids, int32_t B,
+                                 int32_t T) {
+  if (!h || !pcm_in || !pcm_out) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  if (T <= 0) return fail(DPDF_ERR_INVALID, "T must be positive");
+  CU(cudaSetDevice(e.device));
+  const size_t n = (size_t)B * T * e.d.hop;
+  if (int rc = ensure_stage(e, n, n)) return rc;
+  cudaStream_t st = e.own_stream;
+  const int32_t *s_dev, *f_dev;
+  if (int rc = host_ids(e, slot_ids, nullptr, B, &s_dev, &f_dev, st)) return rc;
+  CU(cudaMemcpyAsync(e.stage_in, pcm_in, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = dpdf_run_pcm(h, e.stage_in, (int64_t)T * e.d.hop, e.stage_out, (int64_t)T * e.d.hop, s_dev, nullptr, B, T, st)) return rc;
+  CU(cudaMemcpyAsync(pcm_out, e.stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int dpdf_step_pcm_host(dpdf_engine* h, const float* pcm_in, float* pcm_out, const int32_t* slot_ids,
+                                  const int32_t* flags, int32_t B) {
+  if (!h || !pcm_in || !pcm_out) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  CU(cudaSetDevice(e.device));
+  const size_t n = (size_t)B * e.d.hop;
+  if (int rc = ensure_stage(e, n, n)) return rc;
+  cudaStream_t st = e.own_stream;
+  const int32_t *s_dev, *f_dev;
+  if (int rc = host_ids(e, slot_ids, flags, B, &s_dev, &f_dev, st)) return rc;
+  CU(cudaMemcpyAsync(e.stage_in, pcm_in, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = dpdf_run_pcm(h, e.stage_in, e.d.hop, e.stage_out, e.d.hop, s_dev, f_dev, B, 1, st)) return rc;
+  CU(cudaMemcpyAsync(pcm_out, e.stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference-layout state (onnx_model/dpdfnet.py:737-746)
+// ---------------------------------------------------------------------------------------------
+extern "C" int dpdf_state_size(const dpdf_engine* h) { return h ? h->e.spec.state_size : 0; }
+
+namespace {
+struct Seg { float* base; size_t per; };
+}
+
+static int fetch(Engine& e, const float* base, size_t per, int slot, std::vector<float>& out) {
+  out.resize(per);
+  CU(cudaMemcpy(out.data(), base + (size_t)slot * per, per * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+static int store(Engine& e, float* base, size_t per, int slot, const std::vector<float>& in) {
+  CU(cudaMemcpy(base + (size_t)slot * per, in.data(), per * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int dpdf_state_export(dpdf_engine* h, int32_t slot, float* flat) {
+  if (!h || !flat) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (slot < 0 || slot >= e.max_streams) return fail(DPDF_ERR_INVALID, "slot %d out of range", slot);
+  CU(cudaSetDevice(e.device));
+  CU(cudaDeviceSynchronize());
+  const Dims& d = e.d;
+  int pos = 0;
+  CU(cudaMemcpy(&pos, e.st.pos + slot, sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<float> buf;
+  float* o = flat;
+  auto plain = [&](const float* base, size_t per) -> int {
+    if (int rc = fetch(e, base, per, slot, buf)) return rc;
+    memcpy(o, buf.data(), per * sizeof(float));
+    o += per;
+    return 0;
+  };
+  // ring with L frames of `frame` floats: logical frame k (oldest first) = physical (pos + k) % L
+  auto ring = [&](const float* base, int L, size_t frame) -> int {
+    if (int rc = fetch(e, base, L * frame, slot, buf)) return rc;
+    for (int k = 0; k < L; ++k) memcpy(o + k * frame, buf.data() + ((pos + k) % L) * frame, frame * sizeof(float));
+    o += L * frame;
+    return 0;
+  };
+  int rc = 0;
+  if ((rc = plain(e.st.mu, d.fe_feat))) return rc;
+  if ((rc = plain(e.st.s, NDF))) return rc;
+  if ((rc = ring(e.st.erb_ring, 3, d.fe_feat))) return rc;
+  if (d.N > 0 && (rc = plain(e.st.inter_erb, (size_t)d.N * d.fe[3] * C))) return rc;
+  if ((rc = ring(e.st.df_ring, 3, 2 * NDF))) return rc;
+  if (d.N > 0 && (rc = plain(e.st.inter_df, (size_t)d.N * (NDF / 2) * C))) return rc;
+  if ((rc = plain(e.st.h_enc, H))) return rc;
+  if ((rc = plain(e.st.h_erb, 2 * H))) return rc;
+  if ((rc = plain(e.st.h_df, 2 * H))) return rc;
+  {   // c0 ring: engine [5][96][64] -> reference [5][64][96]
+    if ((rc = fetch(e, e.st.c0_ring, (size_t)ORD * NDF * C, slot, buf))) return rc;
+    for (int k = 0; k < ORD; ++k) {
+      const float* src = buf.data() + (size_t)((pos + k) % ORD) * NDF * C;
+      for (int c = 0; c < C; ++c)
+        for (int f = 0; f < NDF; ++f) o[((size_t)k * C + c) * NDF + f] = src[f * C + c];
+    }
+    o += (size_t)ORD * NDF * C;
+  }
+  if ((rc = ring(e.st.mask_ring, 3, (size_t)d.F * 2))) return rc;
+  {   // coef ring: engine [3][96][5][2] -> reference [3][5][96][2]
+    if ((rc = fetch(e, e.st.coef_ring, (size_t)3 * NDF * 2 * ORD, slot, buf))) return rc;
+    for (int k = 0; k < 3; ++k) {
+      const float* src = buf.data() + (size_t)((pos + k) % 3) * NDF * 2 * ORD;
+      for (int n = 0; n < ORD; ++n)
+        for (int f = 0; f < NDF; ++f)
+          for (int r = 0; r < 2; ++r) o[(((size_t)k * ORD + n) * NDF + f) * 2 + r] = src[(f * ORD + n) * 2 + r];
+    }
+    o += (size_t)3 * NDF * 2 * ORD;
+  }
+  if ((rc = ring(e.st.dfspec_ring, ORD, (size_t)d.F * 2))) return rc;
+  if ((o - flat) != e.spec.state_size) return fail(DPDF_ERR_INVALID, "internal: exported %ld floats, expected %d", (long)(o - flat), e.spec.state_size);
+  return 0;
+}
+
+extern "C" int dpdf_state_import(dpdf_engine* h, int32_t slot, const float* flat) {
+  if (!h || !flat) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (slot < 0 || slot >= e.max_streams) return fail(DPDF_ERR_INVALID, "slot %d out of range", slot);
+  CU(cudaSetDevice(e.device));
+  CU(cudaDeviceSynchronize());
+  const Dims& d = e.d;
+  const float* o = flat;
+  std::vector<float> buf;
+  int rc = 0;
+  auto plain = [&](float* base, size_t per) -> int {
+    buf.assign(o, o + per);
+    o += per;
+    return store(e, base, per, slot, buf);
+  };
+  if ((rc = plain(e.st.mu, d.fe_feat))) return rc;
+  if ((rc = plain(e.st.s, NDF))) return rc;
+  if ((rc = plain(e.st.erb_ring, 3 * d.fe_feat))) return rc;            // pos := 0 => logical == physical
+  if (d.N > 0 && (rc = plain(e.st.inter_erb, (size_t)d.N * d.fe[3] * C))) return rc;
+  if ((rc = plain(e.st.df_ring, 3 * 2 * NDF))) return rc;
+  if (d.N > 0 && (rc = plain(e.st.inter_df, (size_t)d.N * (NDF / 2) * C))) return rc;
+  if ((rc = plain(e.st.h_enc, H))) return rc;
+  if ((rc = plain(e.st.h_erb, 2 * H))) return rc;
+  if ((rc = plain(e.st.h_df, 2 * H))) return rc;
+  {
+    buf.resize((size_t)ORD * NDF * C);
+    for (int k = 0; k < ORD; ++k)
+      for (int c = 0; c < C; ++c)
+        for (int f = 0; f < NDF; ++f) buf[((size_t)k * NDF + f) * C + c] = o[((size_t)k * C + c) * NDF + f];
+    o += buf.size();
+    if ((rc = store(e, e.st.c0_ring, buf.size(), slot, buf))) return rc;
+  }
+  if ((rc = plain(e.st.mask_ring, (size_t)3 * d.F * 2))) return rc;
+  {
+    buf.resize((size_t)3 * NDF * 2 * ORD);
+    for (int k = 0; k < 3; ++k)
+      for (int n = 0; n < ORD; ++n)
+        for (int f = 0; f < NDF; ++f)
+          for (int r = 0; r < 2; ++r) buf[(((size_t)k * NDF + f) * ORD + n) * 2 + r] = o[(((size_t)k * ORD + n) * NDF + f) * 2 + r];
+    o += buf.size();
+    if ((rc = store(e, e.st.coef_ring, buf.size(), slot, buf))) return rc;
+  }
+  if ((rc = plain(e.st.dfspec_ring, (size_t)ORD * d.F * 2))) return rc;
+  const int zero = 0;
+  CU(cudaMemcpy(e.st.pos + slot, &zero, sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+extern "C" int dpdf_debug_tensor(dpdf_engine* h, const char* name, float* out, size_t max_floats, size_t* numel) {
+  if (!h || !name) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  const Dims& d = e.d;
+  const Scratch& c = e.sc;
+  struct Ent { const char* n; const float* p; size_t per; };
+  const Ent table[] = {
+      {"e0", c.e0, (size_t)d.fe[0] * C}, {"e1", c.e1, (size_t)d.fe[1] * C}, {"e2", c.e2, (size_t)d.fe[2] * C},
+      {"e3", c.e3, (size_t)d.fe[3] * C}, {"c0", c.c0, (size_t)NDF * C}, {"xd", c.c1, (size_t)(NDF / 2) * C},
+      {"xe", c.xe, (size_t)d.fe[3] * C}, {"hcat_e", c.hcat_e, (size_t)d.fe[3] * 2 * C}, {"hcat_d", c.hcat_d, (size_t)(NDF / 2) * 2 * C},
+      {"cemb", c.cemb, 512}, {"emb", c.emb, 512}, {"ed", d.hr48 ? c.ed2 : c.ed, d.hr48 ? (size_t)d.fe[3] * C : 512},
+      {"d3", c.d3, (size_t)d.fe[2] * C}, {"d2", c.d2, (size_t)d.fe[1] * C}, {"d1", c.d1, (size_t)d.fe[0] * C},
+      {"m", c.m, (size_t)d.fe[0]}, {"co", c.co, (size_t)NDF * 2 * ORD}, {"g0", c.g0, H}, {"henc", c.henc, H},
+      {"hdf2", c.hdf2, H}, {"herb2", c.herb2, H}, {"cc", c.cc, H}};
+  for (const Ent& t : table) {
+    if (strcmp(t.n, name) == 0) {
+      if (numel) *numel = t.per;
+      if (out) {
+        const size_t n = t.per * (size_t)e.last_B;
+        if (n > max_floats) return fail(DPDF_ERR_INVALID, "buffer too small for %s: need %zu floats", name, n);
+        CU(cudaSetDevice(e.device));
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(out, t.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+      }
+      return 0;
+    }
+  }
+  return fail(DPDF_ERR_INVALID, "unknown debug tensor '%s'", name);
+}
+
+extern "C" int dpdf_kernel_launches(const dpdf_engine* h) { return h ? h->e.launches : 0; }
+
+extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
+  if (!h || !key) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (strcmp(key, "graph") == 0) e.use_graph = value ? 1 : 0;
+  else if (strcmp(key, "intra_bt") == 0) {
+    if (value != 0 && value != 8 && value != 16 && value != 32) return fail(DPDF_ERR_INVALID, "intra_bt must be 0, 8, 16 or 32");
+    e.intra_bt = value;
+    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+    e.graphs.clear();
+  } else return fail(DPDF_ERR_INVALID, "unknown option '%s'", key);
+  return 0;
+}
+
+// Per-kernel device time of a hop at batch B: runs `iters` un-graphed hops on the engine's staging
+// buffers with a CUDA-event pair around every launch.  Advances the state of slots 0..B-1.
+extern "C" int dpdf_time_kernels(dpdf_engine* h, int32_t B, int32_t iters, float* ms_out, const char** names_out,
+                                 int32_t max_entries, int32_t* n_entries) {
+  if (!h || !ms_out || !names_out || !n_entries) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  CU(cudaSetDevice(e.device));
+  const size_t n = (size_t)B * e.d.hop;
+  if (int rc = ensure_stage(e, n, n)) return rc;
+  cudaStream_t st = e.own_stream;
+  CU(cudaMemsetAsync(e.stage_in, 0, n * sizeof(float), st));
+  if (int rc = set_io(e, e.stage_in, e.d.hop, e.stage_out, e.d.hop, nullptr, nullptr, 0, st)) return rc;
+  static std::vector<std::string> keep;     // storage for the returned names
+  std::vector<double> acc;
+  keep.clear();
+  e.last_B = B;
+  for (int it = 0; it < iters + 1; ++it) {
+    if (int rc = set_io(e, e.stage_in, e.d.hop, e.stage_out, e.d.hop, nullptr, nullptr, 0, st)) return rc;
+    e.timing = true;
+    e.tev.clear();
+    e.tnames.clear();
+    enqueue_step(e, B, st);
+    e.timing = false;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    if (acc.empty()) { acc.assign(e.tnames.size(), 0.0); keep = e.tnames; }
+    for (size_t i = 0; i < e.tnames.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e.tev[2 * i], e.tev[2 * i + 1]);
+      if (it > 0) acc[i] += ms;         // first iteration is warm-up
+      cudaEventDestroy(e.tev[2 * i]);
+      cudaEventDestroy(e.tev[2 * i + 1]);
+    }
+    e.tev.clear();
+  }
+  const int cnt = (int)std::min<size_t>(keep.size(), (size_t)max_entries);
+  for (int i = 0; i < cnt; ++i) {
+    ms_out[i] = (float)(acc[i] / std::max(1, iters));
+    names_out[i] = keep[i].c_str();
+  }
+  *n_entries = cnt;
+  return 0;
+}

@@ -1,0 +1,168 @@
+// Engine-internal structures shared by the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dpdfnet_b200.h"
+#include "common.cuh"
+
+namespace dpdf {
+
+// ---- device views ---------------------------------------------------------------------------
+struct Dims {
+  int win, hop, F;        // window, hop, frequency bins
+  int fe_feat;            // 32 | 481
+  int fe[4];              // widths of e0..e3
+  int stride[3];          // erb_conv1..3
+  int up[3];              // convt3, convt2, convt1
+  int N;                  // DPRNN blocks
+  int hr48;
+  float wnorm, inv_wnorm;
+};
+
+struct State {           // all [max_streams][...], float unless noted
+  float* mu;             // [fe_feat]
+  float* s;              // [96]
+  float* erb_ring;       // [3][fe_feat]
+  float* df_ring;        // [3][2][96]
+  float* inter_erb;      // [N][fe3][64]
+  float* inter_df;       // [N][48][64]
+  float* h_enc;          // [256]
+  float* h_erb;          // [2][256]
+  float* h_df;           // [2][256]
+  float* c0_ring;        // [5][96][64]
+  float* mask_ring;      // [3][F][2]
+  float* coef_ring;      // [3][96][10]
+  float* dfspec_ring;    // [5][F][2]
+  float* in_hist;        // [hop]
+  float* ola;            // [hop]
+  int* pos;              // frames pushed so far
+};
+
+struct Scratch {         // all [max_streams][...]
+  float *e0, *e1, *e2, *e3, *c0, *c1, *xe;
+  float *hcat_e, *hcat_d;
+  float *emb_e, *cemb, *g0, *henc, *emb;
+  float *x1, *herb1, *herb2, *ed, *ed2;
+  float *x2, *hdf1, *hdf2, *cc, *co;
+  float *d3, *d2, *d1, *m;
+};
+
+struct SepW { const float *dw, *pw, *b; };
+struct GLW { const float *w, *b; int G, Ng, Kg; };
+struct GRUW { const float *wih, *whh, *bias; };
+struct DprnnW {
+  const float *i_wih, *i_whh, *i_bias, *fc_w, *fc_b, *ln_g, *ln_b;
+  const float *r_wih, *r_whh, *r_bias, *fc2_w, *fc2_b, *ln2_g, *ln2_b;
+};
+
+struct Weights {
+  const float *dft_fwd, *dft_inv, *mu0, *s0;
+  const float *erb_conv0_w, *erb_conv0_b;
+  SepW erb_conv[3], df_conv1, convt[3];
+  const float *df_conv0_w, *df_conv0_pw, *df_conv0_b;
+  std::vector<DprnnW> dprnn_erb, dprnn_df;
+  GLW erb_fc_emb, df_fc_emb, enc_in, enc_out, erbdec_in, erbdec_out, erbdec_fc, dfdec_in, df_skip, df_out;
+  GRUW enc_gru, erb_gru[2], df_gru[2];
+  const float *convp_a[4], *convp_b[4];      // conv3p, conv2p, conv1p, conv0p
+  const float *conv0_out_w, *conv0_out_b;
+  const float *dfp_w, *dfp_pw, *dfp_b;
+  const float* band_inv_w;                   // [32] 1/width
+  const int* band_start;                     // [33]
+  const int* band_of_bin;                    // [F]
+};
+
+// ---- kernel launchers (defined in k_*.cu) ---------------------------------------------------
+struct Engine;
+
+void launch_prime(Engine& e, const float* pcm, long long stride, const int* slot_ids, int B, cudaStream_t st);
+void launch_analysis(Engine& e, int B, cudaStream_t st);
+void launch_synthesis(Engine& e, int B, cudaStream_t st);
+void launch_reset(Engine& e, const int* slots_dev, int n, cudaStream_t st);
+
+void launch_erb_conv0(Engine& e, int B, cudaStream_t st);
+
+struct SepProblem {
+  int mode;                 // 0: depthwise(+pathway) prologue, 1: df_conv0 grouped 3x3 from the df ring
+  const float* in1;         // [B][Fin][64]
+  const float* in2;         // pathway source [B][Fin][64] or nullptr
+  const float *pa, *pb;     // pathway affine
+  const float *dw, *pw, *bias;
+  float* out;               // [B][Fout][64]  (mode 1: c0 ring slot)
+  int Fin, Fout, stride, up;
+  int tile0;                // first tile index of this problem in the launch
+};
+void launch_sepconv(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st);
+void launch_conv0_out(Engine& e, int B, cudaStream_t st);
+void launch_df_pathway(Engine& e, int B, cudaStream_t st);
+
+void launch_dprnn_intra(Engine& e, int blk, int B, cudaStream_t st);
+void launch_dprnn_post(Engine& e, int blk, int B, cudaStream_t st);
+
+struct GLProblem {
+  const float* in0; int ld0;     // input columns [0, split)
+  const float* in1; int ld1;     // input columns [split, ...) (may be nullptr)
+  int split;
+  GLW w;
+  float* out; int ldo; int col0; // output written at out[b*ldo + col0 + ...]
+  const float* addend; int lda;  // optional: y += addend[b*lda + col]
+  int act;                       // 0 none, 1 relu, 2 tanh
+};
+void launch_gl(Engine& e, const GLProblem* probs, int nprob, int B, cudaStream_t st);
+
+struct GRUProblem {
+  const float* x;   // [B][256]
+  float* hstate;    // [max_streams][hs_stride] slot-indexed
+  int hs_stride;
+  GRUW w;
+  float* hout;      // [B][256]
+};
+void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st);
+
+// ---- the engine -----------------------------------------------------------------------------
+struct Engine {
+  dpdf_spec spec;
+  Dims d;
+  int device = 0;
+  int max_streams = 0;
+  int num_sms = 148;
+  float* weights_dev = nullptr;
+  size_t weights_floats = 0;
+  std::map<std::string, std::pair<size_t, size_t>> wtable;   // name -> (offset, numel)
+  Weights w;
+  State st;
+  Scratch sc;
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  int* aux_int = nullptr;         // band tables
+  IoDesc* io_dev = nullptr;
+  IoDesc* io_host = nullptr;      // pinned
+  int* slots_dev = nullptr;       // staging for host slot ids / flags
+  int* flags_dev = nullptr;
+  float* stage_in = nullptr;      // device staging for *_host entry points
+  float* stage_out = nullptr;
+  size_t stage_in_floats = 0, stage_out_floats = 0;
+  float* pinned = nullptr;        // pinned host staging
+  size_t pinned_floats = 0;
+  cudaStream_t own_stream = nullptr;
+  int last_B = 0;
+  int launches = 0;               // kernels launched by the last step
+  int use_graph = 1;
+  int intra_bt = 0;               // 0 = auto
+  std::map<int, cudaGraphExec_t> graphs;     // keyed by B
+  std::vector<std::pair<std::string, float>> ktimes;
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;
+  std::vector<std::string> tnames;
+};
+
+void init_frontend_kernels();
+void init_conv_kernels();
+void init_dprnn_kernels();
+void init_dense_kernels();
+void enqueue_step(Engine& e, int B, cudaStream_t st);    // all kernels of one hop, in order
+
+}  // namespace dpdf

@@ -1,0 +1,285 @@
+// Convolutional stages (a5, conv parts of a9 and a10).
+//   k_erb_conv0  : 3x3 conv 1->64 over the 3-frame feature ring + BN + ReLU   (onnx_model/dpdfnet.py:206-211)
+//   k_sepconv    : [depthwise 1x3 (stride / sub-pixel) | grouped 3x3 from the df ring] prologue feeding a
+//                  64x64 pointwise GEMM tile + BN + ReLU; also fuses the decoder "pathway" adds
+//                  (layers.py:761-834, 895-973; onnx_model/dpdfnet.py:212-227, 361-363)
+//   k_conv0_out  : pathway add + 64->1 1x3 conv + BN + sigmoid -> ERB / per-bin gains (:364)
+//   k_df_pathway : 5-frame c0 ring -> grouped (2 x 32->5, 5x1) + pointwise 10x10 + BN + ReLU, added to the
+//                  tanh'd df_out coefficients and pushed into the coefficient ring (:503-515)
+#include "engine.h"
+
+namespace dpdf {
+
+// ---------------------------------------------------------------------------------------------
+struct Conv0Params {
+  IoDesc* io;
+  State st;
+  const float *w, *bias;   // [9][64], [64]
+  float* e0;               // [B][fe0][64]
+  int fe0, fe_feat, B;
+};
+
+__global__ void __launch_bounds__(256) k_erb_conv0(Conv0Params p) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {      // hop counter tick (see IoDesc)
+    p.io->t_out = p.io->t_in;
+    p.io->t_in = p.io->t_in + 1;
+  }
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.B * p.fe0 * C;
+  if (idx >= total) return;
+  const int c = idx % C;
+  const int f = (idx / C) % p.fe0;
+  const int b = idx / ((long long)C * p.fe0);
+  const int slot = io_slot(p.io, b);
+  const int pos = p.st.pos[slot];
+  const float* ring = p.st.erb_ring + (size_t)slot * 3 * p.fe_feat;
+  float acc = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 3; ++kt) {
+    const float* row = ring + ((pos + 1 + kt) % 3) * p.fe_feat;
+#pragma unroll
+    for (int kf = 0; kf < 3; ++kf) {
+      const int fi = f + kf - 1;
+      const float x = (fi >= 0 && fi < p.fe0) ? row[fi] : 0.f;
+      acc = fmaf(__ldg(p.w + (kt * 3 + kf) * C + c), x, acc);
+    }
+  }
+  p.e0[idx] = fmaxf(acc + __ldg(p.bias + c), 0.f);
+}
+
+void launch_erb_conv0(Engine& e, int B, cudaStream_t st) {
+  Conv0Params p{e.io_dev, e.st, e.w.erb_conv0_w, e.w.erb_conv0_b, e.sc.e0, e.d.fe[0], e.d.fe_feat, B};
+  const long long total = (long long)B * e.d.fe[0] * C;
+  k_erb_conv0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int SEP_MAXP = 4;
+constexpr int SEP_LD = 68;
+struct SepParams {
+  const IoDesc* io;
+  State st;
+  SepProblem prob[SEP_MAXP];
+  int nprob, B;
+};
+constexpr size_t SEP_SMEM = (size_t)(128 * SEP_LD + 64 * SEP_LD + 64) * sizeof(float);
+
+__global__ void __launch_bounds__(256, 1) k_sepconv(SepParams p) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                    // [128][68]
+  float* Ws = As + 128 * SEP_LD;       // [64][68]
+  float* bs = Ws + 64 * SEP_LD;        // [64]
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < SEP_MAXP; ++i)
+    if (i < p.nprob && (int)blockIdx.x >= p.prob[i].tile0) pi = i;
+  const SepProblem& q = p.prob[pi];
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)(blockIdx.x - q.tile0) * 128;
+  const long long nrows = (long long)p.B * q.Fout;
+
+  // pointwise weights + bias -> smem (async)
+  for (int i = tid; i < 64 * 16; i += 256) cp_async16(Ws + (i >> 4) * SEP_LD + (i & 15) * 4, q.pw + (i >> 4) * 64 + (i & 15) * 4);
+  if (tid < 16) cp_async16(bs + tid * 4, q.bias + tid * 4);
+  cp_async_commit();
+
+  // prologue: A[row][c]
+  for (int it = tid; it < 128 * 16; it += 256) {
+    const int r = it >> 4, c = (it & 15) * 4;
+    const long long row = row0 + r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows) {
+      const int b = (int)(row / q.Fout), fo = (int)(row % q.Fout);
+      if (q.mode == 0) {
+        int fc, j;
+        if (q.up > 1) { fc = fo / q.up; j = fo % q.up; } else { fc = fo * q.stride; j = 0; }
+        const float* in1 = q.in1 + (size_t)b * q.Fin * C;
+        const float* in2 = q.in2 ? q.in2 + (size_t)b * q.Fin * C : nullptr;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const int fi = fc + t - 1;
+          if (fi < 0 || fi >= q.Fin) continue;
+          float4 v = __ldg(reinterpret_cast<const float4*>(in1 + (size_t)fi * C + c));
+          if (in2) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(in2 + (size_t)fi * C + c));
+            const float4 a = __ldg(reinterpret_cast<const float4*>(q.pa + c));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(q.pb + c));
+            v.x += fmaxf(fmaf(u.x, a.x, bb.x), 0.f);
+            v.y += fmaxf(fmaf(u.y, a.y, bb.y), 0.f);
+            v.z += fmaxf(fmaf(u.z, a.z, bb.z), 0.f);
+            v.w += fmaxf(fmaf(u.w, a.w, bb.w), 0.f);
+          }
+          const float4 w = __ldg(reinterpret_cast<const float4*>(q.dw + (size_t)(j * 3 + t) * C + c));
+          acc.x = fmaf(w.x, v.x, acc.x);
+          acc.y = fmaf(w.y, v.y, acc.y);
+          acc.z = fmaf(w.z, v.z, acc.z);
+          acc.w = fmaf(w.w, v.w, acc.w);
+        }
+      } else {
+        const int slot = io_slot(p.io, b);
+        const int pos = p.st.pos[slot];
+        const float* ring = p.st.df_ring + (size_t)slot * 3 * 2 * NDF;
+        const int plane = c >= 32 ? 1 : 0;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          const float* rowp = ring + (((pos + 1 + kt) % 3) * 2 + plane) * NDF;
+#pragma unroll
+          for (int kf = 0; kf < 3; ++kf) {
+            const int fi = fo + kf - 1;
+            if (fi < 0 || fi >= NDF) continue;
+            const float x = rowp[fi];
+            const float4 w = __ldg(reinterpret_cast<const float4*>(q.dw + (size_t)(kt * 3 + kf) * C + c));
+            acc.x = fmaf(w.x, x, acc.x);
+            acc.y = fmaf(w.y, x, acc.y);
+            acc.z = fmaf(w.z, x, acc.z);
+            acc.w = fmaf(w.w, x, acc.w);
+          }
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(As + r * SEP_LD + c) = acc;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int tx = tid & 7, ty = tid >> 3;
+  float2 acc[4][8];
+  acc_zero(acc);
+  tile_mac<64, SEP_LD, SEP_LD, 4, 8>(As, Ws, acc, tx, ty);
+  __syncthreads();                          // everyone done reading As
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = tx + 8 * j;
+      As[(ty + 32 * i) * SEP_LD + col] = fmaxf(acc[i][j].x + acc[i][j].y + bs[col], 0.f);
+    }
+  __syncthreads();
+  for (int it = tid; it < 128 * 16; it += 256) {
+    const int r = it >> 4, c = (it & 15) * 4;
+    const long long row = row0 + r;
+    if (row >= nrows) continue;
+    float4 v = *reinterpret_cast<const float4*>(As + r * SEP_LD + c);
+    if (q.mode == 0) {
+      *reinterpret_cast<float4*>(q.out + (size_t)row * C + c) = v;
+    } else {
+      const int b = (int)(row / q.Fout), fo = (int)(row % q.Fout);
+      const int slot = io_slot(p.io, b);
+      const int pos = p.st.pos[slot];
+      *reinterpret_cast<float4*>(q.out + (size_t)row * C + c) = v;      // c0 for df_conv1 (this hop)
+      if (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(p.st.c0_ring + (((size_t)slot * ORD + pos % ORD) * NDF + fo) * C + c) = v;
+    }
+  }
+}
+
+void launch_sepconv(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st) {
+  SepParams p{};
+  p.io = e.io_dev;
+  p.st = e.st;
+  p.nprob = nprob;
+  p.B = B;
+  int tiles = 0;
+  for (int i = 0; i < nprob; ++i) {
+    p.prob[i] = probs[i];
+    p.prob[i].tile0 = tiles;
+    tiles += (int)(((long long)B * probs[i].Fout + 127) / 128);
+  }
+  k_sepconv<<<tiles, 256, SEP_SMEM, st>>>(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Conv0OutParams {
+  const float *e0, *d1, *pa, *pb, *w, *bias;   // w [3][64]
+  float* m;
+  int fe0, B;
+};
+
+__global__ void __launch_bounds__(256) k_conv0_out(Conv0OutParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.B * p.fe0) return;
+  const int b = warp / p.fe0, f = warp % p.fe0;
+  const float2 a = __ldg(reinterpret_cast<const float2*>(p.pa) + lane);
+  const float2 pb = __ldg(reinterpret_cast<const float2*>(p.pb) + lane);
+  float acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const int fi = f + t - 1;
+    if (fi < 0 || fi >= p.fe0) continue;
+    const size_t off = ((size_t)b * p.fe0 + fi) * C;
+    const float2 e = __ldg(reinterpret_cast<const float2*>(p.e0 + off) + lane);
+    const float2 d = __ldg(reinterpret_cast<const float2*>(p.d1 + off) + lane);
+    const float2 w = __ldg(reinterpret_cast<const float2*>(p.w + t * C) + lane);
+    const float u0 = fmaxf(fmaf(e.x, a.x, pb.x), 0.f) + d.x;
+    const float u1 = fmaxf(fmaf(e.y, a.y, pb.y), 0.f) + d.y;
+    acc = fmaf(w.x, u0, acc);
+    acc = fmaf(w.y, u1, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) p.m[(size_t)b * p.fe0 + f] = sigmoidf_(acc + __ldg(p.bias));
+}
+
+void launch_conv0_out(Engine& e, int B, cudaStream_t st) {
+  Conv0OutParams p{e.sc.e0, e.sc.d1, e.w.convp_a[3], e.w.convp_b[3], e.w.conv0_out_w, e.w.conv0_out_b, e.sc.m, e.d.fe[0], B};
+  const long long warps = (long long)B * e.d.fe[0];
+  k_conv0_out<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct DfPathParams {
+  const IoDesc* io;
+  State st;
+  const float *w, *pw, *bias;   // [10][5][32], [10][10], [10]
+  const float* co;              // [B][96][10] tanh(df_out)
+  int B;
+};
+
+__global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= p.B * NDF) return;
+  const int b = warp / NDF, f = warp % NDF;
+  const int slot = io_slot(p.io, b);
+  const int pos = p.st.pos[slot];
+  float part[10];
+#pragma unroll
+  for (int o = 0; o < 10; ++o) part[o] = 0.f;
+  const float* ring = p.st.c0_ring + (size_t)slot * ORD * NDF * C;
+#pragma unroll
+  for (int kt = 0; kt < ORD; ++kt) {
+    const float* src = ring + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C;
+    const float v0 = src[lane], v1 = src[32 + lane];
+#pragma unroll
+    for (int o = 0; o < 5; ++o) {
+      part[o] = fmaf(__ldg(p.w + (o * ORD + kt) * 32 + lane), v0, part[o]);
+      part[5 + o] = fmaf(__ldg(p.w + ((5 + o) * ORD + kt) * 32 + lane), v1, part[5 + o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 10; ++o)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) part[o] += __shfl_xor_sync(0xffffffffu, part[o], s);
+  if (lane < 10) {
+    float u = __ldg(p.bias + lane);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) u = fmaf(__ldg(p.pw + lane * 10 + i), part[i], u);
+    u = fmaxf(u, 0.f);
+    float v = p.co[((size_t)b * NDF + f) * 10 + lane] + u;
+    if (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) v = 0.f;
+    p.st.coef_ring[(((size_t)slot * 3 + pos % 3) * NDF + f) * 10 + lane] = v;
+  }
+}
+
+void launch_df_pathway(Engine& e, int B, cudaStream_t st) {
+  DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B};
+  const long long warps = (long long)B * NDF;
+  k_df_pathway<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+}
+
+void init_conv_kernels() {
+  cudaFuncSetAttribute(k_sepconv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM);
+}
+
+}  // namespace dpdf

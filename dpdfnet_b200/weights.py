@@ -197,8 +197,9 @@ def dft_bases(spec: ModelSpec) -> Dict[str, np.ndarray]:
     inv_s = (-ck[:, None] * np.sin(ang.T)) * (w[None, :] / (N * spec.wnorm))
     inv_s[0, :] = 0.0
     inv_s[-1, :] = 0.0
-    return {"const.dft_fwd_c": fwd_c, "const.dft_fwd_s": fwd_s,
-            "const.dft_inv_c": inv_c, "const.dft_inv_s": inv_s}
+    # interleaved (cos, sin) pairs: one 64-bit load feeds one packed FFMA2 on the device
+    return {"const.dft_fwd": np.stack([fwd_c, fwd_s], -1),      # [N, F, 2]
+            "const.dft_inv": np.stack([inv_c, inv_s], -1)}      # [F, N, 2]
 
 
 def norm_init(spec: ModelSpec) -> Tuple[np.ndarray, np.ndarray]:

@@ -1,0 +1,134 @@
+/*
+ * dpdfnet_b200 - C ABI of the B200-native batched DPDFNet streaming engine.
+ *
+ * This library replaces, for many streams at once, the one seam through which the reference
+ * touches its inference backend:
+ *
+ *     runtime.session.run([spec_e, state_out], {spec: f32[1,1,F,2], state_in: f32[S]})
+ *         reference call sites: package/src/dpdfnet/api.py:98-101, 154-157
+ *                               package/src/dpdfnet/stream.py:129-135
+ *         producer:             package/src/dpdfnet/onnx_backend.py:81-99 (build_runtime_model)
+ *
+ * plus the host DSP that brackets it in the streaming path (causal windowed rfft before, irfft *
+ * window + overlap-add after: stream.py:119-126, 138-156), which the engine fuses on the device.
+ *
+ * Conventions
+ *   - All functions return 0 on success, a negative dpdf_status otherwise; the message is
+ *     available from dpdf_last_error() (thread local).  Nothing throws across the ABI.
+ *   - "device" pointers are CUDA device pointers on the engine's device, "host" pointers are
+ *     ordinary host memory.  `cuda_stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - An engine handle is single-writer: calls on one handle must not overlap.
+ *   - Streams live in numbered slots [0, max_streams).  `slot_ids` (int32[B], may be NULL meaning
+ *     0..B-1) maps batch rows to slots; a slot may appear at most once per call.
+ *   - `flags` (int32[B], may be NULL meaning all zero) are per-row DPDF_FLAG_* bits.
+ */
+#ifndef DPDFNET_B200_H_
+#define DPDFNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPDF_ABI_VERSION 1
+
+typedef struct dpdf_engine dpdf_engine;
+
+enum dpdf_status {
+  DPDF_OK = 0,
+  DPDF_ERR_INVALID = -1,   /* bad argument / spec mismatch   (reference: ValueError)          */
+  DPDF_ERR_WEIGHTS = -2,   /* malformed or incomplete blob   (reference: FileNotFound/Value)  */
+  DPDF_ERR_CUDA = -3,      /* CUDA runtime failure           (reference: RuntimeError)        */
+  DPDF_ERR_NOMEM = -4
+};
+
+/* Per-row step flags (see DESIGN.md "offline-exact schedule"). */
+#define DPDF_FLAG_WARMUP 1    /* network not run: feature/c0/coef ring slots <- 0, GRU states kept   */
+#define DPDF_FLAG_ZERO_FEAT 2 /* normalised features forced to 0 (offline look-ahead padding)        */
+#define DPDF_FLAG_ZERO_SPEC 8 /* step_pcm: analysed spectrum taken as 0 (offline DF look-ahead pad)  */
+
+/* Static model description; mirrors dpdfnet_b200/spec.py:ModelSpec (reference constructor
+ * arguments: onnx_model/dpdfnet.py:522-565, onnx_model/dpdfnet_48khz_hr.py:586-630). */
+typedef struct dpdf_spec {
+  int32_t abi_version;    /* DPDF_ABI_VERSION */
+  int32_t sample_rate;    /* 16000 | 48000 */
+  int32_t win;            /* 320 | 960 */
+  int32_t hop;            /* win / 2 */
+  int32_t freq_bins;      /* win / 2 + 1 */
+  int32_t n_blocks;       /* DPRNN blocks per branch (0,2,4,8) */
+  int32_t hr48;           /* 1 = DPDFNet48HR (per-bin features and mask) */
+  int32_t fe_feat;        /* 32 | 481 */
+  int32_t fe[4];          /* frequency widths of e0..e3 */
+  int32_t erb_strides[3]; /* erb_conv1..3 frequency strides */
+  int32_t dec_up[3];      /* convt3, convt2, convt1 up-sampling factors (1 = plain conv) */
+  int32_t erb_widths[32]; /* ERB band widths in bins (sum = freq_bins) */
+  int32_t state_size;     /* S: floats of the reference's flat state vector */
+} dpdf_spec;
+
+/* Create an engine for `max_streams` slots on CUDA device `device` from a packed weight blob
+ * (dpdfnet_b200/weights.py:pack_checkpoint).  Replaces onnx_backend.py:81-99. */
+int dpdf_create(const dpdf_spec* spec, const void* weights, size_t weights_bytes,
+                int32_t max_streams, int32_t device, dpdf_engine** out);
+int dpdf_destroy(dpdf_engine* e);
+
+/* Re-initialise slots (norm states <- mu0/s0, everything else <- 0).  `slots` is a HOST array;
+ * NULL / n <= 0 resets every slot.  Replaces `state = runtime.init_state.copy()` (api.py:91,
+ * stream.py:69) and the buffer clears of StreamEnhancer.reset (stream.py:62-72). */
+int dpdf_reset(dpdf_engine* e, const int32_t* slots_host, int32_t n, void* cuda_stream);
+
+/* One hop for B streams, ONNX-shaped: un-normalised spectra in and out, f32[B, F, 2]
+ * (the graph multiplies by wnorm on the way in and 1/wnorm on the way out,
+ * onnx_model/export_dpdfnet_to_onnx.py:21-25).  Device pointers, asynchronous on `cuda_stream`. */
+int dpdf_step_spec(dpdf_engine* e, const float* spec_in, float* spec_out, const int32_t* slot_ids,
+                   const int32_t* flags, int32_t B, void* cuda_stream);
+
+/* One hop for B streams, fused DSP: `hop` new PCM samples per stream in, `hop` enhanced samples
+ * out (delayed by one window + 4 frames like StreamEnhancer, stream.py:117-156).  Row b of
+ * pcm_in / pcm_out starts at pcm_in + b*in_stride / pcm_out + b*out_stride (floats). */
+int dpdf_step_pcm(dpdf_engine* e, const float* pcm_in, int64_t in_stride, float* pcm_out,
+                  int64_t out_stride, const int32_t* slot_ids, const int32_t* flags, int32_t B,
+                  void* cuda_stream);
+
+/* T consecutive hops: step t reads pcm_in[b*in_stride + t*hop ...] and writes the same offset of
+ * pcm_out.  One CUDA-graph replay per hop; flags apply to every hop (normally NULL). */
+int dpdf_run_pcm(dpdf_engine* e, const float* pcm_in, int64_t in_stride, float* pcm_out,
+                 int64_t out_stride, const int32_t* slot_ids, const int32_t* flags, int32_t B,
+                 int32_t T, void* cuda_stream);
+
+/* Store one hop per stream as analysis history without producing a frame (the reference emits
+ * nothing until a full window has been buffered, stream.py:116). */
+int dpdf_prime_pcm(dpdf_engine* e, const float* pcm_in, int64_t in_stride, const int32_t* slot_ids,
+                   int32_t B, void* cuda_stream);
+
+/* Host-buffer variants (the call a reference-side binding makes): pageable or pinned HOST
+ * arrays, host->device and device->host copies included, synchronous on return. */
+int dpdf_step_spec_host(dpdf_engine* e, const float* spec_in, float* spec_out,
+                        const int32_t* slot_ids, const int32_t* flags, int32_t B);
+int dpdf_step_pcm_host(dpdf_engine* e, const float* pcm_in, float* pcm_out, const int32_t* slot_ids,
+                       const int32_t* flags, int32_t B);
+int dpdf_run_pcm_host(dpdf_engine* e, const float* pcm_in, float* pcm_out, const int32_t* slot_ids,
+                      int32_t B, int32_t T);
+
+/* Flat state vector of one slot in the reference layout (onnx_model/dpdfnet.py:737-746):
+ * drop-in for StreamEnhancer._state / the `state_in`,`state_out` tensors.  HOST buffers of
+ * dpdf_state_size() floats; synchronous. */
+int dpdf_state_size(const dpdf_engine* e);
+int dpdf_state_export(dpdf_engine* e, int32_t slot, float* flat_host);
+int dpdf_state_import(dpdf_engine* e, int32_t slot, const float* flat_host);
+
+/* Introspection for tests and benches. */
+int dpdf_debug_tensor(dpdf_engine* e, const char* name, float* out_host, size_t max_floats,
+                      size_t* numel_per_stream);    /* stage output of the last step, [B, numel] */
+int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the last step */
+int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value); /* "graph", "intra_bt" */
+int dpdf_time_kernels(dpdf_engine* e, int32_t B, int32_t iters, float* ms_out, const char** names_out,
+                      int32_t max_entries, int32_t* n_entries); /* per-kernel CUDA-event timing */
+const char* dpdf_last_error(void);
+const char* dpdf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPDFNET_B200_H_ */

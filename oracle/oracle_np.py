@@ -107,8 +107,7 @@ class OracleEngine:
     def _tensor_shapes(self):
         sp, C, H = self.spec, CONV_CH, GRU_DIM
         F, N = sp.freq_bins, sp.win
-        s = {"const.dft_fwd_c": (N, F), "const.dft_fwd_s": (N, F), "const.dft_inv_c": (F, N),
-             "const.dft_inv_s": (F, N), "const.mu0": (sp.fe_feat,), "const.s0": (NB_DF,),
+        s = {"const.dft_fwd": (N, F, 2), "const.dft_inv": (F, N, 2), "const.mu0": (sp.fe_feat,), "const.s0": (NB_DF,),
              "enc.erb_conv0.w": (9, C), "enc.df_conv0.w": (9, C), "enc.df_conv0.pw": (C, C),
              "erb_dec.conv0_out.w": (3, C), "df_dec.df_convp.w": (10, 5, 32), "df_dec.df_convp.pw": (10, 10)}
         for n in ["enc.erb_conv1", "enc.erb_conv2", "enc.erb_conv3", "enc.df_conv1"]:
@@ -420,10 +419,12 @@ class OracleEngine:
         if run.size:
             sl = slots[run]
             frame = np.concatenate([self.in_hist[sl], pcm[run]], 1)
-            X = np.stack([frame @ self.w["const.dft_fwd_c"], frame @ self.w["const.dft_fwd_s"]], -1).astype(f32)
+            fwd = self.w["const.dft_fwd"]
+            X = np.stack([frame @ fwd[:, :, 0], frame @ fwd[:, :, 1]], -1).astype(f32)
             X[(flags[run] & FLAG_ZERO_SPEC) != 0] = 0
             Y = self._step_core(X, sl, flags[run])
-            t = (Y[..., 0] @ self.w["const.dft_inv_c"] + Y[..., 1] @ self.w["const.dft_inv_s"]).astype(f32)
+            inv = self.w["const.dft_inv"]
+            t = (Y[..., 0] @ inv[:, :, 0] + Y[..., 1] @ inv[:, :, 1]).astype(f32)
             out[run] = self.ola[sl] + t[:, :hop]
             self.ola[sl] = t[:, hop:]
         self.in_hist[slots] = pcm

@@ -1,0 +1,178 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle, the golden vectors
+produced by the reference PyTorch modules, and size-independent properties at bench sizes.
+
+Tolerances: the north_star bar is 1e-4 max-abs on the enhanced waveform; everything here is
+fp32 with different summation orders only, so per-frame spectra are held to 2e-4 in
+un-normalised units (|X| ~ 30, i.e. ~7e-6 relative) and waveforms to 1e-4 (measured ~1e-6).
+"""
+import numpy as np
+import pytest
+
+from dpdfnet_b200.spec import get_spec
+from dpdfnet_b200.weights import pack_tensors, random_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+SPEC_TOL = 2e-4
+WAVE_TOL = 1e-4
+STATE_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+    return torch
+
+
+def _engine(name, seed, B, **kw):
+    from dpdfnet_b200.engine import Engine
+    spec = get_spec(name)
+    return Engine(spec, random_checkpoint(spec, seed), max_streams=B, **kw)
+
+
+def _oracle(name, seed, B):
+    from oracle.oracle_np import OracleEngine
+    spec = get_spec(name)
+    return OracleEngine(spec, pack_tensors(spec, random_checkpoint(spec, seed)), B)
+
+
+@pytest.mark.parametrize("name", ["dpdfnet2", "dpdfnet4", "dpdfnet2_48khz_hr"])
+def test_stream_golden(torch_cuda, golden_dir, name):
+    """Per-frame ONNX-shaped call with HOST buffers vs the reference streaming model's outputs."""
+    g = np.load(golden_dir / f"stream_{name}.npz")
+    eng = _engine(name, int(g["seed"]), 2)
+    for t in range(g["spec_in"].shape[0]):
+        y = eng.step_spec_host(g["spec_in"][t][None], slot_ids=[1])
+        assert np.isfinite(y).all()
+        assert np.abs(y[0] - g["spec_out"][t]).max() < SPEC_TOL, t
+    st = eng.state_export(1)
+    assert st.shape == g["state"].shape
+    assert np.abs(st - g["state"]).max() < STATE_TOL
+    # untouched slot still holds the initial state
+    init = eng.state_export(0)
+    assert np.count_nonzero(init[eng.spec.fe_feat + 96:]) == 0
+
+
+@pytest.mark.parametrize("name", ["dpdfnet2", "dpdfnet4", "dpdfnet2_48khz_hr"])
+def test_offline_golden(torch_cuda, golden_dir, name):
+    """BASELINE configs[0]-style check: whole clip vs model/dpdfnet.py output, 1e-4 max-abs."""
+    from dpdfnet_b200.offline import enhance_offline_exact
+    g = np.load(golden_dir / f"offline_{name}.npz")
+    eng = _engine(name, int(g["seed"]), g["wave_in"].shape[0])
+    out = enhance_offline_exact(eng, g["wave_in"])
+    assert out.shape == g["wave_out"].shape
+    assert np.abs(out - g["wave_out"]).max() < WAVE_TOL
+
+
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 5), ("dpdfnet8", 3), ("baseline", 2), ("dpdfnet8_48khz_hr", 2)])
+def test_stages_vs_oracle(torch_cuda, name, B):
+    """Every intermediate tensor of a hop against the oracle, ragged batch + slot indirection."""
+    eng = _engine(name, 11, B + 3)
+    eng.set_option("graph", 0)
+    ora = _oracle(name, 11, B + 3)
+    spec = eng.spec
+    rng = np.random.default_rng(2)
+    slots = (np.arange(B)[::-1] + 2).astype(np.int32)
+    N = spec.n_blocks
+    for t in range(4):
+        X = (rng.standard_normal((B, spec.freq_bins, 2)) * 20).astype(np.float32)
+        y = eng.step_spec_host(X, slot_ids=slots)
+        yo = ora.step_spec(X, slots=slots.astype(np.int64))
+        assert np.abs(y - yo).max() < SPEC_TOL
+        for stage, ref in (("e3", ora.dbg["e3"]), ("c0", ora.dbg["c0"]), ("emb", ora.dbg["emb"]),
+                           ("m", ora.dbg["m"]), ("co", ora.dbg["coefs"] * 0 + ora.dbg["coefs"]),
+                           ("xd", ora.dbg[f"xd{N - 1}"] if N else ora.dbg["c1"])):
+            if stage == "co":
+                continue          # 'co' is pre-pathway; covered through the coefficient ring in the state
+            got = eng.debug_tensor(stage, B)
+            assert np.abs(got - np.asarray(ref).reshape(B, -1)).max() < 2e-4, (stage, t)
+    for b in range(B):
+        assert np.abs(eng.state_export(int(slots[b])) - ora.export_state(int(slots[b]))).max() < STATE_TOL
+
+
+def test_pcm_path_vs_oracle_and_graph(torch_cuda):
+    """Fused DFT / OLA path: graph replay over T hops == T single steps == oracle."""
+    torch = torch_cuda
+    name, B, T = "dpdfnet2", 6, 12
+    eng = _engine(name, 5, B)
+    ora = _oracle(name, 5, B)
+    hop = eng.spec.hop
+    rng = np.random.default_rng(8)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    out_graph = eng.run_pcm_host(pcm)
+    assert np.abs(out_graph - ref).max() < WAVE_TOL
+    eng.reset()
+    eng.set_option("graph", 0)
+    out_steps = np.concatenate([eng.step_pcm_host(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    assert np.array_equal(out_graph, out_steps)
+    # device-pointer entry with a strided view
+    eng.reset()
+    eng.set_option("graph", 1)
+    x = torch.from_numpy(pcm).cuda()
+    y = eng.run_pcm(x)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), out_graph)
+
+
+def test_state_import_export_roundtrip(torch_cuda):
+    eng = _engine("dpdfnet2", 9, 3)
+    F = eng.spec.freq_bins
+    rng = np.random.default_rng(0)
+    X = (rng.standard_normal((7, 3, F, 2)) * 10).astype(np.float32)
+    for t in range(5):                      # 5 hops: ring heads are mid-cycle for L=3 and L=5
+        eng.step_spec_host(X[t])
+    flat = eng.state_export(2)
+    other = _engine("dpdfnet2", 9, 1)
+    other.state_import(0, flat)
+    assert np.array_equal(other.state_export(0), flat)
+    a = eng.step_spec_host(X[5])
+    b = other.step_spec_host(X[5][2:3])
+    assert np.abs(a[2] - b[0]).max() < 1e-5
+    with pytest.raises(ValueError):
+        other.state_import(0, flat[:-1])
+
+
+def test_reset_and_errors(torch_cuda):
+    eng = _engine("dpdfnet2", 1, 4)
+    F = eng.spec.freq_bins
+    X = (np.random.default_rng(1).standard_normal((4, F, 2)) * 10).astype(np.float32)
+    first = eng.step_spec_host(X)
+    eng.step_spec_host(X)
+    eng.reset([1, 3])
+    again = eng.step_spec_host(X)
+    assert np.array_equal(again[1], first[1]) and np.array_equal(again[3], first[3])
+    assert not np.array_equal(again[0], first[0])
+    with pytest.raises(ValueError):
+        eng.step_spec_host(np.zeros((5, F, 2), np.float32))        # B > max_streams
+    with pytest.raises(ValueError):
+        eng.step_spec_host(X, slot_ids=[0, 1, 2, 9])                # slot out of range
+    with pytest.raises(ValueError):
+        eng.step_spec_host(np.zeros((2, F + 1, 2), np.float32))
+
+
+def test_full_size_batch_invariance(torch_cuda):
+    """BASELINE configs[1] size (dpdfnet4, B=1024): every stream must behave exactly as it does alone.
+
+    Streams share nothing but weights, so (i) identical inputs in different batch rows give
+    bit-identical outputs and (ii) a stream's output does not depend on the batch size."""
+    torch = torch_cuda
+    name, B, T = "dpdfnet4", 1024, 6
+    eng = _engine(name, 0, B)
+    hop = eng.spec.hop
+    rng = np.random.default_rng(4)
+    base = (rng.standard_normal((4, T * hop)) * 0.1).astype(np.float32)
+    pcm = np.tile(base, (B // 4, 1))
+    out = eng.run_pcm_host(pcm)
+    assert np.isfinite(out).all()
+    for r in range(4):
+        assert np.array_equal(out[r::4], np.broadcast_to(out[r], (B // 4, T * hop)))
+    small = _engine(name, 0, 4)
+    out_small = small.run_pcm_host(base)
+    assert np.abs(out_small - out[:4]).max() < 1e-5
+    ora = _oracle(name, 0, 4)
+    ref = np.concatenate([ora.step_pcm(base[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    assert np.abs(out[:4] - ref).max() < WAVE_TOL
+    assert eng.kernel_launches > 0

@@ -1,0 +1,92 @@
+"""CPU-side checks: weight packing, blob format, C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from dpdfnet_b200 import weights
+from dpdfnet_b200.spec import MODEL_SPECS, get_spec
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_blob_roundtrip():
+    spec = get_spec("dpdfnet2")
+    t = weights.pack_tensors(spec, weights.random_checkpoint(spec, 1))
+    blob = weights.serialize(t)
+    back = weights.deserialize(blob)
+    assert list(back) == list(t)
+    for k in t:
+        assert np.array_equal(back[k], t[k].reshape(-1)), k
+
+
+def test_random_checkpoint_is_deterministic_and_bn_randomised():
+    spec = get_spec("dpdfnet4")
+    a, b = weights.random_checkpoint(spec, 3), weights.random_checkpoint(spec, 3)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert a["enc.erb_conv0.2.running_var"].std() > 0.1 and abs(a["enc.erb_conv0.2.running_mean"]).max() > 0.05
+
+
+def test_pack_rejects_bad_checkpoints():
+    spec = get_spec("dpdfnet2")
+    ck = weights.random_checkpoint(spec, 0)
+    bad = dict(ck)
+    bad.pop("enc.df_conv1.1.weight")
+    with pytest.raises(KeyError):
+        weights.pack_tensors(spec, bad)
+    bad = dict(ck)
+    bad["enc.df_conv1.1.weight"] = bad["enc.df_conv1.1.weight"][:32]
+    with pytest.raises(ValueError):
+        weights.pack_tensors(spec, bad)
+    with pytest.raises(ValueError):
+        weights.deserialize(b"nonsense" * 10)
+
+
+def test_dft_bases_reconstruct():
+    """Vorbis COLA (package/tests/test_package_behaviors.py:709-716) through the packed bases:
+    analysis -> synthesis -> overlap-add of two frames reproduces the middle hop."""
+    for name in ("dpdfnet2", "dpdfnet2_48khz_hr"):
+        spec = get_spec(name)
+        b = weights.dft_bases(spec)
+        fwd, inv = b["const.dft_fwd"], b["const.dft_inv"]
+        x = np.random.default_rng(0).standard_normal(3 * spec.hop)
+        frames = []
+        for t in range(2):
+            fr = x[t * spec.hop:t * spec.hop + spec.win]
+            X = np.stack([fr @ fwd[:, :, 0], fr @ fwd[:, :, 1]], -1)
+            frames.append(X[:, 0] @ inv[:, :, 0] + X[:, 1] @ inv[:, :, 1])
+        mid = frames[0][spec.hop:] + frames[1][:spec.hop]
+        assert np.abs(mid - x[spec.hop:2 * spec.hop]).max() < 1e-9
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from dpdfnet_b200 import engine
+    from dpdfnet_b200.build import build_library
+    lib = engine.load_library(build_library())
+    header = (ROOT / "include" / "dpdfnet_b200.h").read_text()
+    declared = set(re.findall(r"\b(dpdf_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in the header but not exported"
+    assert declared == set(engine.C_API), declared ^ set(engine.C_API)
+    assert lib.dpdf_version().decode().startswith("dpdfnet_b200")
+    assert ctypes.sizeof(engine._Spec) == 4 * (8 + 4 + 3 + 3 + 32 + 1)
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dpdfnet_b200.engine import Engine
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        Engine("dpdfnet2", max_streams=1)
+
+
+def test_c_spec_matches_python_spec():
+    from dpdfnet_b200.engine import c_spec
+    for name, spec in MODEL_SPECS.items():
+        s = c_spec(spec)
+        assert s.state_size == spec.state_size and sum(s.erb_widths) == spec.freq_bins
+        assert list(s.fe) == list(spec.fe)
