@@ -154,6 +154,10 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
     hop = spec.hop
     eng = Engine(spec, ck, max_streams=B, device=local)
+    if args.no_graph:
+        eng.set_option("graph", 0)
+    if args.intra_bt:
+        eng.set_option("intra_bt", args.intra_bt)
     if world > 1:   # weights are replicated from the same seed; one tiny collective to line the ranks up
         dist.barrier()
 
@@ -291,6 +295,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-batch", type=int, default=128)
     ap.add_argument("--cpu-hops", type=int, default=20)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--intra-bt", type=int, default=0)
     ap.add_argument("--profile-only", action="store_true", help="device steps only (for ncu runs)")
     args = ap.parse_args()
     if args.warmup < 3:
