@@ -62,12 +62,14 @@ struct SepParams {
   SepProblem prob[SEP_MAXP];
   int nprob, B;
 };
-constexpr size_t SEP_SMEM = (size_t)(128 * SEP_LD + 64 * SEP_LD + 64) * sizeof(float);
+constexpr int SEP_TM = 2;                 // 64-row tiles: 35 KB smem, <= 128 registers -> 2+ CTAs per SM hide the prologue latency
+constexpr int SEP_ROWS = 32 * SEP_TM;
+constexpr size_t SEP_SMEM = (size_t)(SEP_ROWS * SEP_LD + 64 * SEP_LD + 64) * sizeof(float);
 
-__global__ void __launch_bounds__(256, 1) k_sepconv(SepParams p) {
+__global__ void __launch_bounds__(256, 2) k_sepconv(SepParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* As = smem;                    // [128][68]
-  float* Ws = As + 128 * SEP_LD;       // [64][68]
+  float* As = smem;                    // [SEP_ROWS][68]
+  float* Ws = As + SEP_ROWS * SEP_LD;  // [64][68]
   float* bs = Ws + 64 * SEP_LD;        // [64]
   int pi = 0;
 #pragma unroll
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(256, 1) k_sepconv(SepParams p) {
     if (i < p.nprob && (int)blockIdx.x >= p.prob[i].tile0) pi = i;
   const SepProblem& q = p.prob[pi];
   const int tid = threadIdx.x;
-  const long long row0 = (long long)(blockIdx.x - q.tile0) * 128;
+  const long long row0 = (long long)(blockIdx.x - q.tile0) * SEP_ROWS;
   const long long nrows = (long long)p.B * q.Fout;
 
   // pointwise weights + bias -> smem (async)
@@ -84,7 +86,8 @@ __global__ void __launch_bounds__(256, 1) k_sepconv(SepParams p) {
   cp_async_commit();
 
   // prologue: A[row][c]
-  for (int it = tid; it < 128 * 16; it += 256) {
+#pragma unroll 2
+  for (int it = tid; it < SEP_ROWS * 16; it += 256) {
     const int r = it >> 4, c = (it & 15) * 4;
     const long long row = row0 + r;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -143,19 +146,19 @@ __global__ void __launch_bounds__(256, 1) k_sepconv(SepParams p) {
   __syncthreads();
 
   const int tx = tid & 7, ty = tid >> 3;
-  float2 acc[4][8];
+  float2 acc[SEP_TM][8];
   acc_zero(acc);
-  tile_mac<64, SEP_LD, SEP_LD, 4, 8>(As, Ws, acc, tx, ty);
+  tile_mac<64, SEP_LD, SEP_LD, SEP_TM, 8>(As, Ws, acc, tx, ty);
   __syncthreads();                          // everyone done reading As
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < SEP_TM; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int col = tx + 8 * j;
       As[(ty + 32 * i) * SEP_LD + col] = fmaxf(acc[i][j].x + acc[i][j].y + bs[col], 0.f);
     }
   __syncthreads();
-  for (int it = tid; it < 128 * 16; it += 256) {
+  for (int it = tid; it < SEP_ROWS * 16; it += 256) {
     const int r = it >> 4, c = (it & 15) * 4;
     const long long row = row0 + r;
     if (row >= nrows) continue;
@@ -183,7 +186,7 @@ void launch_sepconv(Engine& e, const SepProblem* probs, int nprob, int B, cudaSt
   for (int i = 0; i < nprob; ++i) {
     p.prob[i] = probs[i];
     p.prob[i].tile0 = tiles;
-    tiles += (int)(((long long)B * probs[i].Fout + 127) / 128);
+    tiles += (int)(((long long)B * probs[i].Fout + SEP_ROWS - 1) / SEP_ROWS);
   }
   k_sepconv<<<tiles, 256, SEP_SMEM, st>>>(p);
 }

@@ -108,82 +108,107 @@ void launch_gl(Engine& e, const GLProblem* probs, int nprob, int B, cudaStream_t
 
 // ---------------------------------------------------------------------------------------------
 constexpr int GRU_MAXP = 2;
-constexpr int G_LDA = 260, G_LDW = 68;
+constexpr int G_LD = 68;
 struct GRUParams {
   const IoDesc* io;
   GRUProblem prob[GRU_MAXP];
   int B;
 };
-constexpr size_t GRU_SMEM = (size_t)(2 * 64 * G_LDA + 2 * 32 * G_LDW) * sizeof(float) + 64 * sizeof(long long);
+template <int TM>
+constexpr size_t gru_smem() { return (size_t)(2 * (32 * TM + 96) * G_LD) * sizeof(float) + 32 * TM * sizeof(long long); }
 
+// One CTA = (32*TM streams) x (32 hidden units, all three gates).  K = 256 (x) + 256 (h_prev) is walked in
+// eight 64-wide chunks; chunk kc+1 (activation tile + the [96 x 64] weight slab) streams in through
+// cp.async while chunk kc is multiplied.  Thread tile: TM rows x 4 units x {r, z, n} -> 16 smem loads
+// feed 96 packed FFMA2 per 4 k (TM = 4).
+template <int TM>
 __global__ void __launch_bounds__(256, 1) k_gru(GRUParams p) {
+  constexpr int ROWS = 32 * TM;
   extern __shared__ __align__(16) float smem[];
-  float* Ax = smem;                     // [64][260]
-  float* Ah = Ax + 64 * G_LDA;          // [64][260]
-  float* Wb = Ah + 64 * G_LDA;          // [2][32][68]
-  long long* s_hoff = reinterpret_cast<long long*>(Wb + 2 * 32 * G_LDW);
+  float* Abuf = smem;                          // [2][ROWS][68]
+  float* Wbuf = Abuf + 2 * ROWS * G_LD;        // [2][96][68]
+  long long* s_hoff = reinterpret_cast<long long*>(Wbuf + 2 * 96 * G_LD);
   const GRUProblem& q = p.prob[blockIdx.z];
   const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  const int b0 = blockIdx.x * 64;
+  const int b0 = blockIdx.x * ROWS;
   const int u0 = blockIdx.y * 32;
-  const int valid = min(64, p.B - b0);
+  const int valid = min(ROWS, p.B - b0);
 
-  if (tid < 64) {
-    s_hoff[tid] = tid < valid ? (long long)io_slot(p.io, b0 + tid) * q.hs_stride : -1;
-  }
+  if (tid < ROWS) s_hoff[tid] = tid < valid ? (long long)io_slot(p.io, b0 + tid) * q.hs_stride : 0;
   __syncthreads();
-  tile_load_async<256, G_LDA, 256>(Ax, 64, valid, [&](int r) { return q.x + (size_t)(b0 + r) * H; });
-  tile_load_async<256, G_LDA, 256>(Ah, 64, valid, [&](int r) { return q.hstate + s_hoff[r]; });
-  cp_async_commit();
 
-  // chunk c: gates r, z -> (ih k0..3, hh k0..3); gate n -> (hh k0..3) then (ih k0..3)
-  auto chunk_src = [&](int c, const float*& wsrc, int& use_h, int& kc) {
-    int g, part;
-    if (c < 16) { g = c >> 3; part = (c >> 2) & 1; }
-    else { g = 2; part = c < 20 ? 1 : 0; }
-    kc = c & 3;
-    use_h = part;
-    const float* base = part ? q.w.whh : q.w.wih;
-    wsrc = base + (size_t)(g * H + u0) * H + kc * 64;
+  auto load_chunk = [&](int kc, int buf) {
+    const bool hpart = kc >= 4;
+    const int k0 = (kc & 3) * 64;
+    float* Ad = Abuf + buf * ROWS * G_LD;
+    float* Wd = Wbuf + buf * 96 * G_LD;
+    for (int i = tid; i < ROWS * 16; i += 256) {
+      const int r = i >> 4, c = (i & 15) * 4;
+      float* dst = Ad + r * G_LD + c;
+      if (r < valid) cp_async16(dst, (hpart ? q.hstate + s_hoff[r] : q.x + (size_t)(b0 + r) * H) + k0 + c);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* wb = hpart ? q.w.whh : q.w.wih;
+    for (int i = tid; i < 96 * 16; i += 256) {
+      const int r = i >> 4, c = (i & 15) * 4;
+      cp_async16(Wd + r * G_LD + c, wb + (size_t)((r >> 5) * H + u0 + (r & 31)) * H + k0 + c);
+    }
   };
-  auto prefetch = [&](int c) {
-    const float* wsrc; int use_h, kc;
-    chunk_src(c, wsrc, use_h, kc);
-    float* dst = Wb + (c & 1) * 32 * G_LDW;
-    for (int i = tid; i < 32 * 16; i += 256) cp_async16(dst + (i >> 4) * G_LDW + (i & 15) * 4, wsrc + (size_t)(i >> 4) * H + (i & 15) * 4);
-  };
-  prefetch(0);
-  cp_async_commit();
 
-  float2 acc[2][4];
-  float rg[2][4], zg[2][4];
-  acc_zero(acc);
-  for (int c = 0; c < 24; ++c) {
+  float2 ar[TM][4], az[TM][4], ain[TM][4], ahn[TM][4];
+  acc_zero(ar); acc_zero(az); acc_zero(ain); acc_zero(ahn);
+
+  auto mac = [&](const float* As, const float* Ws, float2 (&a0)[TM][4], float2 (&a1)[TM][4], float2 (&a2)[TM][4]) {
+    const float* ap = As + ty * G_LD;
+    const float* wp = Ws + tx * G_LD;
+#pragma unroll 2
+    for (int k = 0; k < 64; k += 4) {
+      float4 a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(ap + i * 32 * G_LD + k);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wp + (j * 8) * G_LD + k);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + (32 + j * 8) * G_LD + k);
+        const float4 w2 = *reinterpret_cast<const float4*>(wp + (64 + j * 8) * G_LD + k);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          a0[i][j] = ffma2(lo2(a[i]), lo2(w0), a0[i][j]);
+          a1[i][j] = ffma2(lo2(a[i]), lo2(w1), a1[i][j]);
+          a2[i][j] = ffma2(lo2(a[i]), lo2(w2), a2[i][j]);
+          a0[i][j] = ffma2(hi2(a[i]), hi2(w0), a0[i][j]);
+          a1[i][j] = ffma2(hi2(a[i]), hi2(w1), a1[i][j]);
+          a2[i][j] = ffma2(hi2(a[i]), hi2(w2), a2[i][j]);
+        }
+      }
+    }
+  };
+
+  load_chunk(0, 0);
+  cp_async_commit();
+  for (int kc = 0; kc < 8; ++kc) {
     cp_async_wait<0>();
     __syncthreads();
-    if (c + 1 < 24) prefetch(c + 1);
+    if (kc + 1 < 8) load_chunk(kc + 1, (kc + 1) & 1);
     cp_async_commit();
-    const float* wsrc; int use_h, kc;
-    chunk_src(c, wsrc, use_h, kc);
-    tile_mac<64, G_LDA, G_LDW, 2, 4>((use_h ? Ah : Ax) + kc * 64, Wb + (c & 1) * 32 * G_LDW, acc, tx, ty);
-    if (c == 7 || c == 15 || c == 19 || c == 23) {
+    const float* As = Abuf + (kc & 1) * ROWS * G_LD;
+    const float* Ws = Wbuf + (kc & 1) * 96 * G_LD;
+    if (kc < 4) mac(As, Ws, ar, az, ain);
+    else mac(As, Ws, ar, az, ahn);
+  }
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < TM; ++i) {
+    const int row = ty + 32 * i;
+    if (row >= valid) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int u = u0 + tx + 8 * j;
-          const float s = acc[i][j].x + acc[i][j].y;
-          if (c == 7) rg[i][j] = sigmoidf_(s + __ldg(q.w.bias + u));
-          else if (c == 15) zg[i][j] = sigmoidf_(s + __ldg(q.w.bias + H + u));
-          else if (c == 19) rg[i][j] *= s + __ldg(q.w.bias + 3 * H + u);
-          else {
-            const int row = ty + 32 * i;
-            const float ng = tanhf_(s + __ldg(q.w.bias + 2 * H + u) + rg[i][j]);
-            const float hn = (1.0f - zg[i][j]) * ng + zg[i][j] * Ah[row * G_LDA + u];
-            if (row < valid) q.hout[(size_t)(b0 + row) * H + u] = hn;
-          }
-        }
-      acc_zero(acc);
+    for (int j = 0; j < 4; ++j) {
+      const int u = u0 + tx + 8 * j;
+      const float rg = sigmoidf_(ar[i][j].x + ar[i][j].y + __ldg(q.w.bias + u));
+      const float zg = sigmoidf_(az[i][j].x + az[i][j].y + __ldg(q.w.bias + H + u));
+      const float ng = tanhf_(ain[i][j].x + ain[i][j].y + __ldg(q.w.bias + 2 * H + u) +
+                              rg * (ahn[i][j].x + ahn[i][j].y + __ldg(q.w.bias + 3 * H + u)));
+      const float hprev = q.hstate[s_hoff[row] + u];
+      q.hout[(size_t)(b0 + row) * H + u] = (1.0f - zg) * ng + zg * hprev;
     }
   }
   // Every unit-chunk CTA of a cell reads the full h_prev rows, so the state may only be overwritten
@@ -204,14 +229,20 @@ void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream
   p.io = e.io_dev;
   p.B = B;
   for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
-  dim3 grid((B + 63) / 64, H / 32, nprob);
-  k_gru<<<grid, 256, GRU_SMEM, st>>>(p);
+  if (B >= 4 * e.num_sms) {          // enough streams to fill the chip with 128-row tiles
+    dim3 grid((B + 127) / 128, H / 32, nprob);
+    k_gru<4><<<grid, 256, gru_smem<4>(), st>>>(p);
+  } else {
+    dim3 grid((B + 63) / 64, H / 32, nprob);
+    k_gru<2><<<grid, 256, gru_smem<2>(), st>>>(p);
+  }
   for (int i = 0; i < nprob; ++i)
     k_gru_commit<<<(B * (H / 4) + 255) / 256, 256, 0, st>>>(e.io_dev, probs[i].hout, probs[i].hstate, probs[i].hs_stride, B);
 }
 
 void init_dense_kernels() {
-  cudaFuncSetAttribute(k_gru, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRU_SMEM);
+  cudaFuncSetAttribute(k_gru<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_smem<4>());
+  cudaFuncSetAttribute(k_gru<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_smem<2>());
 }
 
 }  // namespace dpdf

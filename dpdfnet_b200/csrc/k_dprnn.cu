@@ -65,13 +65,19 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
 
   for (int i = tid; i < BT * ILD; i += 256) (&hs[0][0][0])[i] = 0.f;     // h0 = 0 every frame
 
+  // A row holds 64 floats with a 4-float gap after element 31: the four K-quarters of a row then start
+  // in banks {0,16,4,20}, so the broadcast LDS.128 of the four q-lanes never collide.
+  const int qoff = q * 16 + ((q >> 1) << 2);
+  const int jpos = j + ((j >> 5) << 2);
+
   auto prefetch = [&](int t, int buf) {
     const int f = dir ? T - 1 - t : t;
     for (int i = tid; i < BT * 16; i += 256) {
       const int s = i >> 4, c = (i & 15) * 4;
       const int b = b0 + s;
-      if (b < p.B) cp_async16(&xs[buf][s][c], xg + ((size_t)b * T + f) * C + c);
-      else *reinterpret_cast<float4*>(&xs[buf][s][c]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      float* dst = &xs[buf][s][c + ((c >> 5) << 2)];
+      if (b < p.B) cp_async16(dst, xg + ((size_t)b * T + f) * C + c);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   auto store_h = [&](int buf, int t) {
@@ -80,7 +86,8 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
       const int s = i >> 4, c = (i & 15) * 4;
       const int b = b0 + s;
       if (b < p.B)
-        *reinterpret_cast<float4*>(hg + ((size_t)b * T + f) * 2 * C + dir * C + c) = *reinterpret_cast<const float4*>(&hs[buf][s][c]);
+        *reinterpret_cast<float4*>(hg + ((size_t)b * T + f) * 2 * C + dir * C + c) =
+            *reinterpret_cast<const float4*>(&hs[buf][s][c + ((c >> 5) << 2)]);
     }
   };
 
@@ -88,6 +95,7 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
   cp_async_commit();
   int cur = 0;
   const bool hi = (q & 2) != 0, odd = (q & 1) != 0;
+  struct Frag { float4 x[4], h[4]; };
   for (int t = 0; t < T; ++t) {
     cp_async_wait<0>();
     __syncthreads();                       // x_t landed, h_t complete, previous buffers free
@@ -97,17 +105,25 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
     const float(*xb)[ILD] = xs[t & 1];
     const float(*hb)[ILD] = hs[cur];
     float(*hn)[ILD] = hs[cur ^ 1];
-#pragma unroll 1
+    auto load_frag = [&](Frag& f, int row) {
+      const float4* xp = reinterpret_cast<const float4*>(&xb[row][qoff]);
+      const float4* hp = reinterpret_cast<const float4*>(&hb[row][qoff]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { f.x[c] = xp[c]; f.h[c] = hp[c]; }
+    };
+    Frag fr;
+    load_frag(fr, 0);
+#pragma unroll 2
     for (int sb = 0; sb < BT / 4; ++sb) {
       float v[4][4];
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        const float4* xp = reinterpret_cast<const float4*>(&xb[sb * 4 + s][q * 16]);
-        const float4* hp = reinterpret_cast<const float4*>(&hb[sb * 4 + s][q * 16]);
+        Frag nx;                                         // software pipeline: next stream's operands
+        load_frag(nx, min(sb * 4 + s + 1, BT - 1));      // are in flight while this one is multiplied
         float2 ar = make_float2(0.f, 0.f), az = ar, ain = ar, ahn = ar;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 xv = xp[c], hv = hp[c];
+          const float4 xv = fr.x[c], hv = fr.h[c];
           ar = ffma2(wi[0][2 * c], lo2(xv), ar);
           az = ffma2(wi[1][2 * c], lo2(xv), az);
           ain = ffma2(wi[2][2 * c], lo2(xv), ain);
@@ -125,6 +141,7 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
         v[s][1] = az.x + az.y;
         v[s][2] = ain.x + ain.y;
         v[s][3] = ahn.x + ahn.y;
+        fr = nx;
       }
       // reduce-scatter over the 4 K-lanes: lane q ends with the complete sums of stream sb*4+q
       float u[2][4], r[4];
@@ -143,11 +160,11 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
         r[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
       const int srow = sb * 4 + q;
-      const float hprev = hb[srow][j];
+      const float hprev = hb[srow][jpos];
       const float rg = sigmoidf_(r[0] + b_r);
       const float zg = sigmoidf_(r[1] + b_z);
       const float ng = tanhf_(r[2] + b_in + rg * (r[3] + b_hn));
-      hn[srow][j] = (1.0f - zg) * ng + zg * hprev;
+      hn[srow][jpos] = (1.0f - zg) * ng + zg * hprev;
     }
     cur ^= 1;
   }
