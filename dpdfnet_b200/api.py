@@ -1,0 +1,93 @@
+"""Whole-clip enhancement (mirror of ``package/src/dpdfnet/api.py``).
+
+``enhance`` keeps the reference signature and the reference's alignment convention (pad one window,
+centred STFT, per-frame runtime calls, attenuation limit against the 4-frame-delayed noisy spectrum,
+centred iSTFT, drop ``2*win``; ``api.py:51-113``).  File I/O, downloads and the CLI are out of scope.
+``enhance_batch`` is the batched, device-resident variant the engine exists for.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Any, Callable, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from .models import DEFAULT_MODEL, available_model_entries, resolve_model
+
+
+def available_models() -> List[Dict[str, Any]]:
+    return available_model_entries()
+
+
+def _enhance_with_runtime(audio: np.ndarray, sample_rate: int, *, runtime, model_sample_rate: int,
+                          attn_limit_db: Optional[float] = None,
+                          progress_callback: Optional[Callable[[int, int], None]] = None) -> np.ndarray:
+    from .audio import (apply_attn_limit, ensure_sample_rate, fit_length, make_stft_config, postprocess_spec,
+                        preprocess_waveform, to_mono)
+    from .onnx_backend import infer_win_len
+
+    wave = to_mono(np.asarray(audio, dtype=np.float32))
+    sr_in = int(sample_rate)
+    x = ensure_sample_rate(wave, sr_in, model_sample_rate)
+    cfg = make_stft_config(infer_win_len(runtime.session, model_sample_rate))
+    spec = preprocess_waveform(np.pad(x, (0, cfg.win_len)), cfg)          # alignment padding, api.py:88
+    T = int(spec.shape[1])
+    state = runtime.init_state.copy()
+    outs: List[np.ndarray] = []
+    if progress_callback is not None:
+        progress_callback(0, T)
+    for t in range(T):
+        frame = np.ascontiguousarray(spec[:, t:t + 1], dtype=np.float32)
+        y, state = runtime.session.run([runtime.out_spec_name, runtime.out_state_name],
+                                       {runtime.in_spec_name: frame, runtime.in_state_name: state})
+        outs.append(np.ascontiguousarray(y, dtype=np.float32))
+        if progress_callback is not None:
+            progress_callback(t + 1, T)
+    if not outs:
+        return wave.copy()
+    spec_e = apply_attn_limit(spec, np.concatenate(outs, axis=1), attn_limit_db)
+    y = ensure_sample_rate(postprocess_spec(spec_e, cfg), model_sample_rate, sr_in)
+    return fit_length(y, wave.shape[0]).astype(np.float32, copy=False)
+
+
+def enhance(audio: np.ndarray, sample_rate: int, *, model: str = DEFAULT_MODEL,
+            onnx_path: Optional[Union[str, Path]] = None, attn_limit_db: Optional[float] = None,
+            verbose: bool = False, progress_callback: Optional[Callable[[int, int], None]] = None) -> np.ndarray:
+    from .onnx_backend import build_runtime_model
+    resolved = resolve_model(model=model, onnx_path=onnx_path, auto_download=True, verbose=verbose)
+    runtime = build_runtime_model(resolved.onnx_path)
+    return _enhance_with_runtime(audio, sample_rate, runtime=runtime, model_sample_rate=resolved.info.sample_rate,
+                                 attn_limit_db=attn_limit_db, progress_callback=progress_callback)
+
+
+def enhance_batch(clips: Sequence[np.ndarray], sample_rate: int, *, model: str = DEFAULT_MODEL,
+                  onnx_path: Optional[Union[str, Path]] = None, engine=None, exact_offline: bool = True) -> List[np.ndarray]:
+    """Enhance many mono clips at once on one engine (streams = clips, ragged lengths allowed).
+
+    With ``exact_offline`` the result equals the reference's offline PyTorch model
+    (``model/dpdfnet.py``) on every clip; clips are zero-padded to the longest one for the batched run,
+    which does not change earlier samples because the model is causal apart from its 4-frame look-ahead.
+    """
+    from .audio import ensure_sample_rate, to_mono
+    from .offline import enhance_offline_exact
+    from .onnx_backend import create_session
+    resolved = resolve_model(model=model, onnx_path=onnx_path)
+    waves = [ensure_sample_rate(to_mono(np.asarray(c, dtype=np.float32)), int(sample_rate), resolved.info.sample_rate) for c in clips]
+    if not waves:
+        return []
+    if engine is None:
+        engine = create_session(resolved.onnx_path, max_streams=len(waves)).engine
+    hop = engine.spec.hop
+    n = max(w.size for w in waves)
+    n = max((n + 4 * hop + hop - 1) // hop * hop, 2 * hop)             # room for the look-ahead tail
+    batch = np.zeros((len(waves), n), dtype=np.float32)
+    for i, w in enumerate(waves):
+        batch[i, :w.size] = w
+    if not exact_offline:
+        raise NotImplementedError("only the offline-exact schedule is implemented for batches")
+    out = enhance_offline_exact(engine, batch)
+    res = []
+    for i, w in enumerate(waves):
+        y = ensure_sample_rate(out[i, :w.size], resolved.info.sample_rate, int(sample_rate))
+        res.append(np.ascontiguousarray(y[:np.asarray(clips[i]).shape[0]], dtype=np.float32))
+    return res
