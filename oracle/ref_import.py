@@ -50,11 +50,17 @@ def offline_model(spec, checkpoint):
     """Reference whole-utterance model (model/) loaded with ``checkpoint``."""
     import torch
     _prep()
+    import importlib.util
+    # load by path under a private name: a bare ``import dpdfnet`` may already be taken by the drop-in alias
+    fname, cls = ("dpdfnet_48khz_hr.py", "DPDFNet48HR") if spec.hr48 else ("dpdfnet.py", "DPDFNet")
+    modname = "_ref_offline_" + fname[:-3]
+    if modname not in sys.modules:
+        sp = importlib.util.spec_from_file_location(modname, os.path.join(REF, "model", fname))
+        mod = importlib.util.module_from_spec(sp)
+        sys.modules[modname] = mod
+        sp.loader.exec_module(mod)
+    M = getattr(sys.modules[modname], cls)
     with contextlib.redirect_stdout(io.StringIO()):
-        if spec.hr48:
-            from dpdfnet_48khz_hr import DPDFNet48HR as M
-        else:
-            from dpdfnet import DPDFNet as M
         m = M(dprnn_num_blocks=spec.n_blocks)
     sd = {k: torch.from_numpy(v.copy()) for k, v in checkpoint.items()}
     missing, unexpected = m.load_state_dict(sd, strict=False)
