@@ -101,6 +101,8 @@ static int bind_weights(Engine& e) {
       x.r_bias = W(q + ".inter.bias", 4 * C);
       x.fc2_w = W(q + ".inter.fc_w", C * C);       x.fc2_b = W(q + ".inter.fc_b", C);
       x.ln2_g = W(q + ".inter.ln_g", C);           x.ln2_b = W(q + ".inter.ln_b", C);
+      x.tc_fc_w = W(q + ".tc.fc_w", 2 * C * 2 * C); x.tc_gates = W(q + ".tc.gates", 6 * 2 * C * C);
+      x.tc_fc2_w = W(q + ".tc.fc2_w", 2 * C * C);
     }
   }
   auto gl = [&](const std::string& n, int G, int Ng, int Kg) { return GLW{W(n + ".w", (size_t)G * Ng * Kg), W(n + ".b", (size_t)G * Ng), G, Ng, Kg}; };
@@ -270,6 +272,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   init_conv_kernels();
   init_dprnn_kernels();
   init_dense_kernels();
+  init_dprnn_tc_kernels();
   launch_reset(e, nullptr, max_streams, e.own_stream);
   if (cudaStreamSynchronize(e.own_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
     return bail(fail(DPDF_ERR_CUDA, "engine initialisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -344,7 +347,9 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   }
   for (int i = 0; i < d.N; ++i) {
     RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); ++n;
-    RUN("dprnn_post", launch_dprnn_post(e, i, B, st)); ++n;
+    if (e.post_tc) { RUN("dprnn_post", launch_dprnn_post_tc(e, i, B, st)); }
+    else { RUN("dprnn_post", launch_dprnn_post(e, i, B, st)); }
+    ++n;
   }
   const float* xe_final = d.N > 0 ? c.xe : c.e3;
   auto glp = [&](const GLW& gw, const float* in0, int ld0, float* out, int ldo, int act) {
@@ -776,6 +781,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   else if (strcmp(key, "intra_bt") == 0) {
     if (value != 0 && value != 8 && value != 16 && value != 32) return fail(DPDF_ERR_INVALID, "intra_bt must be 0, 8, 16 or 32");
     e.intra_bt = value;
+    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+    e.graphs.clear();
+  } else if (strcmp(key, "post_tc") == 0) {
+    e.post_tc = value ? 1 : 0;
     for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
     e.graphs.clear();
   } else return fail(DPDF_ERR_INVALID, "unknown option '%s'", key);

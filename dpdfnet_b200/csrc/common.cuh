@@ -93,13 +93,16 @@ __device__ __forceinline__ void tile_mac(const float* __restrict__ As, const flo
     for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(ap + i * 32 * LDA + k);
 #pragma unroll
     for (int j = 0; j < TN; ++j) w[j] = *reinterpret_cast<const float4*>(wp + j * 8 * LDW + k);
+    // Issue order: the register file feeds one 64-bit operand per lane per cycle, so an FFMA2 sustains its
+    // 2-cycle rate only if one operand pair sits in the operand-reuse cache -> keep a[i] fixed over a run of j,
+    // and never put the two updates of one accumulator back to back (4.4-cycle dependent-issue latency).
 #pragma unroll
-    for (int i = 0; i < TM; ++i)
+    for (int i = 0; i < TM; ++i) {
 #pragma unroll
-      for (int j = 0; j < TN; ++j) {
-        acc[i][j] = ffma2(lo2(a[i]), lo2(w[j]), acc[i][j]);
-        acc[i][j] = ffma2(hi2(a[i]), hi2(w[j]), acc[i][j]);
-      }
+      for (int j = 0; j < TN; ++j) acc[i][j] = ffma2(lo2(a[i]), lo2(w[j]), acc[i][j]);
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = ffma2(hi2(a[i]), hi2(w[j]), acc[i][j]);
+    }
   }
 }
 

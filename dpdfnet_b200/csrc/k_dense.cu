@@ -172,10 +172,13 @@ __global__ void __launch_bounds__(256, 1) k_gru(GRUParams p) {
         const float4 w1 = *reinterpret_cast<const float4*>(wp + (32 + j * 8) * G_LD + k);
         const float4 w2 = *reinterpret_cast<const float4*>(wp + (64 + j * 8) * G_LD + k);
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
+        for (int i = 0; i < TM; ++i) {          // runs share a[i] (operand-reuse cache), accumulators independent
           a0[i][j] = ffma2(lo2(a[i]), lo2(w0), a0[i][j]);
           a1[i][j] = ffma2(lo2(a[i]), lo2(w1), a1[i][j]);
           a2[i][j] = ffma2(lo2(a[i]), lo2(w2), a2[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
           a0[i][j] = ffma2(hi2(a[i]), hi2(w0), a0[i][j]);
           a1[i][j] = ffma2(hi2(a[i]), hi2(w1), a1[i][j]);
           a2[i][j] = ffma2(hi2(a[i]), hi2(w2), a2[i][j]);

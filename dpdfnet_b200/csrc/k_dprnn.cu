@@ -26,14 +26,19 @@ struct IntraParams {
   int B;
 };
 
-constexpr int ILD = 72;   // smem row stride: 8q + jj bank pattern is conflict-free
+constexpr int ILD = 68;   // smem row stride (floats): 4s + 16u + jj bank pattern of the h exchange is conflict-free
+
+// Position of element k of a 64-float row in shared memory.  The row is stored as [half][q][4]: the eight
+// K-slices (q) of one 128-bit load are contiguous, so every broadcast LDS.128 touches one 128-byte line.
+__device__ __forceinline__ int row_pos(int k) { return ((k >> 2) & 1) * 32 + (k >> 3) * 4 + (k & 3); }
 
 template <int BT>
 __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
   __shared__ __align__(16) float xs[2][BT][ILD];
   __shared__ __align__(16) float hs[2][BT][ILD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = lane & 3, j = warp * 8 + (lane >> 2);
+  // thread = (unit pair {up, up+32}, K-eighth q): 2 units x 6 matrices x 8 k = 96 stationary weights
+  const int q = lane & 7, jj = lane >> 3, up = warp * 4 + jj;
   const int item = blockIdx.x;
   const int br = item / (2 * p.tiles);
   const int dir = (item % (2 * p.tiles)) / p.tiles;
@@ -43,59 +48,56 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
   const float* __restrict__ xg = p.x[br];
   float* __restrict__ hg = p.hcat[br];
 
-  // stationary weights: unit j, K-quarter q, gates r,z,n of W_ih and W_hh
-  float2 wi[3][8], wh[3][8];
+  float2 wi[2][3][4], wh[2][3][4];
   {
     const float* Wih = p.wih[br] + (size_t)dir * 192 * C;
     const float* Whh = p.whh[br] + (size_t)dir * 192 * C;
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      const float4* si = reinterpret_cast<const float4*>(Wih + (size_t)(g * C + j) * C + q * 16);
-      const float4* sh = reinterpret_cast<const float4*>(Whh + (size_t)(g * C + j) * C + q * 16);
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 a = __ldg(si + c), b = __ldg(sh + c);
-        wi[g][2 * c] = lo2(a); wi[g][2 * c + 1] = hi2(a);
-        wh[g][2 * c] = lo2(b); wh[g][2 * c + 1] = hi2(b);
+      for (int g = 0; g < 3; ++g) {
+        const float4* si = reinterpret_cast<const float4*>(Wih + (size_t)(g * C + up + 32 * u) * C + q * 8);
+        const float4* sh = reinterpret_cast<const float4*>(Whh + (size_t)(g * C + up + 32 * u) * C + q * 8);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 a = __ldg(si + c), b = __ldg(sh + c);
+          wi[u][g][2 * c] = lo2(a); wi[u][g][2 * c + 1] = hi2(a);
+          wh[u][g][2 * c] = lo2(b); wh[u][g][2 * c + 1] = hi2(b);
+        }
       }
-    }
   }
+  // after the reduce-scatter lane q finishes (stream q>>1 of the batch, unit up + 32*(q&1))
+  const int myu = q & 1, myj = up + 32 * myu, mypos = row_pos(myj);
   const float* bias = p.bias[br] + dir * 4 * C;
-  const float b_r = __ldg(bias + j), b_z = __ldg(bias + C + j), b_in = __ldg(bias + 2 * C + j), b_hn = __ldg(bias + 3 * C + j);
+  const float b_r = __ldg(bias + myj), b_z = __ldg(bias + C + myj), b_in = __ldg(bias + 2 * C + myj), b_hn = __ldg(bias + 3 * C + myj);
 
   for (int i = tid; i < BT * ILD; i += 256) (&hs[0][0][0])[i] = 0.f;     // h0 = 0 every frame
-
-  // A row holds 64 floats with a 4-float gap after element 31: the four K-quarters of a row then start
-  // in banks {0,16,4,20}, so the broadcast LDS.128 of the four q-lanes never collide.
-  const int qoff = q * 16 + ((q >> 1) << 2);
-  const int jpos = j + ((j >> 5) << 2);
 
   auto prefetch = [&](int t, int buf) {
     const int f = dir ? T - 1 - t : t;
     for (int i = tid; i < BT * 16; i += 256) {
-      const int s = i >> 4, c = (i & 15) * 4;
+      const int s = i >> 4, c = i & 15;
       const int b = b0 + s;
-      float* dst = &xs[buf][s][c + ((c >> 5) << 2)];
-      if (b < p.B) cp_async16(dst, xg + ((size_t)b * T + f) * C + c);
+      float* dst = &xs[buf][s][(c & 1) * 32 + (c >> 1) * 4];
+      if (b < p.B) cp_async16(dst, xg + ((size_t)b * T + f) * C + c * 4);
       else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   auto store_h = [&](int buf, int t) {
     const int f = dir ? T - 1 - t : t;
     for (int i = tid; i < BT * 16; i += 256) {
-      const int s = i >> 4, c = (i & 15) * 4;
+      const int s = i >> 4, c = i & 15;
       const int b = b0 + s;
       if (b < p.B)
-        *reinterpret_cast<float4*>(hg + ((size_t)b * T + f) * 2 * C + dir * C + c) =
-            *reinterpret_cast<const float4*>(&hs[buf][s][c + ((c >> 5) << 2)]);
+        *reinterpret_cast<float4*>(hg + ((size_t)b * T + f) * 2 * C + dir * C + c * 4) =
+            *reinterpret_cast<const float4*>(&hs[buf][s][(c & 1) * 32 + (c >> 1) * 4]);
     }
   };
 
   prefetch(0, 0);
   cp_async_commit();
   int cur = 0;
-  const bool hi = (q & 2) != 0, odd = (q & 1) != 0;
-  struct Frag { float4 x[4], h[4]; };
+  struct Frag { float4 x[2], h[2]; };
   for (int t = 0; t < T; ++t) {
     cp_async_wait<0>();
     __syncthreads();                       // x_t landed, h_t complete, previous buffers free
@@ -106,65 +108,91 @@ __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
     const float(*hb)[ILD] = hs[cur];
     float(*hn)[ILD] = hs[cur ^ 1];
     auto load_frag = [&](Frag& f, int row) {
-      const float4* xp = reinterpret_cast<const float4*>(&xb[row][qoff]);
-      const float4* hp = reinterpret_cast<const float4*>(&hb[row][qoff]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { f.x[c] = xp[c]; f.h[c] = hp[c]; }
+      for (int c = 0; c < 2; ++c) {
+        f.x[c] = *reinterpret_cast<const float4*>(&xb[row][c * 32 + q * 4]);
+        f.h[c] = *reinterpret_cast<const float4*>(&hb[row][c * 32 + q * 4]);
+      }
     };
     Frag fr;
     load_frag(fr, 0);
 #pragma unroll 2
     for (int sb = 0; sb < BT / 4; ++sb) {
-      float v[4][4];
+      float v[4][2][4];                                  // [stream][unit][gate r,z,in,hn]
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         Frag nx;                                         // software pipeline: next stream's operands
         load_frag(nx, min(sb * 4 + s + 1, BT - 1));      // are in flight while this one is multiplied
-        float2 ar = make_float2(0.f, 0.f), az = ar, ain = ar, ahn = ar;
+        // Issue order matters: the register file feeds one 64-bit operand per lane per cycle, so an FFMA2 only
+        // sustains its 2-cycle rate when one of its three operand pairs comes from the operand-reuse cache.
+        // Runs of six FFMA2 share the same x (or h) pair; the six accumulators of a run are independent.
+        float2 ar[2], az[2], ain[2], ahn[2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int u = 0; u < 2; ++u) ar[u] = az[u] = ain[u] = ahn[u] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
           const float4 xv = fr.x[c], hv = fr.h[c];
-          ar = ffma2(wi[0][2 * c], lo2(xv), ar);
-          az = ffma2(wi[1][2 * c], lo2(xv), az);
-          ain = ffma2(wi[2][2 * c], lo2(xv), ain);
-          ahn = ffma2(wh[2][2 * c], lo2(hv), ahn);
-          ar = ffma2(wh[0][2 * c], lo2(hv), ar);
-          az = ffma2(wh[1][2 * c], lo2(hv), az);
-          ar = ffma2(wi[0][2 * c + 1], hi2(xv), ar);
-          az = ffma2(wi[1][2 * c + 1], hi2(xv), az);
-          ain = ffma2(wi[2][2 * c + 1], hi2(xv), ain);
-          ahn = ffma2(wh[2][2 * c + 1], hi2(hv), ahn);
-          ar = ffma2(wh[0][2 * c + 1], hi2(hv), ar);
-          az = ffma2(wh[1][2 * c + 1], hi2(hv), az);
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
+            const float2 xo = hl ? hi2(xv) : lo2(xv);
+            const float2 ho = hl ? hi2(hv) : lo2(hv);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              ar[u] = ffma2(wi[u][0][2 * c + hl], xo, ar[u]);
+              az[u] = ffma2(wi[u][1][2 * c + hl], xo, az[u]);
+              ain[u] = ffma2(wi[u][2][2 * c + hl], xo, ain[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              ar[u] = ffma2(wh[u][0][2 * c + hl], ho, ar[u]);
+              az[u] = ffma2(wh[u][1][2 * c + hl], ho, az[u]);
+              ahn[u] = ffma2(wh[u][2][2 * c + hl], ho, ahn[u]);
+            }
+          }
         }
-        v[s][0] = ar.x + ar.y;
-        v[s][1] = az.x + az.y;
-        v[s][2] = ain.x + ain.y;
-        v[s][3] = ahn.x + ahn.y;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          v[s][u][0] = ar[u].x + ar[u].y;
+          v[s][u][1] = az[u].x + az[u].y;
+          v[s][u][2] = ain[u].x + ain[u].y;
+          v[s][u][3] = ahn[u].x + ahn[u].y;
+        }
         fr = nx;
       }
-      // reduce-scatter over the 4 K-lanes: lane q ends with the complete sums of stream sb*4+q
-      float u[2][4], r[4];
+      // reduce-scatter over the 8 K-lanes (xor 4, 2, 1): lane q ends with the four complete gate sums of
+      // (stream sb*4 + (q>>1), unit up + 32*(q&1))
+      float w2[2][2][4], w1[2][4], r[4];
+      const bool b4 = (q & 4) != 0, b2 = (q & 2) != 0, b1 = (q & 1) != 0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          const float send = hi ? v[s2][g] : v[s2 + 2][g];
-          const float keep = hi ? v[s2 + 2][g] : v[s2][g];
-          u[s2][g] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float send = b4 ? v[s2][u][g] : v[s2 + 2][u][g];
+            const float keep = b4 ? v[s2 + 2][u][g] : v[s2][u][g];
+            w2[s2][u][g] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float send = b2 ? w2[0][u][g] : w2[1][u][g];
+          const float keep = b2 ? w2[1][u][g] : w2[0][u][g];
+          w1[u][g] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
         }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float send = odd ? u[0][g] : u[1][g];
-        const float keep = odd ? u[1][g] : u[0][g];
+        const float send = b1 ? w1[0][g] : w1[1][g];
+        const float keep = b1 ? w1[1][g] : w1[0][g];
         r[g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
       }
-      const int srow = sb * 4 + q;
-      const float hprev = hb[srow][jpos];
+      const int srow = sb * 4 + (q >> 1);
+      const float hprev = hb[srow][mypos];
       const float rg = sigmoidf_(r[0] + b_r);
       const float zg = sigmoidf_(r[1] + b_z);
       const float ng = tanhf_(r[2] + b_in + rg * (r[3] + b_hn));
-      hn[srow][jpos] = (1.0f - zg) * ng + zg * hprev;
+      hn[srow][mypos] = (1.0f - zg) * ng + zg * hprev;
     }
     cur ^= 1;
   }

@@ -273,6 +273,12 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             t[f"{q}.inter.fc_b"] = sd[f"{p}.fc_inter.bias"]
             t[f"{q}.inter.ln_g"] = sd[f"{p}.ln_inter.weight"]
             t[f"{q}.inter.ln_b"] = sd[f"{p}.ln_inter.bias"]
+            # tensor-core (tcgen05, 3xTF32) operand images of the position-parallel matrices of the block:
+            # fc_intra [64x128], the six inter-GRU gate slabs [64x64] (Wih r,z,n then Whh r,z,n), fc_inter [64x64]
+            wih, whh = sd[f"{p}.inter_gru.weight_ih_l0"], sd[f"{p}.inter_gru.weight_hh_l0"]
+            t[f"{q}.tc.fc_w"] = umma_operand(sd[f"{p}.fc_intra.weight"])
+            t[f"{q}.tc.gates"] = np.concatenate([umma_operand(m[g * C:(g + 1) * C]) for m in (wih, whh) for g in range(3)])
+            t[f"{q}.tc.fc2_w"] = umma_operand(sd[f"{p}.fc_inter.weight"])
 
     def gl(out: str, prefix: str, groups: int):
         t[f"{out}.w"], t[f"{out}.b"] = _gl_pack(sd, prefix, groups)
@@ -321,6 +327,32 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
     gl("df_dec.df_skip", "df_dec.df_skip", 16)
     gl("df_dec.df_out", "df_dec.df_out.0", 16)
     return OrderedDict((k, np.ascontiguousarray(v, dtype=np.float32)) for k, v in t.items())
+
+
+def tf32_split(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """w = hi + lo (+ O(2^-24 |w|)) with hi, lo exactly representable in TF32 (round-to-nearest, ties away:
+    ``cvt.rna.tf32.f32``).  Three tensor-core passes a_hi*b_hi + a_lo*b_hi + a_hi*b_lo then reproduce the
+    FP32 product to ~2^-22 relative ("3xTF32")."""
+    def rna(x):
+        u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+        return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    hi = rna(w)
+    return hi, rna(w - hi)
+
+
+def umma_kmajor(mat: np.ndarray) -> np.ndarray:
+    """[rows, K] -> tcgen05 K-major SWIZZLE_NONE operand image: 8x4-float core matrices (128 B), core
+    matrices adjacent in K contiguous (LBO = 128 B), 8-row groups (K/4)*128 B apart (SBO)."""
+    n, k = mat.shape
+    assert n % 8 == 0 and k % 4 == 0
+    return np.ascontiguousarray(mat.reshape(n // 8, 8, k // 4, 4).transpose(0, 2, 1, 3)).reshape(-1)
+
+
+def umma_operand(mat: np.ndarray) -> np.ndarray:
+    """hi image followed by lo image of a weight matrix [N, K] (B operand of D = A * W^T)."""
+    hi, lo = tf32_split(mat)
+    return np.concatenate([umma_kmajor(hi), umma_kmajor(lo)])
 
 
 def serialize(tensors: Mapping[str, np.ndarray]) -> bytes:
