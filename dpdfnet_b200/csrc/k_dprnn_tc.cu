@@ -68,60 +68,21 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// float offset of element (r, k) of a [rows][K] operand image
-template <int K>
-__device__ __forceinline__ int core_off(int r, int k) { return (r >> 3) * (K * 8) + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }
-
-// Stage a [128][K] global tile into hi / lo operand images.  A warp moves an 8-row x 16-float block per
-// iteration: 64 B contiguous per row from HBM/L2, 512 contiguous bytes (four core matrices) into smem.
-template <int K, typename RowPtr>
-__device__ __forceinline__ void stage_split(float* hi, float* lo, int valid, RowPtr row_ptr, int warp, int lane) {
-  const int rr = lane >> 2, cc = lane & 3;
-  constexpr int KB = K / 16;
-#pragma unroll 4
-  for (int blk = warp; blk < 16 * KB; blk += 4) {
-    const int rg = blk / KB, kb = blk % KB;
-    const int r = rg * 8 + rr, k = kb * 16 + cc * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < valid) v = __ldg(reinterpret_cast<const float4*>(row_ptr(r) + k));
-    float4 h, l;
-    split4(v, h, l);
-    const int off = rg * (K * 8) + (kb * 4 + cc) * 32 + rr * 4;
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
-  }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, async proxy), completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-// Copy a [128][64] plain-float operand image (optionally hi + lo) back to row-major global memory, coalesced.
-template <typename RowPtr, typename Pred>
-__device__ __forceinline__ void unstage64(const float* a, const float* b, int valid, RowPtr row_ptr, Pred pred, int warp, int lane) {
-  const int rr = lane >> 2, cc = lane & 3;
-  for (int blk = warp; blk < 16 * 4; blk += 4) {
-    const int rg = blk >> 2, kb = blk & 3;
-    const int r = rg * 8 + rr, k = kb * 16 + cc * 4;
-    if (r >= valid || !pred(r)) continue;
-    const int off = rg * 512 + (kb * 4 + cc) * 32 + rr * 4;
-    float4 v = *reinterpret_cast<const float4*>(a + off);
-    if (b) {
-      const float4 w = *reinterpret_cast<const float4*>(b + off);
-      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-    }
-    *reinterpret_cast<float4*>(row_ptr(r) + k) = v;
-  }
-}
+// float offset of element (r, k) of a [128][64] operand image (K-major, SWIZZLE_NONE, SBO = 2048 B)
+__device__ __forceinline__ int core_off64(int r, int k) { return (r >> 3) * 512 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }
 
-__device__ __forceinline__ void layernorm64(float (&v)[64], const float* g, const float* b) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 64; ++i) s += v[i];
-  const float mean = s * (1.0f / 64.0f);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 64; ++i) { v[i] -= mean; q += v[i] * v[i]; }
-  const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < 64; ++i) v[i] = v[i] * rstd * g[i] + b[i];
-}
+constexpr int TC_NT = 512;        // 16 warps: warp w -> TMEM lane quadrant w & 3, 16-column group w >> 2
+constexpr int IMG = 8192;         // floats of one [128][64] operand image (32 KB)
 
 }  // namespace
 
@@ -132,7 +93,7 @@ struct PostTcBranch {
   float* hstate;          // inter-GRU state of this block: + slot*per_slot + f*64
   long long per_slot;
   int Fp;
-  const float *tc_fc_w, *tc_gates, *tc_fc2_w;         // operand images (hi | lo)
+  const float *tc_fc_w, *tc_gates, *tc_fc2_w;         // [64x64] weight slabs, each hi image | lo image (32 KB)
   const float *fc_b, *ln_g, *ln_b, *bias, *fc2_b, *ln2_g, *ln2_b;
 };
 struct PostTcParams {
@@ -141,33 +102,37 @@ struct PostTcParams {
   int tiles0, B;
 };
 
-constexpr int TC_A = 32768;       // floats: activation operand region (128 KB)
-constexpr int TC_W = 16384;       // floats: weight operand region (64 KB)
-constexpr size_t POST_TC_SMEM = (size_t)(TC_A + TC_W + 640) * sizeof(float) + 128 * sizeof(long long) + 128 * sizeof(int) + 64;
+constexpr size_t POST_TC_SMEM = (size_t)(4 * IMG + 2 * IMG + 640 + 1024) * sizeof(float) + 128 * sizeof(long long) +
+                                128 * sizeof(int) + 64;
 
-__global__ void __launch_bounds__(128, 1) k_dprnn_post_tc(PostTcParams p) {
+// One CTA = one 128-row tile.  Thread 0 is the single MMA issuer and streams the nine 32 KB weight slabs of the
+// block (fc_intra K-halves, six GRU gate slabs, fc_inter) through a two-buffer ring with 1-D bulk copies that
+// complete on mbarriers, two slabs ahead of the tensor core; the other 511 threads never wait for weights.
+__global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
   extern __shared__ __align__(128) float smem[];
-  float* RA = smem;
-  float* RW = RA + TC_A;
-  float* sp = RW + TC_W;
-  long long* s_hoff = reinterpret_cast<long long*>(sp + 640);
+  float* RA = smem;                                 // four activation operand images
+  float* RW = RA + 4 * IMG;                         // two weight slab buffers
+  float* sp = RW + 2 * IMG;                         // small parameters
+  float* red = sp + 640;                            // [2][4][128] LayerNorm partials
+  long long* s_hoff = reinterpret_cast<long long*>(red + 1024);
   int* s_commit = reinterpret_cast<int*>(s_hoff + 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_commit + 128);     // [0] phase barrier, [1],[2] weight-slab buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_commit + 128);   // [0,1] slab full, [2,3] slab consumed, [4] phase result ready
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
   const int bi = (int)blockIdx.x >= p.tiles0 ? 1 : 0;
   const PostTcBranch& q = p.br[bi];
   const long long row0 = (long long)(blockIdx.x - (bi ? p.tiles0 : 0)) * 128;
   const long long nrows = (long long)p.B * q.Fp;
   const int valid = (int)min((long long)128, nrows - row0);
 
-  {
+  if (tid < 128) {
     long long off = 0;
     int commit = 0;
     if (tid < valid) {
-      const long long row = row0 + tid;
-      const int b = (int)(row / q.Fp), f = (int)(row % q.Fp);
+      const long long r = row0 + tid;
+      const int b = (int)(r / q.Fp), f = (int)(r % q.Fp);
       off = (long long)io_slot(p.io, b) * q.per_slot + (long long)f * C;
       commit = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) ? 0 : 1;
     }
@@ -178,141 +143,183 @@ __global__ void __launch_bounds__(128, 1) k_dprnn_post_tc(PostTcParams p) {
     sp[tid] = q.fc_b[tid]; sp[64 + tid] = q.ln_g[tid]; sp[128 + tid] = q.ln_b[tid];
     sp[448 + tid] = q.fc2_b[tid]; sp[512 + tid] = q.ln2_g[tid]; sp[576 + tid] = q.ln2_b[tid];
   }
-  sp[192 + tid] = q.bias[tid];
-  sp[320 + tid] = q.bias[128 + tid];
-  if (tid == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); }
+  if (tid < 256) sp[192 + tid] = q.bias[tid];
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  __syncthreads();                                       // barriers initialised, s_hoff visible
 
-  // ---- stage phase-1 operands: hcat tile (split on the fly) and the fc_intra operand image -------------------
+  // ---- weight slab ring (thread 0 only) --------------------------------------------------------------------
+  auto slab_src = [&](int i) -> const float* {
+    if (i < 2) return q.tc_fc_w + (size_t)i * IMG;
+    if (i == 8) return q.tc_fc2_w;
+    const int pidx = i - 2;                                // processing order r(y),r(h),z(y),z(h),n(y),n(h)
+    return q.tc_gates + (size_t)((pidx & 1) ? 3 + (pidx >> 1) : (pidx >> 1)) * IMG;
+  };
+  auto load_slab = [&](int i) {
+    const int buf = i & 1;
+    if (i >= 2) mbar_wait(bars + 2 + buf, ((i - 2) >> 1) & 1);      // MMAs of the previous tenant have completed
+    mbar_expect_tx(bars + buf, IMG * 4);
+    bulk_g2s(RW + buf * IMG, slab_src(i), IMG * 4, bars + buf);
+  };
+  if (tid == 0) { load_slab(0); load_slab(1); }
+
+  // ---- stage the hcat tile as two K=64 operand image pairs (split on the fly) --------------------------------
+  const int rr = lane >> 2, cc = lane & 3;
   {
     const float* hc = q.hcat + row0 * 2 * C;
-    stage_split<128>(RA, RA + 16384, valid, [&](int r) { return hc + (size_t)r * 2 * C; }, warp, lane);
-    for (int i = tid; i < TC_W / 4; i += 128) cp_async16(RW + i * 4, q.tc_fc_w + i * 4);
-    cp_async_commit();
-    cp_async_wait<0>();
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                          // 128 blocks of 8 rows x 16 floats, 8 per warp, all in flight
+      const int blk = warp + 16 * i, rg = blk >> 3, kb = blk & 7;
+      const int r = rg * 8 + rr;
+      v[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(hc + (size_t)r * 2 * C + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int blk = warp + 16 * i, rg = blk >> 3, kb = blk & 7;
+      float4 h, l;
+      split4(v[i], h, l);
+      const int off = (kb >> 2) * 2 * IMG + rg * 512 + ((kb & 3) * 4 + cc) * 32 + rr * 4;
+      *reinterpret_cast<float4*>(RA + off) = h;
+      *reinterpret_cast<float4*>(RA + IMG + off) = l;
+    }
+  }
+  // prefetch what the first epilogue needs while the tensor core works: residual input and h_prev
+  float4 xv[4], hv[4];
+  {
+    const float* xr = q.xin + (size_t)(row0 + row) * C + cg * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xv[c] = row < valid ? __ldg(reinterpret_cast<const float4*>(xr + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                          // 64 blocks, 4 per warp
+      const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+      const int r = rg * 8 + rr;
+      hv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16) + cg * 16;
   constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // M=128, N=64, tf32, f32 acc
   const uint32_t a_base = smem_u32(RA), w_base = smem_u32(RW);
 
-  // D[tmem_col .. +64) (+)= A[128][K] * W[64][K]^T, three TF32 passes per 8-wide k-step (single issuing thread)
-  auto gemm3 = [&](uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int K, uint32_t col, uint32_t accumulate) {
-    const uint32_t sbo = (uint32_t)K * 32;            // (K/4) * 128 B
-    for (int ks = 0; ks < K / 8; ++ks) {
-      const uint64_t dah = umma_desc(a_hi + ks * 256, sbo), dal = umma_desc(a_lo + ks * 256, sbo);
-      const uint64_t dbh = umma_desc(b_hi + ks * 256, sbo), dbl = umma_desc(b_lo + ks * 256, sbo);
+  // slab i: D[col .. col+64) (+)= A[128][64] * W_i[64][64]^T, three TF32 passes per 8-wide k-step
+  auto run_slab = [&](int i, int a_img, uint32_t col, uint32_t accumulate) {
+    const int buf = i & 1;
+    mbar_wait(bars + buf, (i >> 1) & 1);                   // slab landed (async proxy write -> async proxy read)
+    const uint32_t ah = a_base + a_img * (IMG * 4), al = ah + IMG * 4;
+    const uint32_t bh = w_base + buf * (IMG * 4), bl = bh + IMG * 2;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t dah = umma_desc(ah + ks * 256, 2048), dal = umma_desc(al + ks * 256, 2048);
+      const uint64_t dbh = umma_desc(bh + ks * 256, 2048), dbl = umma_desc(bl + ks * 256, 2048);
       umma_tf32(tmem + col, dah, dbh, IDESC, accumulate);
       umma_tf32(tmem + col, dal, dbh, IDESC, 1);
       umma_tf32(tmem + col, dah, dbl, IDESC, 1);
       accumulate = 1;
     }
+    umma_commit(bars + 2 + buf);
   };
 
-  // ---- phase 1: acc[0..64) = hcat * fc_intra^T --------------------------------------------------------------
+  // ---- phase 1: acc[0,64) = hcat * fc_intra^T ---------------------------------------------------------------
   if (tid == 0) {
-    gemm3(a_base, a_base + 65536, w_base, w_base + 32768, 128, 0, 0);
-    umma_commit(bars);
+    run_slab(0, 0, 0, 0);
+    run_slab(1, 2, 0, 1);
+    umma_commit(bars + 4);
+    load_slab(2);
+    load_slab(3);
   }
-  mbar_wait(bars, 0);
+  mbar_wait(bars + 4, 0);
   tc_fence_after();
 
-  float* y_hi = RA;                 // [128][64] operand images, K = 64
-  float* y_lo = RA + 8192;
-  float* h_hi = RA + 16384;
-  float* h_lo = RA + 24576;
+  float* y_hi = RA;
+  float* y_lo = RA + IMG;
+  float* h_hi = RA + 2 * IMG;
+  float* h_lo = RA + 3 * IMG;
+  // row statistics over 64 columns held by the four column-group warps of a lane quadrant
+  auto layernorm16 = [&](float (&v)[16], const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    red[cg * 128 + row] = s;
+    __syncthreads();
+    const float mean = (red[row] + red[128 + row] + red[256 + row] + red[384 + row]) * (1.0f / 64.0f);
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] -= mean; qq += v[i] * v[i]; }
+    red[512 + cg * 128 + row] = qq;
+    __syncthreads();
+    const float rstd = rsqrtf((red[512 + row] + red[640 + row] + red[768 + row] + red[896 + row]) * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * g[cg * 16 + i] + b[cg * 16 + i];
+  };
   {
-    float v[64];
+    float v[16];
+    tmem_ld16(lane_base, v);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float t[16];
-      tmem_ld16(lane_base + c * 16, t);
+    for (int i = 0; i < 16; ++i) v[i] += sp[cg * 16 + i];
+    layernorm16(v, sp + 64, sp + 128);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[c * 16 + i] = t[i] + sp[c * 16 + i];
-    }
-    layernorm64(v, sp + 64, sp + 128);
-    const float* xr = q.xin + (size_t)(row0 + tid) * C;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tid < valid) x = __ldg(reinterpret_cast<const float4*>(xr + c * 4));
-      const float4 y = make_float4(v[c * 4] + x.x, v[c * 4 + 1] + x.y, v[c * 4 + 2] + x.z, v[c * 4 + 3] + x.w);
+    for (int c = 0; c < 4; ++c) {                           // y = LN(...) + x, staged as the hi / lo operand of the gate GEMMs
+      const float4 y = make_float4(v[c * 4] + xv[c].x, v[c * 4 + 1] + xv[c].y, v[c * 4 + 2] + xv[c].z, v[c * 4 + 3] + xv[c].w);
       float4 h, l;
       split4(y, h, l);
-      const int off = core_off<64>(tid, c * 4);
-      *reinterpret_cast<float4*>(y_hi + off) = h;       // all MMAs that read the hcat image have completed
+      const int off = core_off64(row, cg * 16 + c * 4);
+      *reinterpret_cast<float4*>(y_hi + off) = h;
       *reinterpret_cast<float4*>(y_lo + off) = l;
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                           // h_prev tile (loaded before the wait) -> hi / lo images
+      const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+      float4 h, l;
+      split4(hv[i], h, l);
+      const int off = rg * 512 + (kb * 4 + cc) * 32 + rr * 4;
+      *reinterpret_cast<float4*>(h_hi + off) = h;
+      *reinterpret_cast<float4*>(h_lo + off) = l;
+    }
   }
-  __syncthreads();                                        // every thread is done reading the fc_intra image / hcat rows
-  // h_prev tile (split) + first two gate slabs
-  stage_split<64>(h_hi, h_lo, valid, [&](int r) { return q.hstate + s_hoff[r]; }, warp, lane);
-  auto load_slab = [&](int pidx, int buf) {               // processing order -> slab id in the blob (Wih r,z,n | Whh r,z,n)
-    const int slab = (pidx & 1) ? 3 + (pidx >> 1) : (pidx >> 1);
-    const float* src = q.tc_gates + (size_t)slab * 8192;
-    float* dst = RW + buf * 8192;
-    for (int i = tid; i < 2048; i += 128) cp_async16(dst + i * 4, src + i * 4);
-    cp_async_commit();
-  };
-  load_slab(0, 0);
-  load_slab(1, 1);
-  cp_async_wait<0>();
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 
-  // ---- phase 2: inter-frame GRU gate pre-activations in TMEM: r [64,128) z [128,192) in [192,256) hn [256,320) ---
-  const uint32_t yh = a_base, yl = a_base + 32768, hh = a_base + 65536, hl = a_base + 98304;
-  auto issue_slab = [&](int pidx) {
-    if (tid == 0) {
-      const int buf = pidx & 1;
-      const bool use_h = (pidx & 1) != 0;
-      const int gate = pidx >> 1;                                   // 0 r, 1 z, 2 n
-      const uint32_t col = gate < 2 ? 64 + 64 * gate : (use_h ? 256 : 192);
-      const uint32_t acc = (gate < 2 && use_h) ? 1u : 0u;
-      const uint32_t wb = w_base + buf * 32768;
-      gemm3(use_h ? hh : yh, use_h ? hl : yl, wb, wb + 16384, 64, col, acc);
-      umma_commit(bars + 1 + buf);
-    }
-  };
-  issue_slab(0);
-  issue_slab(1);
-  for (int pidx = 0; pidx < 4; ++pidx) {
-    mbar_wait(bars + 1 + (pidx & 1), (pidx >> 1) & 1);              // slab pidx consumed -> its buffer is free
-    load_slab(pidx + 2, pidx & 1);
-    cp_async_wait<0>();
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    issue_slab(pidx + 2);
+  // ---- phase 2: GRU gate pre-activations in TMEM: r [64,128) z [128,192) in [192,256) hn [256,320) ------------
+  if (tid == 0) {
+    run_slab(2, 0, 64, 0);    // Wih_r * y
+    run_slab(3, 2, 64, 1);    // Whh_r * h
+    load_slab(4);
+    load_slab(5);
+    run_slab(4, 0, 128, 0);   // Wih_z * y
+    run_slab(5, 2, 128, 1);   // Whh_z * h
+    load_slab(6);
+    load_slab(7);
+    run_slab(6, 0, 192, 0);   // Wih_n * y
+    run_slab(7, 2, 256, 0);   // Whh_n * h
+    umma_commit(bars + 4);
+    load_slab(8);
   }
-  mbar_wait(bars + 1, 0);
-  mbar_wait(bars + 2, 0);
+  mbar_wait(bars + 4, 1);
   tc_fence_after();
-  // prefetch the fc_inter operand image while the gates are evaluated (both slab buffers are free now)
-  for (int i = tid; i < 2048; i += 128) cp_async16(RW + i * 4, q.tc_fc2_w + i * 4);
-  cp_async_commit();
-
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  {
     float gr[16], gz[16], gi[16], gh[16];
-    tmem_ld16(lane_base + 64 + c * 16, gr);
-    tmem_ld16(lane_base + 128 + c * 16, gz);
-    tmem_ld16(lane_base + 192 + c * 16, gi);
-    tmem_ld16(lane_base + 256 + c * 16, gh);
+    tmem_ld16(lane_base + 64, gr);
+    tmem_ld16(lane_base + 128, gz);
+    tmem_ld16(lane_base + 192, gi);
+    tmem_ld16(lane_base + 256, gh);
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
-      const int k = c * 16 + c4 * 4;
-      const int off = core_off<64>(tid, k);
+      const int k = cg * 16 + c4 * 4;
+      const int off = core_off64(row, k);
       const float4 ph = *reinterpret_cast<const float4*>(h_hi + off);
       const float4 pl = *reinterpret_cast<const float4*>(h_lo + off);
       const float hp[4] = {ph.x + pl.x, ph.y + pl.y, ph.z + pl.z, ph.w + pl.w};
@@ -327,37 +334,41 @@ __global__ void __launch_bounds__(128, 1) k_dprnn_post_tc(PostTcParams p) {
       }
       float4 h, l;
       split4(make_float4(hn[0], hn[1], hn[2], hn[3]), h, l);
-      *reinterpret_cast<float4*>(h_hi + off) = h;      // in place: this thread is the only reader of its row
+      *reinterpret_cast<float4*>(h_hi + off) = h;      // in place: this thread is the only reader of these 16 bytes
       *reinterpret_cast<float4*>(h_lo + off) = l;
     }
   }
-  cp_async_wait<0>();
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 
-  // ---- phase 3: acc[320..384) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena ----------
+  // ---- phase 3: acc[320,384) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena -----------
   if (tid == 0) {
-    gemm3(hh, hl, w_base, w_base + 16384, 64, 320, 0);
-    umma_commit(bars);
+    run_slab(8, 2, 320, 0);
+    umma_commit(bars + 4);
   }
-  unstage64(h_hi, h_lo, valid, [&](int r) { return q.hstate + s_hoff[r]; }, [&](int r) { return s_commit[r] != 0; }, warp, lane);
-  mbar_wait(bars, 1);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+    const int r = rg * 8 + rr;
+    if (r < valid && s_commit[r]) {
+      const int off = rg * 512 + (kb * 4 + cc) * 32 + rr * 4;
+      const float4 a = *reinterpret_cast<const float4*>(h_hi + off), b = *reinterpret_cast<const float4*>(h_lo + off);
+      *reinterpret_cast<float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+  }
+  mbar_wait(bars + 4, 0);
   tc_fence_after();
   {
-    float v[64];
+    float v[16];
+    tmem_ld16(lane_base + 320, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += sp[448 + cg * 16 + i];
+    layernorm16(v, sp + 512, sp + 576);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      float t[16];
-      tmem_ld16(lane_base + 320 + c * 16, t);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[c * 16 + i] = t[i] + sp[448 + c * 16 + i];
-    }
-    layernorm64(v, sp + 512, sp + 576);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int off = core_off<64>(tid, c * 4);
+      const int off = core_off64(row, cg * 16 + c * 4);
       const float4 a = *reinterpret_cast<const float4*>(y_hi + off);
       const float4 b = *reinterpret_cast<const float4*>(y_lo + off);
       *reinterpret_cast<float4*>(y_hi + off) =
@@ -367,7 +378,14 @@ __global__ void __launch_bounds__(128, 1) k_dprnn_post_tc(PostTcParams p) {
   tc_fence_before();
   __syncthreads();
   float* xo = q.xout + row0 * C;
-  unstage64(y_hi, nullptr, valid, [&](int r) { return xo + (size_t)r * C; }, [](int) { return true; }, warp, lane);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                             // coalesced write-out of the block output
+    const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+    const int r = rg * 8 + rr;
+    if (r < valid)
+      *reinterpret_cast<float4*>(xo + (size_t)r * C + kb * 16 + cc * 4) =
+          *reinterpret_cast<const float4*>(y_hi + rg * 512 + (kb * 4 + cc) * 32 + rr * 4);
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
@@ -387,7 +405,7 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   fill(p.br[1], e.w.dprnn_erb[blk], e.sc.hcat_e, blk == 0 ? e.sc.e3 : e.sc.xe, e.sc.xe, e.st.inter_erb, e.d.fe[3]);
   p.tiles0 = (int)(((long long)B * (NDF / 2) + 127) / 128);
   const int tiles1 = (int)(((long long)B * e.d.fe[3] + 127) / 128);
-  k_dprnn_post_tc<<<p.tiles0 + tiles1, 128, POST_TC_SMEM, st>>>(p);
+  k_dprnn_post_tc<<<p.tiles0 + tiles1, TC_NT, POST_TC_SMEM, st>>>(p);
 }
 
 void init_dprnn_tc_kernels() {

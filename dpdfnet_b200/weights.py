@@ -274,9 +274,10 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             t[f"{q}.inter.ln_g"] = sd[f"{p}.ln_inter.weight"]
             t[f"{q}.inter.ln_b"] = sd[f"{p}.ln_inter.bias"]
             # tensor-core (tcgen05, 3xTF32) operand images of the position-parallel matrices of the block:
-            # fc_intra [64x128], the six inter-GRU gate slabs [64x64] (Wih r,z,n then Whh r,z,n), fc_inter [64x64]
+            # nine [64x64] slabs (hi | lo): fc_intra K-halves, inter-GRU gates (Wih r,z,n then Whh r,z,n), fc_inter
             wih, whh = sd[f"{p}.inter_gru.weight_ih_l0"], sd[f"{p}.inter_gru.weight_hh_l0"]
-            t[f"{q}.tc.fc_w"] = umma_operand(sd[f"{p}.fc_intra.weight"])
+            fcw = sd[f"{p}.fc_intra.weight"]
+            t[f"{q}.tc.fc_w"] = np.concatenate([umma_operand(fcw[:, :C]), umma_operand(fcw[:, C:])])   # two K=64 slabs
             t[f"{q}.tc.gates"] = np.concatenate([umma_operand(m[g * C:(g + 1) * C]) for m in (wih, whh) for g in range(3)])
             t[f"{q}.tc.fc2_w"] = umma_operand(sd[f"{p}.fc_inter.weight"])
 
