@@ -372,7 +372,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   }
   {
     GRUProblem g{c.g0, e.st.h_enc, H, w.enc_gru, c.henc};
-    RUN("gru", launch_gru(e, &g, 1, B, st)); n += 2;
+    RUN("gru", launch_gru(e, &g, 1, B, st)); ++n;
   }
   {
     GLProblem q = glp(w.enc_out, c.henc, H, c.emb, 512, 1);
@@ -384,9 +384,11 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   }
   {
     GRUProblem g[2] = {{c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1}};
-    RUN("gru", launch_gru(e, g, 2, B, st)); n += 3;
+    RUN("gru", launch_gru(e, g, 2, B, st)); ++n;
     GRUProblem g2[2] = {{c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
-    RUN("gru", launch_gru(e, g2, 2, B, st)); n += 3;
+    RUN("gru", launch_gru(e, g2, 2, B, st)); ++n;
+    GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc}, g[0], g[1], g2[0], g2[1]};
+    RUN("gru_commit", launch_gru_commit(e, all, 5, B, st)); ++n;
   }
   {
     GLProblem pr[2] = {glp(w.erbdec_out, c.herb2, H, c.ed, 512, 1), glp(w.df_skip, c.emb, 512, c.cc, H, 0)};

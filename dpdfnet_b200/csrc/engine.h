@@ -123,6 +123,7 @@ struct GRUProblem {
   float* hout;      // [B][256]
 };
 void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st);
+void launch_gru_commit(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st);   // nprob <= 5
 
 // ---- the engine -----------------------------------------------------------------------------
 struct Engine {

@@ -85,62 +85,73 @@ __global__ void __launch_bounds__(256, 2) k_sepconv(SepParams p) {
   if (tid < 16) cp_async16(bs + tid * 4, q.bias + tid * 4);
   cp_async_commit();
 
-  // prologue: A[row][c]
-#pragma unroll 2
-  for (int it = tid; it < SEP_ROWS * 16; it += 256) {
-    const int r = it >> 4, c = (it & 15) * 4;
-    const long long row = row0 + r;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < nrows) {
-      const int b = (int)(row / q.Fout), fo = (int)(row % q.Fout);
-      if (q.mode == 0) {
-        int fc, j;
-        if (q.up > 1) { fc = fo / q.up; j = fo % q.up; } else { fc = fo * q.stride; j = 0; }
-        const float* in1 = q.in1 + (size_t)b * q.Fin * C;
-        const float* in2 = q.in2 ? q.in2 + (size_t)b * q.Fin * C : nullptr;
+  // prologue: A[row][c].  A thread keeps the same 4 channels for all of its rows, so the depthwise / grouped
+  // 3x3 taps and the pathway affine are loaded once; all rows' activation loads are issued back to back.
+  {
+    const int c = (tid & 15) * 4;
+    const int nw = q.mode == 0 ? 3 * q.up : 9;
+    float4 wt[9];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          const int fi = fc + t - 1;
-          if (fi < 0 || fi >= q.Fin) continue;
-          float4 v = __ldg(reinterpret_cast<const float4*>(in1 + (size_t)fi * C + c));
-          if (in2) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(in2 + (size_t)fi * C + c));
-            const float4 a = __ldg(reinterpret_cast<const float4*>(q.pa + c));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(q.pb + c));
-            v.x += fmaxf(fmaf(u.x, a.x, bb.x), 0.f);
-            v.y += fmaxf(fmaf(u.y, a.y, bb.y), 0.f);
-            v.z += fmaxf(fmaf(u.z, a.z, bb.z), 0.f);
-            v.w += fmaxf(fmaf(u.w, a.w, bb.w), 0.f);
+    for (int t = 0; t < 9; ++t) wt[t] = t < nw ? __ldg(reinterpret_cast<const float4*>(q.dw + (size_t)t * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+    if (q.mode == 0 && q.in2) {
+      pa = __ldg(reinterpret_cast<const float4*>(q.pa + c));
+      pb = __ldg(reinterpret_cast<const float4*>(q.pb + c));
+    }
+#pragma unroll
+    for (int i = 0; i < SEP_ROWS / 16; ++i) {
+      const int r = (tid >> 4) + 16 * i;
+      const long long row = row0 + r;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < nrows) {
+        const int b = (int)(row / q.Fout), fo = (int)(row % q.Fout);
+        if (q.mode == 0) {
+          int fc, j;
+          if (q.up > 1) { fc = fo / q.up; j = fo % q.up; } else { fc = fo * q.stride; j = 0; }
+          const float* in1 = q.in1 + (size_t)b * q.Fin * C;
+          const float* in2 = q.in2 ? q.in2 + (size_t)b * q.Fin * C : nullptr;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) {
+            const int fi = fc + t - 1;
+            if (fi < 0 || fi >= q.Fin) continue;
+            float4 v = __ldg(reinterpret_cast<const float4*>(in1 + (size_t)fi * C + c));
+            if (in2) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(in2 + (size_t)fi * C + c));
+              v.x += fmaxf(fmaf(u.x, pa.x, pb.x), 0.f);
+              v.y += fmaxf(fmaf(u.y, pa.y, pb.y), 0.f);
+              v.z += fmaxf(fmaf(u.z, pa.z, pb.z), 0.f);
+              v.w += fmaxf(fmaf(u.w, pa.w, pb.w), 0.f);
+            }
+            const float4 w = j == 0 ? wt[t] : (j == 1 ? wt[3 + t] : wt[6 + t]);
+            acc.x = fmaf(w.x, v.x, acc.x);
+            acc.y = fmaf(w.y, v.y, acc.y);
+            acc.z = fmaf(w.z, v.z, acc.z);
+            acc.w = fmaf(w.w, v.w, acc.w);
           }
-          const float4 w = __ldg(reinterpret_cast<const float4*>(q.dw + (size_t)(j * 3 + t) * C + c));
-          acc.x = fmaf(w.x, v.x, acc.x);
-          acc.y = fmaf(w.y, v.y, acc.y);
-          acc.z = fmaf(w.z, v.z, acc.z);
-          acc.w = fmaf(w.w, v.w, acc.w);
-        }
-      } else {
-        const int slot = io_slot(p.io, b);
-        const int pos = p.st.pos[slot];
-        const float* ring = p.st.df_ring + (size_t)slot * 3 * 2 * NDF;
-        const int plane = c >= 32 ? 1 : 0;
+        } else {
+          const int slot = io_slot(p.io, b);
+          const int pos = p.st.pos[slot];
+          const float* ring = p.st.df_ring + (size_t)slot * 3 * 2 * NDF;
+          const int plane = c >= 32 ? 1 : 0;
 #pragma unroll
-        for (int kt = 0; kt < 3; ++kt) {
-          const float* rowp = ring + (((pos + 1 + kt) % 3) * 2 + plane) * NDF;
+          for (int kt = 0; kt < 3; ++kt) {
+            const float* rowp = ring + (((pos + 1 + kt) % 3) * 2 + plane) * NDF;
 #pragma unroll
-          for (int kf = 0; kf < 3; ++kf) {
-            const int fi = fo + kf - 1;
-            if (fi < 0 || fi >= NDF) continue;
-            const float x = rowp[fi];
-            const float4 w = __ldg(reinterpret_cast<const float4*>(q.dw + (size_t)(kt * 3 + kf) * C + c));
-            acc.x = fmaf(w.x, x, acc.x);
-            acc.y = fmaf(w.y, x, acc.y);
-            acc.z = fmaf(w.z, x, acc.z);
-            acc.w = fmaf(w.w, x, acc.w);
+            for (int kf = 0; kf < 3; ++kf) {
+              const int fi = fo + kf - 1;
+              if (fi < 0 || fi >= NDF) continue;
+              const float x = rowp[fi];
+              const float4 w = wt[kt * 3 + kf];
+              acc.x = fmaf(w.x, x, acc.x);
+              acc.y = fmaf(w.y, x, acc.y);
+              acc.z = fmaf(w.z, x, acc.z);
+              acc.w = fmaf(w.w, x, acc.w);
+            }
           }
         }
       }
+      *reinterpret_cast<float4*>(As + r * SEP_LD + c) = acc;
     }
-    *reinterpret_cast<float4*>(As + r * SEP_LD + c) = acc;
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -239,46 +250,73 @@ struct DfPathParams {
   int B;
 };
 
+// One warp = four consecutive bins of a stream; lane = (bin, 4-channel chunk).  Every load of the 5-frame c0 ring
+// is a fully used 128-byte line per bin, weights are broadcast float4 from shared memory, the 8 chunk-lanes of a
+// bin are reduced with xor shuffles.  HBM-bound on the ring (120 KB per stream-frame).
 __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= p.B * NDF) return;
-  const int b = warp / NDF, f = warp % NDF;
+  __shared__ __align__(16) float ws[2 * ORD * 8 * 5 * 4];        // [g][kt][ci/4][o][4]
+  __shared__ float pws[100], bs[10];
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 2 * ORD * 8 * 5 * 4; i += 256) {
+    const int e = i & 3, o = (i >> 2) % 5, c4 = (i / 20) % 8, kt = (i / 160) % ORD, g = i / 800;
+    ws[i] = __ldg(p.w + ((g * 5 + o) * ORD + kt) * 32 + c4 * 4 + e);
+  }
+  if (tid < 100) pws[tid] = __ldg(p.pw + tid);
+  if (tid < 10) bs[tid] = __ldg(p.bias + tid);
+  __syncthreads();
+  const long long witem = ((long long)blockIdx.x * 256 + tid) >> 5;       // (b, group of 4 bins)
+  if (witem >= (long long)p.B * (NDF / 4)) return;
+  const int b = (int)(witem / (NDF / 4)), f = (int)(witem % (NDF / 4)) * 4 + (lane >> 3), c8 = lane & 7;
   const int slot = io_slot(p.io, b);
   const int pos = p.st.pos[slot];
-  float part[10];
-#pragma unroll
-  for (int o = 0; o < 10; ++o) part[o] = 0.f;
   const float* ring = p.st.c0_ring + (size_t)slot * ORD * NDF * C;
+  float t[10];
+#pragma unroll
+  for (int o = 0; o < 10; ++o) t[o] = 0.f;
+  float4 x[ORD][2];
 #pragma unroll
   for (int kt = 0; kt < ORD; ++kt) {
-    const float* src = ring + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C;
-    const float v0 = src[lane], v1 = src[32 + lane];
-#pragma unroll
-    for (int o = 0; o < 5; ++o) {
-      part[o] = fmaf(__ldg(p.w + (o * ORD + kt) * 32 + lane), v0, part[o]);
-      part[5 + o] = fmaf(__ldg(p.w + ((5 + o) * ORD + kt) * 32 + lane), v1, part[5 + o]);
-    }
+    const float* src = ring + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
+    x[kt][0] = *reinterpret_cast<const float4*>(src);
+    x[kt][1] = *reinterpret_cast<const float4*>(src + 32);
   }
 #pragma unroll
-  for (int o = 0; o < 10; ++o)
+  for (int kt = 0; kt < ORD; ++kt)
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) part[o] += __shfl_xor_sync(0xffffffffu, part[o], s);
-  if (lane < 10) {
-    float u = __ldg(p.bias + lane);
+    for (int g = 0; g < 2; ++g) {
+      const float4* wp = reinterpret_cast<const float4*>(ws) + (g * ORD + kt) * 40 + c8 * 5;
+      const float4 xv = x[kt][g];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) u = fmaf(__ldg(p.pw + lane * 10 + i), part[i], u);
-    u = fmaxf(u, 0.f);
-    float v = p.co[((size_t)b * NDF + f) * 10 + lane] + u;
-    if (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) v = 0.f;
-    p.st.coef_ring[(((size_t)slot * 3 + pos % 3) * NDF + f) * 10 + lane] = v;
+      for (int o = 0; o < 5; ++o) {
+        const float4 w = wp[o];
+        t[g * 5 + o] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, t[g * 5 + o]))));
+      }
+    }
+#pragma unroll
+  for (int o = 0; o < 10; ++o) {
+    t[o] += __shfl_xor_sync(0xffffffffu, t[o], 1);
+    t[o] += __shfl_xor_sync(0xffffffffu, t[o], 2);
+    t[o] += __shfl_xor_sync(0xffffffffu, t[o], 4);
+  }
+  const bool warm = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) != 0;
+  float* dst = p.st.coef_ring + (((size_t)slot * 3 + pos % 3) * NDF + f) * 10;
+  const float* cop = p.co + ((size_t)b * NDF + f) * 10;
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int oo = c8 + 8 * rep;                      // lanes 0..7 of a bin finish outputs 0..7, lanes 0,1 also 8,9
+    if (oo < 10) {
+      float u = bs[oo];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) u = fmaf(pws[oo * 10 + i], t[i], u);
+      dst[oo] = warm ? 0.f : cop[oo] + fmaxf(u, 0.f);
+    }
   }
 }
 
 void launch_df_pathway(Engine& e, int B, cudaStream_t st) {
   DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B};
-  const long long warps = (long long)B * NDF;
-  k_df_pathway<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+  const long long threads = (long long)B * (NDF / 4) * 32;
+  k_df_pathway<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p);
 }
 
 void init_conv_kernels() {

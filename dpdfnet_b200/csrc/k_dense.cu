@@ -218,13 +218,24 @@ __global__ void __launch_bounds__(256, 1) k_gru(GRUParams p) {
   // once all of them are done: hout is the hand-off buffer and k_gru_commit (next launch) copies it.
 }
 
-__global__ void k_gru_commit(const IoDesc* io, const float* hout, float* hstate, int hs_stride, int B) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index
-  if (idx >= B * (H / 4)) return;
+struct GRUCommitParams {
+  const IoDesc* io;
+  const float* hout[5];
+  float* hstate[5];
+  int stride[5];
+  int n, B;
+};
+// Every unit-chunk CTA of a cell reads the full h_prev rows, and nothing else reads the GRU states inside a
+// hop, so all five cells' new states are written back by one launch at the end of the hop.
+__global__ void k_gru_commit(GRUCommitParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index within one cell
+  if (idx >= p.B * (H / 4)) return;
   const int b = idx / (H / 4), c = (idx % (H / 4)) * 4;
-  if (io_flags(io, b) & DPDF_FLAG_WARMUP_) return;
-  *reinterpret_cast<float4*>(hstate + (size_t)io_slot(io, b) * hs_stride + c) =
-      *reinterpret_cast<const float4*>(hout + (size_t)b * H + c);
+  if (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) return;
+  const int slot = io_slot(p.io, b);
+  const int cell = blockIdx.y;
+  *reinterpret_cast<float4*>(p.hstate[cell] + (size_t)slot * p.stride[cell] + c) =
+      *reinterpret_cast<const float4*>(p.hout[cell] + (size_t)b * H + c);
 }
 
 void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st) {
@@ -239,8 +250,16 @@ void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream
     dim3 grid((B + 63) / 64, H / 32, nprob);
     k_gru<2><<<grid, 256, gru_smem<2>(), st>>>(p);
   }
-  for (int i = 0; i < nprob; ++i)
-    k_gru_commit<<<(B * (H / 4) + 255) / 256, 256, 0, st>>>(e.io_dev, probs[i].hout, probs[i].hstate, probs[i].hs_stride, B);
+}
+
+void launch_gru_commit(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st) {
+  GRUCommitParams p{};
+  p.io = e.io_dev;
+  p.n = nprob;
+  p.B = B;
+  for (int i = 0; i < nprob; ++i) { p.hout[i] = probs[i].hout; p.hstate[i] = probs[i].hstate; p.stride[i] = probs[i].hs_stride; }
+  dim3 grid((B * (H / 4) + 255) / 256, nprob);
+  k_gru_commit<<<grid, 256, 0, st>>>(p);
 }
 
 void init_dense_kernels() {

@@ -65,16 +65,21 @@ __global__ void __launch_bounds__(512) k_analysis(AnaParams p) {
       p.st.in_hist[(size_t)s_slot[bb] * hop + n] = xs2[(n + hop) * ABT + bb].x;
     }
     if (tid < F) {
+      // the (cos, sin) basis streams from L2 (412 KB at 16 kHz, larger than L1): keep 16 loads in flight
       const float2* basis = reinterpret_cast<const float2*>(p.dft_fwd) + tid;
-#pragma unroll 2
-      for (int n = 0; n < win; ++n) {
-        const float2 cs = __ldg(basis + (size_t)n * F);
-        const float4* xr = reinterpret_cast<const float4*>(xs2 + n * ABT);
+      for (int n0 = 0; n0 < win; n0 += 16) {
+        float2 cs[16];
 #pragma unroll
-        for (int q = 0; q < ABT / 2; ++q) {
-          float4 xx = xr[q];
-          X[2 * q] = ffma2(cs, lo2(xx), X[2 * q]);
-          X[2 * q + 1] = ffma2(cs, hi2(xx), X[2 * q + 1]);
+        for (int u = 0; u < 16; ++u) cs[u] = __ldg(basis + (size_t)(n0 + u) * F);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float4* xr = reinterpret_cast<const float4*>(xs2 + (n0 + u) * ABT);
+#pragma unroll
+          for (int q = 0; q < ABT / 2; ++q) {
+            float4 xx = xr[q];
+            X[2 * q] = ffma2(cs[u], lo2(xx), X[2 * q]);
+            X[2 * q + 1] = ffma2(cs[u], hi2(xx), X[2 * q + 1]);
+          }
         }
       }
     }
@@ -218,15 +223,20 @@ __global__ void __launch_bounds__(1024) k_synthesis(SynParams p) {
 #pragma unroll
     for (int bb = 0; bb < SBT; ++bb) acc[bb] = make_float2(0.f, 0.f);
     const float2* basis = reinterpret_cast<const float2*>(p.dft_inv) + n;
-#pragma unroll 2
-    for (int k = 0; k < F; ++k) {
-      const float2 cs = __ldg(basis + (size_t)k * win);
-      const float4* yr = reinterpret_cast<const float4*>(Ys + k * SBT);
+    for (int k0 = 0; k0 < F; k0 += 16) {                     // 16 basis loads in flight (F = 161 / 481: one tail element)
+      float2 cs[16];
 #pragma unroll
-      for (int q = 0; q < SBT / 2; ++q) {
-        float4 yy = yr[q];
-        acc[2 * q] = ffma2(cs, lo2(yy), acc[2 * q]);
-        acc[2 * q + 1] = ffma2(cs, hi2(yy), acc[2 * q + 1]);
+      for (int u = 0; u < 16; ++u) cs[u] = (k0 + u < F) ? __ldg(basis + (size_t)(k0 + u) * win) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (k0 + u >= F) break;
+        const float4* yr = reinterpret_cast<const float4*>(Ys + (k0 + u) * SBT);
+#pragma unroll
+        for (int q = 0; q < SBT / 2; ++q) {
+          float4 yy = yr[q];
+          acc[2 * q] = ffma2(cs[u], lo2(yy), acc[2 * q]);
+          acc[2 * q + 1] = ffma2(cs[u], hi2(yy), acc[2 * q + 1]);
+        }
       }
     }
     const long long toff = (long long)io->t_out * hop;
