@@ -90,6 +90,19 @@ def synth_pcm(B: int, n: int, seed: int) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; give the CPU legs every host core and return the count used."""
+    n = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        pools = threadpoolctl.threadpool_info()
+        used = max([p_.get("num_threads", 1) for p_ in pools] or [1])
+        return int(used)
+    except Exception:
+        return 1
+
+
 def cpu_port_throughput(spec, ck, B_cpu: int, hops: int, warm: int = 2):
     """stream-frames/s of the oracle port on the host cores (numpy + OpenBLAS threads)."""
     from oracle.oracle_np import OracleEngine
@@ -111,6 +124,7 @@ def run_reference(args):
     spec = get_spec(args.model)
     ck = random_checkpoint(spec, 0)
     B_cpu = args.cpu_batch
+    cores = use_all_host_threads()
     from oracle.oracle_np import OracleEngine
     ora = OracleEngine(spec, pack_tensors(spec, ck), B_cpu)
     pcm = synth_pcm(B_cpu, (args.steps + args.warmup) * spec.hop, 99)
@@ -121,7 +135,6 @@ def run_reference(args):
         ora.step_pcm(pcm[:, t * spec.hop:(t + 1) * spec.hop])
     dt = time.perf_counter() - t0
     val = B_cpu * args.steps / dt
-    cores = os.cpu_count() or 1
     sample = f"{B_cpu} streams x {args.steps} hops of {args.model} (bounded sample of the {args.batch}-stream workload)"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -222,6 +235,52 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * B * Ke / float(te.item())
 
+    # ---- per-hop latency distribution at this batch (one graph replay per hop, CUDA events) -------------
+    Kl = min(K, 200)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(Kl + 1)]
+    eng.reset()
+    eng.run_pcm(pcm[:, :W * hop], out=out[:, :W * hop])
+    sync_all()
+    evs[0].record(stream)
+    for t_ in range(Kl):
+        eng.step_pcm(pcm[:, (W + t_) * hop:(W + t_ + 1) * hop], out=out[:, (W + t_) * hop:(W + t_ + 1) * hop])
+        evs[t_ + 1].record(stream)
+    torch.cuda.synchronize()
+    hop_ms = np.array([evs[i].elapsed_time(evs[i + 1]) for i in range(Kl)])
+    lat = {"p50_ms": float(np.percentile(hop_ms, 50)), "p99_ms": float(np.percentile(hop_ms, 99)), "max_ms": float(hop_ms.max()),
+           "hops": Kl, "batch": B, "note": "device time per hop incl. per-hop launch from Python; budget is the 10 ms hop"}
+
+    # ---- largest batch whose hop still fits the 10 ms real-time budget (all ranks loaded at once) -------
+    fps = spec.sample_rate / spec.hop
+    sustained = None
+    if not args.no_ladder:
+        del eng
+        ladder = []
+        for Bl in args.ladder:
+            engl = Engine(spec, ck, max_streams=Bl, device=local)
+            xl = torch.from_numpy(synth_pcm(Bl, 30 * hop, 777 + rank)).cuda()
+            yl = torch.empty_like(xl)
+            engl.run_pcm(xl[:, :5 * hop], out=yl[:, :5 * hop])
+            sync_all()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            engl.run_pcm(xl[:, 5 * hop:], out=yl[:, 5 * hop:])
+            b_.record(stream)
+            sync_all()
+            tl = torch.tensor([a.elapsed_time(b_) / 25.0], device="cuda")
+            if world > 1:
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            ladder.append({"streams_per_gpu": Bl, "ms_per_hop": float(tl.item()), "stream_frames_per_s": world * Bl / (float(tl.item()) * 1e-3)})
+            engl.close()
+            del engl, xl, yl
+        ok = [r for r in ladder if r["ms_per_hop"] < 1e3 / fps]
+        best = max(ok, key=lambda r: r["streams_per_gpu"]) if ok else None
+        sustained = {"ladder": ladder, "hop_budget_ms": 1e3 / fps,
+                     "realtime_streams_per_gpu": best["streams_per_gpu"] if best else None,
+                     "realtime_streams_total": world * best["streams_per_gpu"] if best else None,
+                     "ms_per_hop_at_that_batch": best["ms_per_hop"] if best else None}
+        eng = Engine(spec, ck, max_streams=B, device=local)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -249,9 +308,8 @@ def run_ours(args):
     tflops = flops * B * K / (ms_max * 1e-3) / 1e12
 
     # ---- CPU port beside it -------------------------------------------------
+    cores = use_all_host_threads()
     cpu_val, cpu_dt = cpu_port_throughput(spec, ck, args.cpu_batch, args.cpu_hops)
-    cores = os.cpu_count() or 1
-    fps = spec.sample_rate / spec.hop
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -262,6 +320,8 @@ def run_ours(args):
                    "weights": "seeded random (no checkpoint offline), BN stats randomised"},
         "realtime_streams": value / fps,
         "hop_latency_ms": ms_max / K,
+        "hop_latency": lat,
+        "sustained": sustained,
         "gpu_launches": launches,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * hop * 4, "d2h_bytes_per_step": B * hop * 4,
                 "steps": Ke, "api": "dpdf_step_pcm_host (pinned host buffers, H2D + hop + D2H, synchronous)"},
@@ -296,6 +356,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=128)
     ap.add_argument("--cpu-hops", type=int, default=20)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-ladder", action="store_true", help="skip the sustained-streams batch ladder")
+    ap.add_argument("--ladder", type=int, nargs="*", default=[4096, 6144, 7168, 8192])
     ap.add_argument("--intra-bt", type=int, default=0)
     ap.add_argument("--profile-only", action="store_true", help="device steps only (for ncu runs)")
     args = ap.parse_args()
