@@ -1,0 +1,44 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, the bench line (both arms), an ncu launch list and full captures of the
+# two dominant kernels.  Everything lands in gpurun_out/<tag>_*.   usage: tools/gpu_round.sh <tag> [what...]
+set -u
+TAG=${1:-r01}; shift || true
+WHAT=${*:-tests bench ref launches ncu}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
+for w in $WHAT; do
+  case $w in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1
+      echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.log; tail -3 $OUT/${TAG}_pytest_gpu.log ;;
+    smoke)
+      timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; tail -2 $OUT/${TAG}_smoke.log ;;
+    bench)
+      timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+      echo "bench exit $?"; tail -c 3000 $OUT/${TAG}_bench.json ;;
+    ref)
+      timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
+      echo "ref exit $?"; cat $OUT/${TAG}_bench_ref.json ;;
+    launches)
+      # 5 warm-up hops skipped by -s (launches per hop printed by the bench), one hop listed; graph off so
+      # every node is a plain launch
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 120 --csv \
+        --log-file $OUT/${TAG}_launches.csv python bench.py --steps 8 --warmup 8 --no-graph --profile-only \
+        > $OUT/${TAG}_launches.log 2>&1
+      echo "launches exit $?" ;;
+    ncu)
+      for k in k_dprnn_intra k_dprnn_post_tc; do
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 2 \
+          -f -o $OUT/${TAG}_$k python bench.py --steps 4 --warmup 4 --no-graph --profile-only \
+          > $OUT/${TAG}_ncu_$k.log 2>&1
+        echo "ncu $k exit $?"
+      done ;;
+    ncuall)
+      timeout 1500 ncu --set full --clock-control none --import-source on -s 300 -c 60 \
+        -f -o $OUT/${TAG}_allkernels python bench.py --steps 8 --warmup 8 --no-graph --profile-only \
+        > $OUT/${TAG}_ncu_all.log 2>&1
+      echo "ncuall exit $?" ;;
+  esac
+done
+ls -la $OUT | tail -20
