@@ -103,6 +103,7 @@ static int bind_weights(Engine& e) {
       x.ln2_g = W(q + ".inter.ln_g", C);           x.ln2_b = W(q + ".inter.ln_b", C);
       x.tc_fc_w = W(q + ".tc.fc_w", 2 * C * 2 * C); x.tc_gates = W(q + ".tc.gates", 6 * 2 * C * C);
       x.tc_fc2_w = W(q + ".tc.fc2_w", 2 * C * C);
+      x.tc_intra = W(q + ".tc.intra", 2 * 4 * 192 * C / 2);
     }
   }
   auto gl = [&](const std::string& n, int G, int Ng, int Kg) { return GLW{W(n + ".w", (size_t)G * Ng * Kg), W(n + ".b", (size_t)G * Ng), G, Ng, Kg}; };
@@ -273,6 +274,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   init_dprnn_kernels();
   init_dense_kernels();
   init_dprnn_tc_kernels();
+  init_dprnn_intra_tc_kernels();
   launch_reset(e, nullptr, max_streams, e.own_stream);
   if (cudaStreamSynchronize(e.own_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
     return bail(fail(DPDF_ERR_CUDA, "engine initialisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -346,7 +348,9 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     RUN("sepconv", launch_sepconv(e, pr, 1, B, st)); ++n;
   }
   for (int i = 0; i < d.N; ++i) {
-    RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); ++n;
+    if (e.intra_tc == 1 || (e.intra_tc == 2 && B >= e.intra_tc_min)) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
+    else { RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); }
+    ++n;
     if (e.post_tc) { RUN("dprnn_post", launch_dprnn_post_tc(e, i, B, st)); }
     else { RUN("dprnn_post", launch_dprnn_post(e, i, B, st)); }
     ++n;
@@ -783,6 +787,15 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   else if (strcmp(key, "intra_bt") == 0) {
     if (value != 0 && value != 8 && value != 16 && value != 32) return fail(DPDF_ERR_INVALID, "intra_bt must be 0, 8, 16 or 32");
     e.intra_bt = value;
+    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+    e.graphs.clear();
+  } else if (strcmp(key, "intra_tc") == 0 || strcmp(key, "intra_tc_min") == 0) {
+    if (key[8] == 0) {
+      if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "intra_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
+      e.intra_tc = value;
+    } else {
+      e.intra_tc_min = value;
+    }
     for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
     e.graphs.clear();
   } else if (strcmp(key, "post_tc") == 0) {

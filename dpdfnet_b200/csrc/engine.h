@@ -58,6 +58,7 @@ struct DprnnW {
   const float *i_wih, *i_whh, *i_bias, *fc_w, *fc_b, *ln_g, *ln_b;
   const float *r_wih, *r_whh, *r_bias, *fc2_w, *fc2_b, *ln2_g, *ln2_b;
   const float *tc_fc_w, *tc_gates, *tc_fc2_w;      // tcgen05 operand images (hi | lo), weights.py:umma_operand
+  const float* tc_intra;                           // FP16 operand images of the intra GRU, weights.py:umma_operand16
 };
 
 struct Weights {
@@ -103,6 +104,7 @@ void launch_df_pathway(Engine& e, int B, cudaStream_t st);
 void launch_dprnn_intra(Engine& e, int blk, int B, cudaStream_t st);
 void launch_dprnn_post(Engine& e, int blk, int B, cudaStream_t st);
 void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st);
+void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st);
 
 struct GLProblem {
   const float* in0; int ld0;     // input columns [0, split)
@@ -155,6 +157,8 @@ struct Engine {
   int launches = 0;               // kernels launched by the last step
   int use_graph = 1;
   int intra_bt = 0;               // 0 = auto
+  int intra_tc = 2;               // intra-frame GRU on tcgen05 (FP16 split): 0 never, 1 always, 2 = when B >= intra_tc_min
+  int intra_tc_min = 512;
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
   std::map<int, cudaGraphExec_t> graphs;     // keyed by B
   std::vector<std::pair<std::string, float>> ktimes;
@@ -168,6 +172,7 @@ void init_conv_kernels();
 void init_dprnn_kernels();
 void init_dense_kernels();
 void init_dprnn_tc_kernels();
+void init_dprnn_intra_tc_kernels();
 void enqueue_step(Engine& e, int B, cudaStream_t st);    // all kernels of one hop, in order
 
 }  // namespace dpdf

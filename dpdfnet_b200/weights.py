@@ -280,6 +280,10 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             t[f"{q}.tc.fc_w"] = np.concatenate([umma_operand(fcw[:, :C]), umma_operand(fcw[:, C:])])   # two K=64 slabs
             t[f"{q}.tc.gates"] = np.concatenate([umma_operand(m[g * C:(g + 1) * C]) for m in (wih, whh) for g in range(3)])
             t[f"{q}.tc.fc2_w"] = umma_operand(sd[f"{p}.fc_inter.weight"])
+            # FP16 hi/lo operand images of the intra-frame GRU (k_dprnn_intra_tc): per direction
+            # [W_ih hi | W_ih lo | W_hh hi | W_hh lo], each [192][64] halves stored as raw bytes in the f32 blob
+            t[f"{q}.tc.intra"] = np.concatenate([
+                umma_operand16(sd[f"{p}.intra_gru.{m}_l0{sfx}"]) for sfx in ("", "_reverse") for m in ("weight_ih", "weight_hh")])
 
     def gl(out: str, prefix: str, groups: int):
         t[f"{out}.w"], t[f"{out}.b"] = _gl_pack(sd, prefix, groups)
@@ -354,6 +358,32 @@ def umma_operand(mat: np.ndarray) -> np.ndarray:
     """hi image followed by lo image of a weight matrix [N, K] (B operand of D = A * W^T)."""
     hi, lo = tf32_split(mat)
     return np.concatenate([umma_kmajor(hi), umma_kmajor(lo)])
+
+
+def fp16_split(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """w = hi + lo with hi, lo in IEEE half precision (round-to-nearest-even, ``cvt.rn.f16.f32``): the same
+    11-bit significands as the TF32 split, so hi*hi + lo*hi + hi*lo is again FP32-accurate (~2^-22) as long as
+    |w| stays inside the FP16 range (checked)."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    if not np.all(np.abs(w) < 6.0e4):
+        raise ValueError("weight magnitude outside the FP16 range: the FP16-split tensor-core path cannot represent it")
+    hi = w.astype(np.float16)
+    lo = (w - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def umma_kmajor16(mat: np.ndarray) -> np.ndarray:
+    """FP16 [rows, K] -> tcgen05 K-major SWIZZLE_NONE operand image: core matrices of 8 rows x 8 halves (128 B),
+    adjacent in K contiguous (LBO = 128 B), 8-row groups (K/8)*128 B apart (SBO)."""
+    n, k = mat.shape
+    assert n % 8 == 0 and k % 8 == 0 and mat.dtype == np.float16
+    return np.ascontiguousarray(mat.reshape(n // 8, 8, k // 8, 8).transpose(0, 2, 1, 3)).reshape(-1)
+
+
+def umma_operand16(mat: np.ndarray) -> np.ndarray:
+    """hi image then lo image of a weight matrix [N, K] in FP16, returned as float32 words (raw bytes)."""
+    hi, lo = fp16_split(mat)
+    return np.concatenate([umma_kmajor16(hi), umma_kmajor16(lo)]).view(np.float32)
 
 
 def serialize(tensors: Mapping[str, np.ndarray]) -> bytes:

@@ -66,11 +66,14 @@ def test_offline_golden(torch_cuda, golden_dir, name):
     assert np.abs(out - g["wave_out"]).max() < WAVE_TOL
 
 
+@pytest.mark.parametrize("intra_tc", [0, 1])
 @pytest.mark.parametrize("name,B", [("dpdfnet2", 5), ("dpdfnet8", 3), ("baseline", 2), ("dpdfnet8_48khz_hr", 2)])
-def test_stages_vs_oracle(torch_cuda, name, B):
-    """Every intermediate tensor of a hop against the oracle, ragged batch + slot indirection."""
+def test_stages_vs_oracle(torch_cuda, name, B, intra_tc):
+    """Every intermediate tensor of a hop against the oracle, ragged batch + slot indirection; the intra-frame
+    GRU on the FFMA2 kernel (intra_tc=0) and on the tcgen05 FP16-split kernel (intra_tc=1)."""
     eng = _engine(name, 11, B + 3)
     eng.set_option("graph", 0)
+    eng.set_option("intra_tc", intra_tc)
     ora = _oracle(name, 11, B + 3)
     spec = eng.spec
     rng = np.random.default_rng(2)
@@ -115,6 +118,31 @@ def test_pcm_path_vs_oracle_and_graph(torch_cuda):
     y = eng.run_pcm(x)
     torch.cuda.synchronize()
     assert np.array_equal(y.cpu().numpy(), out_graph)
+
+
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 130), ("dpdfnet2_48khz_hr", 129)])
+def test_intra_tc_multi_tile(torch_cuda, name, B):
+    """tcgen05 intra-GRU kernel with more than one 128-stream tile and a ragged last tile: waveform and the
+    dual-path activations against the oracle, and bit-equal rows for equal inputs across tiles."""
+    T = 5
+    eng = _engine(name, 3, B)
+    eng.set_option("intra_tc", 1)
+    ora = _oracle(name, 3, B)
+    hop = eng.spec.hop
+    rng = np.random.default_rng(12)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    pcm[128:] = pcm[:B - 128]                      # rows of the second tile repeat rows of the first
+    ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    out = eng.run_pcm_host(pcm)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < WAVE_TOL
+    assert np.array_equal(out[128:], out[:B - 128])
+    N = eng.spec.n_blocks
+    got = eng.debug_tensor("xd", B)
+    assert np.abs(got - np.asarray(ora.dbg[f"xd{N - 1}"]).reshape(B, -1)).max() < 2e-4
+    ffma = _engine(name, 3, B)
+    ffma.set_option("intra_tc", 0)
+    assert np.abs(ffma.run_pcm_host(pcm) - out).max() < 1e-5
 
 
 def test_state_import_export_roundtrip(torch_cuda):

@@ -4,6 +4,7 @@
 
 Used on the GPU box to localise a numerical discrepancy to one kernel in a single run.
 """
+import os
 import sys
 import time
 from pathlib import Path
@@ -40,6 +41,9 @@ def compare(model: str, B: int = 3, frames: int = 4, seed: int = 0):
     ck = random_checkpoint(spec, seed)
     eng = Engine(spec, ck, max_streams=B + 2)
     eng.set_option("graph", 0)
+    for kv in os.environ.get("DPDF_OPTIONS", "").split(","):       # e.g. DPDF_OPTIONS=intra_tc=1,post_tc=0
+        if "=" in kv:
+            eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     ora = OracleEngine(spec, pack_tensors(spec, ck), B + 2)
     rng = np.random.default_rng(3)
     slots = np.arange(B, dtype=np.int32)[::-1].copy() + 1     # exercise the slot indirection

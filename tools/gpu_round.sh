@@ -12,6 +12,8 @@ for w in $WHAT; do
     tests)
       timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1
       echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.log; tail -3 $OUT/${TAG}_pytest_gpu.log ;;
+    debugtc)
+      DPDF_OPTIONS=intra_tc=1 timeout 600 python tools/gpu_debug.py dpdfnet2 > $OUT/${TAG}_debug_tc.log 2>&1; tail -25 $OUT/${TAG}_debug_tc.log ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; tail -2 $OUT/${TAG}_smoke.log ;;
     bench)
@@ -28,9 +30,9 @@ for w in $WHAT; do
         > $OUT/${TAG}_launches.log 2>&1
       echo "launches exit $?" ;;
     ncu)
-      for k in k_dprnn_intra k_dprnn_post_tc; do
+      for k in ${NCU_KERNELS:-k_dprnn_intra k_dprnn_post_tc}; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 2 \
-          -f -o $OUT/${TAG}_$k python bench.py --steps 4 --warmup 4 --no-graph --profile-only \
+          -f -o $OUT/${TAG}_$k python bench.py --steps 4 --warmup 4 --no-graph --profile-only ${BENCH_ARGS:-} \
           > $OUT/${TAG}_ncu_$k.log 2>&1
         echo "ncu $k exit $?"
       done ;;
