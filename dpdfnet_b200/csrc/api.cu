@@ -104,6 +104,7 @@ static int bind_weights(Engine& e) {
       x.tc_fc_w = W(q + ".tc.fc_w", 2 * C * 2 * C); x.tc_gates = W(q + ".tc.gates", 6 * 2 * C * C);
       x.tc_fc2_w = W(q + ".tc.fc2_w", 2 * C * C);
       x.tc_intra = W(q + ".tc.intra", 2 * 4 * 192 * C / 2);
+      x.tc_intra_bias = W(q + ".tc.intra_bias", 2 * 4 * C);
     }
   }
   auto gl = [&](const std::string& n, int G, int Ng, int Kg) { return GLW{W(n + ".w", (size_t)G * Ng * Kg), W(n + ".b", (size_t)G * Ng), G, Ng, Kg}; };

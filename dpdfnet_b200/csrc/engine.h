@@ -58,6 +58,7 @@ struct DprnnW {
   const float *i_wih, *i_whh, *i_bias, *fc_w, *fc_b, *ln_g, *ln_b;
   const float *r_wih, *r_whh, *r_bias, *fc2_w, *fc2_b, *ln2_g, *ln2_b;
   const float *tc_fc_w, *tc_gates, *tc_fc2_w;      // tcgen05 operand images (hi | lo), weights.py:umma_operand
+  const float* tc_intra_bias;                      // [2][4][64] with the same exponent scales as the images
   const float* tc_intra;                           // FP16 operand images of the intra GRU, weights.py:umma_operand16
 };
 

@@ -7,11 +7,14 @@
 // kept by the error-compensated split x = hi + lo (both FP16, 11-bit significands; three products hi*hi + lo*hi
 // + hi*lo; weights.py:fp16_split): the same accuracy as 3xTF32 at half the shared-memory footprint and twice the
 // tensor rate, which is what lets both 192x64 weight matrices of a direction stay resident in shared memory
-// (96 KB) next to the operand images of x_t, x_{t+1} and h.
+// (96 KB) next to the operand images of x_t and x_{t+1}.  h_t never touches shared memory: the gate warps write
+// its FP16 hi/lo halves with tcgen05.st into tensor memory, from where the recurrent product reads its A operand
+// (SS-mode MMAs re-read the 4 KB A tile from shared memory for every instruction, which made the N = 64 / 128
+// recurrent MMAs shared-memory-bandwidth bound: tools/ubench/intra_tc_timeline.cu).
 //
-// Pipeline per step t (TMEM is double buffered, 2 x 256 columns):
-//   thread 0     : h-part MMAs of step t (critical path) -> commit -> x-part MMAs of step t+1 into the other buffer
-//   all threads  : wait commit, tcgen05.ld the four gate pre-activations of (row = TMEM lane, 16 units), gate
+// Pipeline per step t (the r|z|in accumulators are double buffered in TMEM: 2 x 192 + 64 (hn) + 64 (h operand) columns):
+//   warp 16      : h-part MMAs of step t (critical path) -> commit -> x-part MMAs of step t+1 into the other buffer
+//   warps 0..15  : wait commit, tcgen05.ld the four gate pre-activations of (row = TMEM lane, 16 units), gate
 //                  math in registers (h_{t-1} never leaves registers), write h_t as FP16 hi/lo operand rows for
 //                  the next step and as FP32 to hcat[b][f][dir*64 + u]; convert the prefetched x_{t+2} tile.
 // The x-part MMAs and the global loads of x are hidden behind the gate math of the previous step.
@@ -24,14 +27,28 @@ namespace {
 
 using namespace tc;
 
-constexpr int ITC_NT = 512;                 // 16 warps: warp w -> TMEM lane quadrant w & 3, 16-unit group w >> 2
+constexpr int ITC_GATE = 512;               // 16 gate warps: warp w -> TMEM lane quadrant w & 3, 16-unit group w >> 2
+constexpr int ITC_NT = ITC_GATE + 32;       // + warp 16: the MMA issuer (does nothing else, so its descriptors stay in uniform registers)
 constexpr int W_IMG = 192 * 64 * 2;         // bytes of one FP16 [192][64] weight image
 constexpr int A_IMG = 128 * 64 * 2;         // bytes of one FP16 [128][64] activation image
 constexpr int OFF_X = 4 * W_IMG;            // x images: [2 buffers][hi | lo]
-constexpr int OFF_H = OFF_X + 4 * A_IMG;    // h images: [hi | lo]
-constexpr int OFF_BIAS = OFF_H + 2 * A_IMG; // [4][64] floats
+constexpr int OFF_BIAS = OFF_X + 4 * A_IMG; // [4][64] floats
 constexpr int OFF_BAR = OFF_BIAS + 1024;    // two mbarriers + TMEM base slot
 constexpr size_t INTRA_TC_SMEM = OFF_BAR + 64;
+// tensor-memory columns: P[2] = (r | z | in) double buffered, hn single (written and drained inside one step),
+// h_{t} as the FP16 hi / lo A operand of the recurrent product (two K halves per 32-bit column)
+constexpr uint32_t TM_P = 0, TM_HN = 384, TM_HHI = 448, TM_HLO = 480;
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 }  // namespace
 
@@ -40,16 +57,28 @@ struct IntraTcParams {
   float* hcat[2];         // [B][Fp][128]
   int Fp[2];
   const float* wimg[2];   // [2 dirs][W_ih hi | W_ih lo | W_hh hi | W_hh lo] FP16 operand images
-  const float* bias[2];   // [2][4][64]
+  const float* bias[2];   // [2][4][64], exponent scales folded in (weights.py: tc.intra_bias)
   int tiles;              // ceil(B / 128)
   int B;
+#ifdef ITC_TIMELINE
+  long long* tl;          // [steps][8] SM-clock stamps of CTA 0 (tools/ubench/intra_tc_timeline.cu)
+#endif
 };
+
+#ifdef ITC_TIMELINE
+// stamp AFTER everything issued so far has completed as far as this warp can tell: the clock read depends on a
+// volatile shared-memory load, which cannot issue before a pending (deferred-blocking) barrier has released
+#define TL(slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 16 || warp == 5)) { \
+    unsigned v_; long long c_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v_) : "r"(smem_u32(tmem_slot))); \
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) : "r"(v_)); p.tl[t * 8 + (slot)] = c_; } } while (0)
+#else
+#define TL(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* Wsm = smem_raw;
   unsigned char* Xsm = smem_raw + OFF_X;
-  unsigned char* Hsm = smem_raw + OFF_H;
   float* sb = reinterpret_cast<float*>(smem_raw + OFF_BIAS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + OFF_BAR);       // [0] weights landed, [1] step accumulators complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -72,7 +101,6 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid < 256) sb[tid] = __ldg((br ? p.bias[1] : p.bias[0]) + dir * 4 * C + tid);
-  for (int i = tid; i < 2 * A_IMG / 16; i += ITC_NT) reinterpret_cast<uint4*>(Hsm)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_0 = 0
   __syncthreads();                                           // barriers initialised
   if (tid == 0) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(br ? p.wimg[1] : p.wimg[0]) + (size_t)dir * 4 * W_IMG;
@@ -112,111 +140,169 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
     }
   };
   float xv[2][8];
-  load_x(0, xv);
-  store_x(0, xv);
-  if (T > 1) {
-    load_x(1, xv);
-    store_x(1, xv);
+  if (warp < 16) {
+    load_x(0, xv);
+    store_x(0, xv);
+    if (T > 1) {
+      load_x(1, xv);
+      store_x(1, xv);
+    }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-
-  // ---- MMA issue (thread 0) ---------------------------------------------------------------------------------
-  const uint32_t w_base = smem_u32(Wsm), x_base = smem_u32(Xsm), h_base = smem_u32(Hsm);
-  auto mma3 = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {                         // K = 64 in steps of 16 halves = two core matrices = 256 B
-      const uint64_t dah = umma_desc(a_hi + ks * 256, 1024), dal = umma_desc(a_lo + ks * 256, 1024);
-      const uint64_t dbh = umma_desc(b_hi + ks * 256, 1024), dbl = umma_desc(b_lo + ks * 256, 1024);
-      umma_f16(d, dah, dbh, idesc, accumulate);
-      umma_f16(d, dal, dbh, idesc, 1);
-      umma_f16(d, dah, dbl, idesc, 1);
-      accumulate = 1;
-    }
-  };
-  auto x_mma = [&](int t) {                                  // P[t & 1][0, 192) = x_t * W_ih^T
-    const uint32_t xa = x_base + (t & 1) * 2 * A_IMG;
-    mma3(tmem + (t & 1) * 256, xa, xa + A_IMG, w_base, w_base + W_IMG, idesc_f16(128, 192), 0);
-  };
-  auto h_mma = [&](int t) {
-    const uint32_t d = tmem + (t & 1) * 256;
-    const uint32_t whi = w_base + 2 * W_IMG, wlo = w_base + 3 * W_IMG;
-    mma3(d, h_base, h_base + A_IMG, whi, wlo, idesc_f16(128, 128), 1);                               // r, z += h * W_hh[r,z]^T
-    mma3(d + 192, h_base, h_base + A_IMG, whi + 16 * 1024, wlo + 16 * 1024, idesc_f16(128, 64), 0);  // hn = h * W_hh[n]^T
-  };
-  if (tid == 0) {
-    mbar_wait(bars, 0);                                      // weight images landed (async proxy -> async proxy)
-    x_mma(0);
-    h_mma(0);
-    umma_commit(bars + 1);
-    if (T > 1) x_mma(1);
+  if (warp < 16) {                                           // h_0 = 0 in the TMEM operand columns
+    const uint32_t a = tmem + ((uint32_t)(qd * 32) << 16) + cg * 8;
+    tmem_st4(a + TM_HHI, 0u, 0u, 0u, 0u); tmem_st4(a + TM_HHI + 4, 0u, 0u, 0u, 0u);
+    tmem_st4(a + TM_HLO, 0u, 0u, 0u, 0u); tmem_st4(a + TM_HLO + 4, 0u, 0u, 0u, 0u);
+    tmem_st_wait();
   }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
-  // ---- the sweep --------------------------------------------------------------------------------------------
-  float h[16];
+  // ---- MMA issue (warp 16, one elected lane) ------------------------------------------------------------------
+  if (warp == 16) {
+    const uint32_t w_base = smem_u32(Wsm), x_base = smem_u32(Xsm);
+    constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
+    auto mma3 = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+      const uint64_t dah = DESC0 | (a_hi >> 4), dal = DESC0 | (a_lo >> 4), dbh = DESC0 | (b_hi >> 4), dbl = DESC0 | (b_lo >> 4);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) h[i] = 0.f;
-  const int bme = b0 + row;
-  const bool live = bme < p.B;
-  const uint32_t lane_addr = tmem + ((uint32_t)(qd * 32) << 16) + cg * 16;
-  for (int t = 0; t < T; ++t) {
-    if (t + 2 < T) load_x(t + 2, xv);                        // in flight during the wait
-    mbar_wait(bars + 1, t & 1);
-    tc_fence_after();
-    const int f = dir ? T - 1 - t : t;
-    float* hdst = hg + ((size_t)bme * T + f) * 2 * C + dir * C + cg * 16;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t gr[8], gz[8], gi[8], gh[8];
-      const uint32_t ta = lane_addr + (t & 1) * 256 + half * 8;
-      tmem_ld8_nowait(ta, gr);
-      tmem_ld8_nowait(ta + 64, gz);
-      tmem_ld8_nowait(ta + 128, gi);
-      tmem_ld8_nowait(ta + 192, gh);
-      tmem_ld_wait();
-      float bu[4][8];                                        // biases of these 8 units (warp-uniform: broadcast LDS.128)
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float4* b4 = reinterpret_cast<const float4*>(sb + g * C + cg * 16 + half * 8);
-        const float4 u0 = b4[0], u1 = b4[1];
-        bu[g][0] = u0.x; bu[g][1] = u0.y; bu[g][2] = u0.z; bu[g][3] = u0.w;
-        bu[g][4] = u1.x; bu[g][5] = u1.y; bu[g][6] = u1.z; bu[g][7] = u1.w;
+      for (int ks = 0; ks < 4; ++ks) {                       // K = 64 in steps of 16 halves = two core matrices = 256 B
+        umma_f16(d, dah + ks * 16, dbh + ks * 16, idesc, accumulate);
+        umma_f16(d, dal + ks * 16, dbh + ks * 16, idesc, 1);
+        umma_f16(d, dah + ks * 16, dbl + ks * 16, idesc, 1);
+        accumulate = 1;
       }
-      float hn[8];
+    };
+    auto x_mma = [&](int t) {                                // P[t & 1][0, 192) = x_t * W_ih^T
+      const uint32_t xa = x_base + (t & 1) * 2 * A_IMG;
+      mma3(tmem + TM_P + (t & 1) * 192, xa, xa + A_IMG, w_base, w_base + W_IMG, idesc_f16(128, 192), 0);
+    };
+    // recurrent part: A = h (hi, lo) straight from tensor memory, so the only shared-memory traffic is W_hh
+    auto mma3_ts = [&](uint32_t d, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+      const uint64_t dbh = DESC0 | (b_hi >> 4), dbl = DESC0 | (b_lo >> 4);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float r = sigmoidf_(__uint_as_float(gr[e]) + bu[0][e]);
-        const float z = sigmoidf_(__uint_as_float(gz[e]) + bu[1][e]);
-        const float n = tanhf_(__uint_as_float(gi[e]) + bu[2][e] + r * (__uint_as_float(gh[e]) + bu[3][e]));
-        hn[e] = (1.0f - z) * n + z * h[half * 8 + e];
-        h[half * 8 + e] = hn[e];
+      for (int ks = 0; ks < 4; ++ks) {                       // 16 halves of K = 8 columns of the TMEM operand
+        umma_f16_ts(d, tmem + TM_HHI + ks * 8, dbh + ks * 16, idesc, accumulate);
+        umma_f16_ts(d, tmem + TM_HLO + ks * 8, dbh + ks * 16, idesc, 1);
+        umma_f16_ts(d, tmem + TM_HHI + ks * 8, dbl + ks * 16, idesc, 1);
+        accumulate = 1;
       }
-      uint4 hi, lo;
-      split8_f16(hn, hi, lo);
-      unsigned char* dst = Hsm + img16_off(row, cg * 2 + half);
-      *reinterpret_cast<uint4*>(dst) = hi;
-      *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
-      if (live) {
-        *reinterpret_cast<float4*>(hdst + half * 8) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        *reinterpret_cast<float4*>(hdst + half * 8 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-      }
+    };
+    auto h_mma = [&](int t) {
+      const uint32_t whi = w_base + 2 * W_IMG, wlo = w_base + 3 * W_IMG;
+      mma3_ts(tmem + TM_P + (t & 1) * 192, whi, wlo, idesc_f16(128, 128), 1);                 // r, z += h * W_hh[r,z]^T
+      mma3_ts(tmem + TM_HN, whi + 16 * 1024, wlo + 16 * 1024, idesc_f16(128, 64), 0);         // hn = h * W_hh[n]^T
+    };
+    if (lane == 0) {
+      mbar_wait(bars, 0);                                    // weight images landed (async proxy -> async proxy)
+      x_mma(0);
+      h_mma(0);
+      umma_commit(bars + 1);
+      if (T > 1) x_mma(1);
     }
-    if (t + 2 < T) store_x(t & 1, xv);                       // x_mma(t) (reader of this buffer) completed with the commit
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      if (t + 1 < T) {
+    for (int t = 0; t + 1 < T; ++t) {
+      asm volatile("bar.sync 1, %0;" ::"n"(ITC_NT) : "memory");     // h_t written, P[t & 1] drained, x_{t+2} staged
+      TL(5);
+      if (lane == 0) {
+        tc_fence_after();
         h_mma(t + 1);
         umma_commit(bars + 1);
+        TL(6);
+#ifndef ITC_NO_X
+        if (t + 2 < T) x_mma(t + 2);
+#endif
+        TL(7);
       }
-      if (t + 2 < T) x_mma(t + 2);
+      __syncwarp();
+    }
+  } else {
+    // ---- the sweep (gate warps) -----------------------------------------------------------------------------
+    float h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = 0.f;
+    const int bme = b0 + row;
+    const bool live = bme < p.B;
+    const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16);
+    const uint32_t lane_addr = lane_base + cg * 16;
+    for (int t = 0; t < T; ++t) {
+      TL(0);
+      if (t + 2 < T) load_x(t + 2, xv);                      // in flight during the wait
+      mbar_wait(bars + 1, t & 1);
+      tc_fence_after();
+      TL(1);
+      const int f = dir ? T - 1 - t : t;
+      float* hdst = hg + ((size_t)bme * T + f) * 2 * C + dir * C + cg * 16;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t gr[8], gz[8], gi[8], gh[8];
+        const uint32_t ta = lane_addr + TM_P + (t & 1) * 192 + half * 8;
+        tmem_ld8_nowait(ta, gr);
+        tmem_ld8_nowait(ta + 64, gz);
+        tmem_ld8_nowait(ta + 128, gi);
+        tmem_ld8_nowait(lane_addr + TM_HN + half * 8, gh);
+        tmem_ld_wait();
+        if (half == 0) TL(2);
+        // Gate math on unit pairs (packed f32x2 FMA-pipe ops).  The operand images and biases carry the exponent
+        // scales (weights.py: r, z rows x -log2(e); n rows x 2 log2(e)), so
+        //   r = 1 / (1 + 2^a_r),  z = 1 / (1 + 2^a_z)   (one shared reciprocal),   n = tanh(c) = 1 - 2 / (1 + 2^c')
+        float hn[8];
+#ifdef ITC_NO_MATH
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hn[e] = __uint_as_float(gr[e] ^ gz[e] ^ gi[e] ^ gh[e]) * 1e-30f + h[half * 8 + e];
+#else
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float2 b_r = *reinterpret_cast<const float2*>(sb + cg * 16 + half * 8 + e);
+          const float2 b_z = *reinterpret_cast<const float2*>(sb + C + cg * 16 + half * 8 + e);
+          const float2 b_i = *reinterpret_cast<const float2*>(sb + 2 * C + cg * 16 + half * 8 + e);
+          const float2 b_h = *reinterpret_cast<const float2*>(sb + 3 * C + cg * 16 + half * 8 + e);
+          const float2 one = make_float2(1.0f, 1.0f);
+          const float2 ar = __fadd2_rn(make_float2(__uint_as_float(gr[e]), __uint_as_float(gr[e + 1])), b_r);
+          const float2 az = __fadd2_rn(make_float2(__uint_as_float(gz[e]), __uint_as_float(gz[e + 1])), b_z);
+          // 2^60 * 2^60 stays finite in the shared reciprocal; sigmoid(-41) = 1e-18 is already 0 in FP32 terms
+          const float2 pr = __fadd2_rn(make_float2(ex2_ftz(fminf(ar.x, 60.f)), ex2_ftz(fminf(ar.y, 60.f))), one);
+          const float2 pz = __fadd2_rn(make_float2(ex2_ftz(fminf(az.x, 60.f)), ex2_ftz(fminf(az.y, 60.f))), one);
+          const float2 pp = __fmul2_rn(pr, pz);
+          const float2 ip = make_float2(rcp_ftz(pp.x), rcp_ftz(pp.y));
+          const float2 r = __fmul2_rn(ip, pz), z = __fmul2_rn(ip, pr);
+          const float2 ghn = __fadd2_rn(make_float2(__uint_as_float(gh[e]), __uint_as_float(gh[e + 1])), b_h);
+          const float2 gin = __fadd2_rn(make_float2(__uint_as_float(gi[e]), __uint_as_float(gi[e + 1])), b_i);
+          const float2 c = __ffma2_rn(r, ghn, gin);
+          const float2 pc = __fadd2_rn(make_float2(ex2_ftz(c.x), ex2_ftz(c.y)), one);
+          const float2 q = make_float2(rcp_ftz(pc.x), rcp_ftz(pc.y));
+          const float2 n = __ffma2_rn(make_float2(-2.0f, -2.0f), q, one);
+          const float2 hp = make_float2(h[half * 8 + e], h[half * 8 + e + 1]);
+          const float2 hv = __ffma2_rn(z, __fadd2_rn(hp, make_float2(-n.x, -n.y)), n);      // (1 - z) n + z h
+          hn[e] = hv.x; hn[e + 1] = hv.y;
+          h[half * 8 + e] = hv.x; h[half * 8 + e + 1] = hv.y;
+        }
+#endif
+        uint4 hi, lo;
+        split8_f16(hn, hi, lo);
+        tmem_st4(lane_base + TM_HHI + cg * 8 + half * 4, hi.x, hi.y, hi.z, hi.w);      // units 2c, 2c+1 -> column c
+        tmem_st4(lane_base + TM_HLO + cg * 8 + half * 4, lo.x, lo.y, lo.z, lo.w);
+        if (live) {
+          *reinterpret_cast<float4*>(hdst + half * 8) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+          *reinterpret_cast<float4*>(hdst + half * 8 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        }
+      }
+      TL(3);
+      if (t + 2 < T) store_x(t & 1, xv);                     // x_mma(t) (reader of this buffer) completed with the commit
+      TL(4);
+      if (t + 1 < T) {
+        tmem_st_wait();
+        fence_async_smem();                                  // generic-proxy smem writes -> visible to the tensor core
+        tc_fence_before();
+        asm volatile("bar.arrive 1, %0;" ::"n"(ITC_NT) : "memory");   // hand over to the issuer, do not wait
+      }
     }
   }
+  tc_fence_before();
+  __syncthreads();
   tc_fence_after();
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
@@ -229,8 +315,8 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.hcat[1] = e.sc.hcat_e;
   p.Fp[0] = NDF / 2;
   p.Fp[1] = e.d.fe[3];
-  p.wimg[0] = e.w.dprnn_df[blk].tc_intra;  p.bias[0] = e.w.dprnn_df[blk].i_bias;
-  p.wimg[1] = e.w.dprnn_erb[blk].tc_intra; p.bias[1] = e.w.dprnn_erb[blk].i_bias;
+  p.wimg[0] = e.w.dprnn_df[blk].tc_intra;  p.bias[0] = e.w.dprnn_df[blk].tc_intra_bias;
+  p.wimg[1] = e.w.dprnn_erb[blk].tc_intra; p.bias[1] = e.w.dprnn_erb[blk].tc_intra_bias;
   p.B = B;
   p.tiles = (B + 127) / 128;
   k_dprnn_intra_tc<<<4 * p.tiles, ITC_NT, INTRA_TC_SMEM, st>>>(p);

@@ -28,6 +28,7 @@ from .spec import CONV_CH, DF_ORDER, GRU_DIM, NB_DF, ModelSpec, vorbis_window
 MAGIC = b"DPDFW001"
 NAME_LEN = 56
 ALIGN = 32  # floats
+LOG2E = 1.4426950408889634
 BN_EPS = 1e-5
 
 
@@ -281,9 +282,14 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             t[f"{q}.tc.gates"] = np.concatenate([umma_operand(m[g * C:(g + 1) * C]) for m in (wih, whh) for g in range(3)])
             t[f"{q}.tc.fc2_w"] = umma_operand(sd[f"{p}.fc_inter.weight"])
             # FP16 hi/lo operand images of the intra-frame GRU (k_dprnn_intra_tc): per direction
-            # [W_ih hi | W_ih lo | W_hh hi | W_hh lo], each [192][64] halves stored as raw bytes in the f32 blob
+            # [W_ih hi | W_ih lo | W_hh hi | W_hh lo], each [192][64] halves stored as raw bytes in the f32 blob.
+            # The exponent scales of the gate non-linearities are folded into rows and biases: the kernel
+            # evaluates sigmoid(a) = 1 / (1 + 2^(-log2(e) a)) and tanh(c) = 1 - 2 / (1 + 2^(2 log2(e) c)).
+            gscale = np.repeat(np.array([-LOG2E, -LOG2E, 2.0 * LOG2E]), C).astype(np.float32)[:, None]
             t[f"{q}.tc.intra"] = np.concatenate([
-                umma_operand16(sd[f"{p}.intra_gru.{m}_l0{sfx}"]) for sfx in ("", "_reverse") for m in ("weight_ih", "weight_hh")])
+                umma_operand16(sd[f"{p}.intra_gru.{m}_l0{sfx}"] * gscale) for sfx in ("", "_reverse") for m in ("weight_ih", "weight_hh")])
+            t[f"{q}.tc.intra_bias"] = t[f"{q}.intra.bias"] * np.repeat(
+                np.array([-LOG2E, -LOG2E, 2.0 * LOG2E, 2.0 * LOG2E]), C).astype(np.float32).reshape(1, 4, C)
 
     def gl(out: str, prefix: str, groups: int):
         t[f"{out}.w"], t[f"{out}.b"] = _gl_pack(sd, prefix, groups)

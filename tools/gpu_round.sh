@@ -14,10 +14,21 @@ for w in $WHAT; do
       echo "pytest exit $?" >> $OUT/${TAG}_pytest_gpu.log; tail -3 $OUT/${TAG}_pytest_gpu.log ;;
     debugtc)
       DPDF_OPTIONS=intra_tc=1 timeout 600 python tools/gpu_debug.py dpdfnet2 > $OUT/${TAG}_debug_tc.log 2>&1; tail -25 $OUT/${TAG}_debug_tc.log ;;
+    quick)   # kernel-time table at two batch sizes, no ladder
+      for b in 1024 8192; do
+        timeout 600 python bench.py --steps 50 --warmup 10 --no-ladder --batch $b --cpu-hops 2 --cpu-batch 16 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('B=$b', round(d['ms_per_step'], 4), 'ms/hop', int(d['value']), 'sf/s', d['kernel_ms'])
+    else:
+        print(l, end='')
+" | tee -a $OUT/${TAG}_quick.log
+      done ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; tail -2 $OUT/${TAG}_smoke.log ;;
     bench)
-      timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+      timeout 900 python bench.py ${BENCH_ARGS:-} > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
       echo "bench exit $?"; tail -c 3000 $OUT/${TAG}_bench.json ;;
     ref)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
