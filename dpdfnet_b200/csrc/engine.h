@@ -159,7 +159,7 @@ struct Engine {
   int use_graph = 1;
   int intra_bt = 0;               // 0 = auto
   int intra_tc = 2;               // intra-frame GRU on tcgen05 (FP16 split): 0 never, 1 always, 2 = when B >= intra_tc_min
-  int intra_tc_min = 512;
+  int intra_tc_min = 1024;
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
   std::map<int, cudaGraphExec_t> graphs;     // keyed by B
   std::vector<std::pair<std::string, float>> ktimes;

@@ -21,6 +21,12 @@
 #include "engine.h"
 #include "tc_common.cuh"
 
+#ifndef ITC_POLY
+#define ITC_POLY 0          // 1: r, z exponentials on the FMA pipe instead of MUFU (measured: no gain, the gate phase is issue/latency bound)
+#endif
+#ifndef ITC_XEARLY
+#define ITC_XEARLY 0        // convert x_{t+2} inside the gate loop instead of after it
+#endif
 namespace dpdf {
 
 namespace {
@@ -32,7 +38,9 @@ constexpr int ITC_NT = ITC_GATE + 32;       // + warp 16: the MMA issuer (does n
 constexpr int W_IMG = 192 * 64 * 2;         // bytes of one FP16 [192][64] weight image
 constexpr int A_IMG = 128 * 64 * 2;         // bytes of one FP16 [128][64] activation image
 constexpr int OFF_X = 4 * W_IMG;            // x images: [2 buffers][hi | lo]
-constexpr int OFF_BIAS = OFF_X + 4 * A_IMG; // [4][64] floats
+constexpr int OFF_ST = OFF_X + 4 * A_IMG;   // h_t staging for the coalesced write-out: [2 buffers][128 rows][16 chunks of 16 B],
+constexpr int ST_BUF = 128 * 256;           // chunk index XOR-swizzled with the row so that both the per-row writes of the gate
+constexpr int OFF_BIAS = OFF_ST + 2 * ST_BUF;  // warps and the row-contiguous reads of the write-out are conflict-free
 constexpr int OFF_BAR = OFF_BIAS + 1024;    // two mbarriers + TMEM base slot
 constexpr size_t INTRA_TC_SMEM = OFF_BAR + 64;
 // tensor-memory columns: P[2] = (r | z | in) double buffered, hn single (written and drained inside one step),
@@ -44,6 +52,25 @@ __device__ __forceinline__ float ex2_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+#if ITC_POLY
+// 2^x for a pair of values on the FMA pipe (the gate math is MUFU bound: 16 lanes/clk/SM): round-to-nearest split
+// x = n + f with the 1.5*2^23 trick, degree-5 minimax polynomial for 2^f on [-0.5, 0.5] (2.3e-7 max relative error
+// in FP32 Horner form, the same as ex2.approx), 2^n by adding n to the exponent field.  Needs -125 <= x <= 126.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 y = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(y, nmagic);
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 q = __ffma2_rn(make_float2(0.0013276409590616822f, 0.0013276409590616822f), f, make_float2(0.00967552699148655f, 0.00967552699148655f));
+  q = __ffma2_rn(q, f, make_float2(0.05550713464617729f, 0.05550713464617729f));
+  q = __ffma2_rn(q, f, make_float2(0.24022120237350464f, 0.24022120237350464f));
+  q = __ffma2_rn(q, f, make_float2(0.6931469440460205f, 0.6931469440460205f));
+  q = __ffma2_rn(q, f, make_float2(1.0000001192092896f, 1.0000001192092896f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(y.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(y.y) << 23)));
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+#endif
 __device__ __forceinline__ float rcp_ftz(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -75,10 +102,15 @@ struct IntraTcParams {
 #define TL(slot) do { } while (0)
 #endif
 
+#ifdef ITC_MAXNREG
+__global__ void __maxnreg__(ITC_MAXNREG) k_dprnn_intra_tc(IntraTcParams p) {
+#else
 __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
+#endif
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* Wsm = smem_raw;
   unsigned char* Xsm = smem_raw + OFF_X;
+  unsigned char* Ssm = smem_raw + OFF_ST;
   float* sb = reinterpret_cast<float*>(smem_raw + OFF_BIAS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + OFF_BAR);       // [0] weights landed, [1] step accumulators complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -129,15 +161,16 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
       v[i][4] = c.x; v[i][5] = c.y; v[i][6] = c.z; v[i][7] = c.w;
     }
   };
+  auto store_x1 = [&](int buf, const float (&v)[2][8], int i) {
+    uint4 hi, lo;
+    split8_f16(v[i], hi, lo);
+    unsigned char* dst = Xsm + buf * 2 * A_IMG + img16_off(xr_[i], xkc);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
+  };
   auto store_x = [&](int buf, const float (&v)[2][8]) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      uint4 hi, lo;
-      split8_f16(v[i], hi, lo);
-      unsigned char* dst = Xsm + buf * 2 * A_IMG + img16_off(xr_[i], xkc);
-      *reinterpret_cast<uint4*>(dst) = hi;
-      *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
-    }
+    store_x1(buf, v, 0);
+    store_x1(buf, v, 1);
   };
   float xv[2][8];
   if (warp < 16) {
@@ -204,13 +237,15 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
       umma_commit(bars + 1);
       if (T > 1) x_mma(1);
     }
-    for (int t = 0; t + 1 < T; ++t) {
-      asm volatile("bar.sync 1, %0;" ::"n"(ITC_NT) : "memory");     // h_t written, P[t & 1] drained, x_{t+2} staged
+    for (int t = 0; t < T; ++t) {
+      asm volatile("bar.sync 1, %0;" ::"n"(ITC_NT) : "memory");     // h_t written (TMEM + staging), P[t & 1] drained, x_{t+2} staged
       TL(5);
-      if (lane == 0) {
+      if (lane == 0 && t + 1 < T) {
         tc_fence_after();
         h_mma(t + 1);
-        umma_commit(bars + 1);
+      }
+      if (lane == 0) {
+        if (t + 1 < T) umma_commit(bars + 1);
         TL(6);
 #ifndef ITC_NO_X
         if (t + 2 < T) x_mma(t + 2);
@@ -224,8 +259,6 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
     float h[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) h[i] = 0.f;
-    const int bme = b0 + row;
-    const bool live = bme < p.B;
     const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16);
     const uint32_t lane_addr = lane_base + cg * 16;
     for (int t = 0; t < T; ++t) {
@@ -234,8 +267,6 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
       mbar_wait(bars + 1, t & 1);
       tc_fence_after();
       TL(1);
-      const int f = dir ? T - 1 - t : t;
-      float* hdst = hg + ((size_t)bme * T + f) * 2 * C + dir * C + cg * 16;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t gr[8], gz[8], gi[8], gh[8];
@@ -244,6 +275,11 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
         tmem_ld8_nowait(ta + 64, gz);
         tmem_ld8_nowait(ta + 128, gi);
         tmem_ld8_nowait(lane_addr + TM_HN + half * 8, gh);
+        // x_{t+2} item of this half: converted and stored while the TMEM loads are in flight and under the MUFU-bound
+        // gate math (x_mma(t), the reader of this buffer, completed with the commit just waited on)
+#if ITC_XEARLY
+        if (t + 2 < T) store_x1(t & 1, xv, half);
+#endif
         tmem_ld_wait();
         if (half == 0) TL(2);
         // Gate math on unit pairs (packed f32x2 FMA-pipe ops).  The operand images and biases carry the exponent
@@ -264,8 +300,13 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
           const float2 ar = __fadd2_rn(make_float2(__uint_as_float(gr[e]), __uint_as_float(gr[e + 1])), b_r);
           const float2 az = __fadd2_rn(make_float2(__uint_as_float(gz[e]), __uint_as_float(gz[e + 1])), b_z);
           // 2^60 * 2^60 stays finite in the shared reciprocal; sigmoid(-41) = 1e-18 is already 0 in FP32 terms
+#if ITC_POLY
+          const float2 pr = __fadd2_rn(ex2_poly2(make_float2(clampf(ar.x, -125.f, 60.f), clampf(ar.y, -125.f, 60.f))), one);
+          const float2 pz = __fadd2_rn(ex2_poly2(make_float2(clampf(az.x, -125.f, 60.f), clampf(az.y, -125.f, 60.f))), one);
+#else
           const float2 pr = __fadd2_rn(make_float2(ex2_ftz(fminf(ar.x, 60.f)), ex2_ftz(fminf(ar.y, 60.f))), one);
           const float2 pz = __fadd2_rn(make_float2(ex2_ftz(fminf(az.x, 60.f)), ex2_ftz(fminf(az.y, 60.f))), one);
+#endif
           const float2 pp = __fmul2_rn(pr, pz);
           const float2 ip = make_float2(rcp_ftz(pp.x), rcp_ftz(pp.y));
           const float2 r = __fmul2_rn(ip, pz), z = __fmul2_rn(ip, pr);
@@ -285,19 +326,40 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
         split8_f16(hn, hi, lo);
         tmem_st4(lane_base + TM_HHI + cg * 8 + half * 4, hi.x, hi.y, hi.z, hi.w);      // units 2c, 2c+1 -> column c
         tmem_st4(lane_base + TM_HLO + cg * 8 + half * 4, lo.x, lo.y, lo.z, lo.w);
-        if (live) {
-          *reinterpret_cast<float4*>(hdst + half * 8) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-          *reinterpret_cast<float4*>(hdst + half * 8 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-        }
+        unsigned char* srow = Ssm + (t & 1) * ST_BUF + row * 256;
+        const int c0 = cg * 4 + half * 2;
+        *reinterpret_cast<float4*>(srow + (((c0) ^ (row & 15)) << 4)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(srow + (((c0 + 1) ^ (row & 15)) << 4)) = make_float4(hn[4], hn[5], hn[6], hn[7]);
       }
       TL(3);
+#if !ITC_XEARLY
       if (t + 2 < T) store_x(t & 1, xv);                     // x_mma(t) (reader of this buffer) completed with the commit
+#endif
       TL(4);
-      if (t + 1 < T) {
-        tmem_st_wait();
-        fence_async_smem();                                  // generic-proxy smem writes -> visible to the tensor core
-        tc_fence_before();
-        asm volatile("bar.arrive 1, %0;" ::"n"(ITC_NT) : "memory");   // hand over to the issuer, do not wait
+      tmem_st_wait();
+      fence_async_smem();                                    // generic-proxy smem writes -> visible to the tensor core / TMA
+      tc_fence_before();
+      asm volatile("bar.arrive 1, %0;" ::"n"(ITC_NT) : "memory");     // hand over to the issuer, do not wait
+      // Write-out of h_t while the recurrent MMAs of the next step run (the gate warps would only wait): staging[t & 1]
+      // -> hcat[b][f][dir*64 ..], two full 256-byte rows per warp instruction.  The buffer is rewritten in step t + 2,
+      // which no warp can reach before every warp has passed this point of step t + 1.
+      asm volatile("bar.sync 2, %0;" ::"n"(ITC_GATE) : "memory");     // all staging rows of this step written
+      {
+        const int f = dir ? T - 1 - t : t;
+        const unsigned char* sbuf = Ssm + (t & 1) * ST_BUF;
+        const int nvalid = min(128, p.B - b0);
+        float* gdst = hg + ((size_t)b0 * T + f) * 2 * C + dir * C + (tid & 15) * 4;
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (tid >> 4) + 32 * i;
+          v[i] = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (tid >> 4) + 32 * i;
+          if (r < nvalid) *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = v[i];
+        }
       }
     }
   }
