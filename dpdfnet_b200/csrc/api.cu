@@ -101,8 +101,8 @@ static int bind_weights(Engine& e) {
       x.r_bias = W(q + ".inter.bias", 4 * C);
       x.fc2_w = W(q + ".inter.fc_w", C * C);       x.fc2_b = W(q + ".inter.fc_b", C);
       x.ln2_g = W(q + ".inter.ln_g", C);           x.ln2_b = W(q + ".inter.ln_b", C);
-      x.tc_fc_w = W(q + ".tc.fc_w", 2 * C * 2 * C); x.tc_gates = W(q + ".tc.gates", 6 * 2 * C * C);
-      x.tc_fc2_w = W(q + ".tc.fc2_w", 2 * C * C);
+      x.tc_fc_w = W(q + ".tc.fc_w", 2 * C * C);     x.tc_gates = W(q + ".tc.gates", 6 * C * C);
+      x.tc_fc2_w = W(q + ".tc.fc2_w", C * C);
       x.tc_intra = W(q + ".tc.intra", 2 * 4 * 192 * C / 2);
       x.tc_intra_bias = W(q + ".tc.intra_bias", 2 * 4 * C);
     }

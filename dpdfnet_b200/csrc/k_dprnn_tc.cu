@@ -2,16 +2,17 @@
 //
 // Same math as k_dprnn_post (fc_intra + LayerNorm + residual, inter-frame GRUCell, fc_inter + LayerNorm +
 // residual; layers.py:178-196) for a 128-row tile, but every matrix product is a chain of
-// tcgen05.mma.kind::tf32 instructions with the FP32 accumulators in tensor memory.  FP32 accuracy is kept
-// with the error-compensated 3xTF32 scheme: every operand is split as x = hi + lo with hi, lo exactly
-// representable in TF32 (cvt.rna), and D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (the dropped lo*lo term and
-// the rounding of lo are ~2^-24 relative).  Weights are split and laid out on the host
-// (weights.py:umma_operand); activations are split on the fly while they are staged into shared memory.
+// tcgen05.mma.kind::f16 instructions with the FP32 accumulators in tensor memory.  FP32 accuracy is kept
+// with the error-compensated split scheme: every operand is x = hi + lo with hi, lo in FP16 (11-bit significands,
+// like TF32, at half the bytes and twice the tensor rate), and D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (the dropped
+// lo*lo term and the rounding of lo are ~2^-22 relative).  Weights are split and laid out on the host
+// (weights.py:umma_operand16); activations are split on the fly while they are staged into shared memory.
 //
 // Operand layout: K-major, SWIZZLE_NONE ("interleave"): 8 rows x 16 B core matrices (128 B contiguous), core
-// matrices adjacent in K are LBO = 128 B apart, 8-row groups are SBO = (K/4)*128 B apart.
-// One CTA = 128 threads; thread t owns TMEM lane t = tile row t, so LayerNorm and the GRU gate math are
-// row-local register code straight out of tcgen05.ld (no shuffles).
+// matrices adjacent in K are LBO = 128 B apart, 8-row groups are SBO = (K/8)*128 B = 1 KB apart.
+// One CTA = 512 threads, thread (row = TMEM lane, 16-column group): LayerNorm and the GRU gate math are register
+// code straight out of tcgen05.ld.  103 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, so the
+// load -> MMA -> epilogue chain of one tile overlaps with the other's.
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -21,11 +22,18 @@ namespace {
 
 using namespace tc;
 
-// float offset of element (r, k) of a [128][64] operand image (K-major, SWIZZLE_NONE, SBO = 2048 B)
-__device__ __forceinline__ int core_off64(int r, int k) { return (r >> 3) * 512 + (k >> 2) * 32 + (r & 7) * 4 + (k & 3); }
-
 constexpr int TC_NT = 512;        // 16 warps: warp w -> TMEM lane quadrant w & 3, 16-column group w >> 2
-constexpr int IMG = 8192;         // floats of one [128][64] operand image (32 KB)
+constexpr int IMG = 128 * 64 * 2; // bytes of one FP16 [128][64] activation image (16 KB)
+constexpr int WSLAB = 2 * 64 * 64 * 2;   // bytes of one [64][64] weight slab, hi image | lo image (16 KB)
+
+__device__ __forceinline__ float2 h2f(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+// the 8 values of a 16-byte operand row chunk, reconstructed as hi + lo
+__device__ __forceinline__ void unsplit8(const uint4& hi, const uint4& lo, float (&v)[8]) {
+  const float2 a0 = h2f(hi.x), a1 = h2f(hi.y), a2 = h2f(hi.z), a3 = h2f(hi.w);
+  const float2 b0 = h2f(lo.x), b1 = h2f(lo.y), b2 = h2f(lo.z), b3 = h2f(lo.w);
+  v[0] = a0.x + b0.x; v[1] = a0.y + b0.y; v[2] = a1.x + b1.x; v[3] = a1.y + b1.y;
+  v[4] = a2.x + b2.x; v[5] = a2.y + b2.y; v[6] = a3.x + b3.x; v[7] = a3.y + b3.y;
+}
 
 }  // namespace
 
@@ -45,22 +53,29 @@ struct PostTcParams {
   int tiles0, B;
 };
 
-constexpr size_t POST_TC_SMEM = (size_t)(4 * IMG + 2 * IMG + 640 + 1024) * sizeof(float) + 128 * sizeof(long long) +
-                                128 * sizeof(int) + 64;
+constexpr int PT_OFF_W = 4 * IMG;                       // two weight slab buffers
+constexpr int PT_OFF_SP = PT_OFF_W + 2 * WSLAB;         // 640 floats of small parameters
+constexpr int PT_OFF_RED = PT_OFF_SP + 640 * 4;         // [2][4][128] LayerNorm partials
+constexpr int PT_OFF_HOFF = PT_OFF_RED + 1024 * 4;      // 128 x int64 state offsets
+constexpr int PT_OFF_COMMIT = PT_OFF_HOFF + 128 * 8;    // 128 x int
+constexpr int PT_OFF_BAR = PT_OFF_COMMIT + 128 * 4;     // 5 mbarriers + TMEM base slot
+constexpr size_t POST_TC_SMEM = PT_OFF_BAR + 64;
 
-// One CTA = one 128-row tile.  Thread 0 is the single MMA issuer and streams the nine 32 KB weight slabs of the
+// One CTA = one 128-row tile.  Thread 0 is the single MMA issuer and streams the nine 16 KB weight slabs of the
 // block (fc_intra K-halves, six GRU gate slabs, fc_inter) through a two-buffer ring with 1-D bulk copies that
 // complete on mbarriers, two slabs ahead of the tensor core; the other 511 threads never wait for weights.
-__global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
-  extern __shared__ __align__(128) float smem[];
-  float* RA = smem;                                 // four activation operand images
-  float* RW = RA + 4 * IMG;                         // two weight slab buffers
-  float* sp = RW + 2 * IMG;                         // small parameters
-  float* red = sp + 640;                            // [2][4][128] LayerNorm partials
-  long long* s_hoff = reinterpret_cast<long long*>(red + 1024);
-  int* s_commit = reinterpret_cast<int*>(s_hoff + 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_commit + 128);   // [0,1] slab full, [2,3] slab consumed, [4] phase result ready
-  __shared__ uint32_t tmem_base_s;
+// TMEM columns: [0,64) fc_intra, then the gate pre-activations r [0,64) z [64,128) in [128,192) hn [192,256),
+// then fc_inter in [0,64) again (each phase is drained by all threads before the next one is issued).
+__global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* RA = smem_raw;                     // four activation operand images
+  unsigned char* RW = smem_raw + PT_OFF_W;
+  float* sp = reinterpret_cast<float*>(smem_raw + PT_OFF_SP);
+  float* red = reinterpret_cast<float*>(smem_raw + PT_OFF_RED);
+  long long* s_hoff = reinterpret_cast<long long*>(smem_raw + PT_OFF_HOFF);
+  int* s_commit = reinterpret_cast<int*>(smem_raw + PT_OFF_COMMIT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + PT_OFF_BAR);   // [0,1] slab full, [2,3] slab consumed, [4] phase result ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
@@ -92,29 +107,29 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
     for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
   __syncthreads();                                       // barriers initialised, s_hoff visible
 
   // ---- weight slab ring (thread 0 only) --------------------------------------------------------------------
-  auto slab_src = [&](int i) -> const float* {
-    if (i < 2) return q.tc_fc_w + (size_t)i * IMG;
-    if (i == 8) return q.tc_fc2_w;
+  auto slab_src = [&](int i) -> const unsigned char* {
+    if (i < 2) return reinterpret_cast<const unsigned char*>(q.tc_fc_w) + (size_t)i * WSLAB;
+    if (i == 8) return reinterpret_cast<const unsigned char*>(q.tc_fc2_w);
     const int pidx = i - 2;                                // processing order r(y),r(h),z(y),z(h),n(y),n(h)
-    return q.tc_gates + (size_t)((pidx & 1) ? 3 + (pidx >> 1) : (pidx >> 1)) * IMG;
+    return reinterpret_cast<const unsigned char*>(q.tc_gates) + (size_t)((pidx & 1) ? 3 + (pidx >> 1) : (pidx >> 1)) * WSLAB;
   };
   auto load_slab = [&](int i) {
     const int buf = i & 1;
     if (i >= 2) mbar_wait(bars + 2 + buf, ((i - 2) >> 1) & 1);      // MMAs of the previous tenant have completed
-    mbar_expect_tx(bars + buf, IMG * 4);
-    bulk_g2s(RW + buf * IMG, slab_src(i), IMG * 4, bars + buf);
+    mbar_expect_tx(bars + buf, WSLAB);
+    bulk_g2s(RW + buf * WSLAB, slab_src(i), WSLAB, bars + buf);
   };
   if (tid == 0) { load_slab(0); load_slab(1); }
 
   // ---- stage the hcat tile as two K=64 operand image pairs (split on the fly) --------------------------------
+  // a warp instruction covers 8 rows x 16 floats; thread = (row rr of the group, float4 cc): its four halves are
+  // 8 bytes of a 16-byte operand row chunk, the 32 lanes write two full 128-byte core matrices
   const int rr = lane >> 2, cc = lane & 3;
+  const int sub_off = (cc >> 1) * 128 + rr * 16 + (cc & 1) * 8;      // inside a [8 rows][16 k] block of an image
   {
     const float* hc = q.hcat + row0 * 2 * C;
     float4 v[8];
@@ -127,48 +142,43 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int blk = warp + 16 * i, rg = blk >> 3, kb = blk & 7;
-      float4 h, l;
-      split4(v[i], h, l);
-      const int off = (kb >> 2) * 2 * IMG + rg * 512 + ((kb & 3) * 4 + cc) * 32 + rr * 4;
-      *reinterpret_cast<float4*>(RA + off) = h;
-      *reinterpret_cast<float4*>(RA + IMG + off) = l;
+      uint2 h, l;
+      split2_f16(v[i].x, v[i].y, h.x, l.x);
+      split2_f16(v[i].z, v[i].w, h.y, l.y);
+      unsigned char* dst = RA + (kb >> 2) * 2 * IMG + rg * 1024 + (kb & 3) * 256 + sub_off;
+      *reinterpret_cast<uint2*>(dst) = h;
+      *reinterpret_cast<uint2*>(dst + IMG) = l;
     }
   }
-  // prefetch what the first epilogue needs while the tensor core works: residual input and h_prev
-  float4 xv[4], hv[4];
+  // prefetch what the first epilogue needs while the tensor core works: the residual input
+  float4 xv[4];
   {
     const float* xr = q.xin + (size_t)(row0 + row) * C + cg * 16;
 #pragma unroll
     for (int c = 0; c < 4; ++c) xv[c] = row < valid ? __ldg(reinterpret_cast<const float4*>(xr + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {                          // 64 blocks, 4 per warp
-      const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
-      const int r = rg * 8 + rr;
-      hv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = *tmem_slot;
   const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16) + cg * 16;
-  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // M=128, N=64, tf32, f32 acc
+  constexpr uint32_t IDESC = idesc_f16(128, 64);
   const uint32_t a_base = smem_u32(RA), w_base = smem_u32(RW);
 
-  // slab i: D[col .. col+64) (+)= A[128][64] * W_i[64][64]^T, three TF32 passes per 8-wide k-step
+  // slab i: D[col .. col+64) (+)= A[128][64] * W_i[64][64]^T, three FP16 passes per 16-wide k-step
   auto run_slab = [&](int i, int a_img, uint32_t col, uint32_t accumulate) {
     const int buf = i & 1;
     mbar_wait(bars + buf, (i >> 1) & 1);                   // slab landed (async proxy write -> async proxy read)
-    const uint32_t ah = a_base + a_img * (IMG * 4), al = ah + IMG * 4;
-    const uint32_t bh = w_base + buf * (IMG * 4), bl = bh + IMG * 2;
+    const uint32_t ah = a_base + a_img * IMG, al = ah + IMG;
+    const uint32_t bh = w_base + buf * WSLAB, bl = bh + WSLAB / 2;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const uint64_t dah = umma_desc(ah + ks * 256, 2048), dal = umma_desc(al + ks * 256, 2048);
-      const uint64_t dbh = umma_desc(bh + ks * 256, 2048), dbl = umma_desc(bl + ks * 256, 2048);
-      umma_tf32(tmem + col, dah, dbh, IDESC, accumulate);
-      umma_tf32(tmem + col, dal, dbh, IDESC, 1);
-      umma_tf32(tmem + col, dah, dbl, IDESC, 1);
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t dah = umma_desc(ah + ks * 256, 1024), dal = umma_desc(al + ks * 256, 1024);
+      const uint64_t dbh = umma_desc(bh + ks * 256, 1024), dbl = umma_desc(bl + ks * 256, 1024);
+      umma_f16(tmem + col, dah, dbh, IDESC, accumulate);
+      umma_f16(tmem + col, dal, dbh, IDESC, 1);
+      umma_f16(tmem + col, dah, dbl, IDESC, 1);
       accumulate = 1;
     }
     umma_commit(bars + 2 + buf);
@@ -185,10 +195,8 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
   mbar_wait(bars + 4, 0);
   tc_fence_after();
 
-  float* y_hi = RA;
-  float* y_lo = RA + IMG;
-  float* h_hi = RA + 2 * IMG;
-  float* h_lo = RA + 3 * IMG;
+  unsigned char* y_hi = RA;                                // images 0, 1: y = block input of the inter-frame half
+  unsigned char* h_hi = RA + 2 * IMG;                      // images 2, 3: h_prev, then h_new
   // row statistics over 64 columns held by the four column-group warps of a lane quadrant
   auto layernorm16 = [&](float (&v)[16], const float* g, const float* b) {
     float s = 0.f;
@@ -207,28 +215,38 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
     for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * g[cg * 16 + i] + b[cg * 16 + i];
   };
   {
+    float4 hv[4];                                          // h_prev tile: in flight under the LayerNorm (the other CTA of the SM covers the rest)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                          // 64 blocks of 8 rows x 16 floats, 4 per warp
+      const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+      const int r = rg * 8 + rr;
+      hv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float v[16];
     tmem_ld16(lane_base, v);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += sp[cg * 16 + i];
-    layernorm16(v, sp + 64, sp + 128);
+    layernorm16(v, sp + 64, sp + 128);                     // its barriers also order the hcat image reads (MMAs done) before the writes below
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {                           // y = LN(...) + x, staged as the hi / lo operand of the gate GEMMs
-      const float4 y = make_float4(v[c * 4] + xv[c].x, v[c * 4 + 1] + xv[c].y, v[c * 4 + 2] + xv[c].z, v[c * 4 + 3] + xv[c].w);
-      float4 h, l;
-      split4(y, h, l);
-      const int off = core_off64(row, cg * 16 + c * 4);
-      *reinterpret_cast<float4*>(y_hi + off) = h;
-      *reinterpret_cast<float4*>(y_lo + off) = l;
+    for (int c = 0; c < 2; ++c) {                           // y = LN(...) + x, staged as the hi / lo operand of the gate GEMMs
+      float y[8];
+      y[0] = v[c * 8 + 0] + xv[2 * c].x; y[1] = v[c * 8 + 1] + xv[2 * c].y; y[2] = v[c * 8 + 2] + xv[2 * c].z; y[3] = v[c * 8 + 3] + xv[2 * c].w;
+      y[4] = v[c * 8 + 4] + xv[2 * c + 1].x; y[5] = v[c * 8 + 5] + xv[2 * c + 1].y; y[6] = v[c * 8 + 6] + xv[2 * c + 1].z; y[7] = v[c * 8 + 7] + xv[2 * c + 1].w;
+      uint4 h, l;
+      split8_f16(y, h, l);
+      const int off = img16_off(row, cg * 2 + c);
+      *reinterpret_cast<uint4*>(y_hi + off) = h;
+      *reinterpret_cast<uint4*>(y_hi + IMG + off) = l;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {                           // h_prev tile (loaded before the wait) -> hi / lo images
       const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
-      float4 h, l;
-      split4(hv[i], h, l);
-      const int off = rg * 512 + (kb * 4 + cc) * 32 + rr * 4;
-      *reinterpret_cast<float4*>(h_hi + off) = h;
-      *reinterpret_cast<float4*>(h_lo + off) = l;
+      uint2 h, l;
+      split2_f16(hv[i].x, hv[i].y, h.x, l.x);
+      split2_f16(hv[i].z, hv[i].w, h.y, l.y);
+      unsigned char* dst = h_hi + rg * 1024 + kb * 256 + sub_off;
+      *reinterpret_cast<uint2*>(dst) = h;
+      *reinterpret_cast<uint2*>(dst + IMG) = l;
     }
   }
   fence_async_smem();
@@ -236,59 +254,56 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
   __syncthreads();
   tc_fence_after();
 
-  // ---- phase 2: GRU gate pre-activations in TMEM: r [64,128) z [128,192) in [192,256) hn [256,320) ------------
+  // ---- phase 2: GRU gate pre-activations in TMEM: r [0,64) z [64,128) in [128,192) hn [192,256) ---------------
   if (tid == 0) {
-    run_slab(2, 0, 64, 0);    // Wih_r * y
-    run_slab(3, 2, 64, 1);    // Whh_r * h
+    run_slab(2, 0, 0, 0);     // Wih_r * y
+    run_slab(3, 2, 0, 1);     // Whh_r * h
     load_slab(4);
     load_slab(5);
-    run_slab(4, 0, 128, 0);   // Wih_z * y
-    run_slab(5, 2, 128, 1);   // Whh_z * h
+    run_slab(4, 0, 64, 0);    // Wih_z * y
+    run_slab(5, 2, 64, 1);    // Whh_z * h
     load_slab(6);
     load_slab(7);
-    run_slab(6, 0, 192, 0);   // Wih_n * y
-    run_slab(7, 2, 256, 0);   // Whh_n * h
+    run_slab(6, 0, 128, 0);   // Wih_n * y
+    run_slab(7, 2, 192, 0);   // Whh_n * h
     umma_commit(bars + 4);
     load_slab(8);
   }
   mbar_wait(bars + 4, 1);
   tc_fence_after();
-  {
-    float gr[16], gz[16], gi[16], gh[16];
-    tmem_ld16(lane_base + 64, gr);
-    tmem_ld16(lane_base + 128, gz);
-    tmem_ld16(lane_base + 192, gi);
-    tmem_ld16(lane_base + 256, gh);
 #pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-      const int k = cg * 16 + c4 * 4;
-      const int off = core_off64(row, k);
-      const float4 ph = *reinterpret_cast<const float4*>(h_hi + off);
-      const float4 pl = *reinterpret_cast<const float4*>(h_lo + off);
-      const float hp[4] = {ph.x + pl.x, ph.y + pl.y, ph.z + pl.z, ph.w + pl.w};
-      float hn[4];
+  for (int c = 0; c < 2; ++c) {                             // two chunks of 8 units: bounded register footprint (2 CTAs / SM)
+    uint32_t gr[8], gz[8], gi[8], gh[8];
+    tmem_ld8_nowait(lane_base + c * 8, gr);
+    tmem_ld8_nowait(lane_base + 64 + c * 8, gz);
+    tmem_ld8_nowait(lane_base + 128 + c * 8, gi);
+    tmem_ld8_nowait(lane_base + 192 + c * 8, gh);
+    const int off = img16_off(row, cg * 2 + c);
+    float hp[8];
+    unsplit8(*reinterpret_cast<const uint4*>(h_hi + off), *reinterpret_cast<const uint4*>(h_hi + IMG + off), hp);
+    tmem_ld_wait();
+    float hn[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int u = k + e, i = c4 * 4 + e;
-        const float r = sigmoidf_(gr[i] + sp[192 + u]);
-        const float z = sigmoidf_(gz[i] + sp[256 + u]);
-        const float n = tanhf_(gi[i] + sp[320 + u] + r * (gh[i] + sp[384 + u]));
-        hn[e] = (1.0f - z) * n + z * hp[e];
-      }
-      float4 h, l;
-      split4(make_float4(hn[0], hn[1], hn[2], hn[3]), h, l);
-      *reinterpret_cast<float4*>(h_hi + off) = h;      // in place: this thread is the only reader of these 16 bytes
-      *reinterpret_cast<float4*>(h_lo + off) = l;
+    for (int e = 0; e < 8; ++e) {
+      const int u = cg * 16 + c * 8 + e;
+      const float r = sigmoidf_(__uint_as_float(gr[e]) + sp[192 + u]);
+      const float z = sigmoidf_(__uint_as_float(gz[e]) + sp[256 + u]);
+      const float n = tanhf_(__uint_as_float(gi[e]) + sp[320 + u] + r * (__uint_as_float(gh[e]) + sp[384 + u]));
+      hn[e] = (1.0f - z) * n + z * hp[e];
     }
+    uint4 h, l;
+    split8_f16(hn, h, l);
+    *reinterpret_cast<uint4*>(h_hi + off) = h;              // in place: this thread is the only reader of these 16 bytes
+    *reinterpret_cast<uint4*>(h_hi + IMG + off) = l;
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 
-  // ---- phase 3: acc[320,384) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena -----------
+  // ---- phase 3: acc[0,64) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena --------------
   if (tid == 0) {
-    run_slab(8, 2, 320, 0);
+    run_slab(8, 2, 0, 0);
     umma_commit(bars + 4);
   }
 #pragma unroll
@@ -296,40 +311,45 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_tc(PostTcParams p) {
     const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
     const int r = rg * 8 + rr;
     if (r < valid && s_commit[r]) {
-      const int off = rg * 512 + (kb * 4 + cc) * 32 + rr * 4;
-      const float4 a = *reinterpret_cast<const float4*>(h_hi + off), b = *reinterpret_cast<const float4*>(h_lo + off);
-      *reinterpret_cast<float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      const unsigned char* src = h_hi + rg * 1024 + kb * 256 + sub_off;
+      const uint2 a = *reinterpret_cast<const uint2*>(src), b = *reinterpret_cast<const uint2*>(src + IMG);
+      const float2 a0 = h2f(a.x), a1 = h2f(a.y), b0 = h2f(b.x), b1 = h2f(b.y);
+      *reinterpret_cast<float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4) = make_float4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y);
     }
+  }
+  float yv[16];                                             // y back from its operand images, before they become the output staging
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int off = img16_off(row, cg * 2 + c);
+    float t8[8];
+    unsplit8(*reinterpret_cast<const uint4*>(y_hi + off), *reinterpret_cast<const uint4*>(y_hi + IMG + off), t8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) yv[c * 8 + e] = t8[e];
   }
   mbar_wait(bars + 4, 0);
   tc_fence_after();
   {
     float v[16];
-    tmem_ld16(lane_base + 320, v);
+    tmem_ld16(lane_base, v);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += sp[448 + cg * 16 + i];
-    layernorm16(v, sp + 512, sp + 576);
+    layernorm16(v, sp + 512, sp + 576);                    // its barriers: every thread has read its y chunks
+    // output tile as FP32 [128][16 chunks of 16 B] over images 0/1 (32 KB), chunk XOR-swizzled with the row
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int off = core_off64(row, cg * 16 + c * 4);
-      const float4 a = *reinterpret_cast<const float4*>(y_hi + off);
-      const float4 b = *reinterpret_cast<const float4*>(y_lo + off);
-      *reinterpret_cast<float4*>(y_hi + off) =
-          make_float4(v[c * 4] + a.x + b.x, v[c * 4 + 1] + a.y + b.y, v[c * 4 + 2] + a.z + b.z, v[c * 4 + 3] + a.w + b.w);
-    }
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(RA + row * 256 + (((cg * 4 + c) ^ (row & 15)) << 4)) =
+          make_float4(v[c * 4] + yv[c * 4], v[c * 4 + 1] + yv[c * 4 + 1], v[c * 4 + 2] + yv[c * 4 + 2], v[c * 4 + 3] + yv[c * 4 + 3]);
   }
   tc_fence_before();
   __syncthreads();
   float* xo = q.xout + row0 * C;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {                             // coalesced write-out of the block output
-    const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
-    const int r = rg * 8 + rr;
+  for (int i = 0; i < 4; ++i) {                             // coalesced write-out of the block output: two rows per warp instruction
+    const int r = (tid >> 4) + 32 * i, ch = tid & 15;
     if (r < valid)
-      *reinterpret_cast<float4*>(xo + (size_t)r * C + kb * 16 + cc * 4) =
-          *reinterpret_cast<const float4*>(y_hi + rg * 512 + (kb * 4 + cc) * 32 + rr * 4);
+      *reinterpret_cast<float4*>(xo + (size_t)r * C + ch * 4) = *reinterpret_cast<const float4*>(RA + r * 256 + ((ch ^ (r & 15)) << 4));
   }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
 void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {

@@ -274,13 +274,13 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             t[f"{q}.inter.fc_b"] = sd[f"{p}.fc_inter.bias"]
             t[f"{q}.inter.ln_g"] = sd[f"{p}.ln_inter.weight"]
             t[f"{q}.inter.ln_b"] = sd[f"{p}.ln_inter.bias"]
-            # tensor-core (tcgen05, 3xTF32) operand images of the position-parallel matrices of the block:
-            # nine [64x64] slabs (hi | lo): fc_intra K-halves, inter-GRU gates (Wih r,z,n then Whh r,z,n), fc_inter
+            # tensor-core (tcgen05, FP16 hi/lo split) operand images of the position-parallel matrices of the block:
+            # nine [64x64] slabs (hi | lo, 16 KB each): fc_intra K-halves, inter-GRU gates (Wih r,z,n then Whh r,z,n), fc_inter
             wih, whh = sd[f"{p}.inter_gru.weight_ih_l0"], sd[f"{p}.inter_gru.weight_hh_l0"]
             fcw = sd[f"{p}.fc_intra.weight"]
-            t[f"{q}.tc.fc_w"] = np.concatenate([umma_operand(fcw[:, :C]), umma_operand(fcw[:, C:])])   # two K=64 slabs
-            t[f"{q}.tc.gates"] = np.concatenate([umma_operand(m[g * C:(g + 1) * C]) for m in (wih, whh) for g in range(3)])
-            t[f"{q}.tc.fc2_w"] = umma_operand(sd[f"{p}.fc_inter.weight"])
+            t[f"{q}.tc.fc_w"] = np.concatenate([umma_operand16(fcw[:, :C]), umma_operand16(fcw[:, C:])])   # two K=64 slabs
+            t[f"{q}.tc.gates"] = np.concatenate([umma_operand16(m[g * C:(g + 1) * C]) for m in (wih, whh) for g in range(3)])
+            t[f"{q}.tc.fc2_w"] = umma_operand16(sd[f"{p}.fc_inter.weight"])
             # FP16 hi/lo operand images of the intra-frame GRU (k_dprnn_intra_tc): per direction
             # [W_ih hi | W_ih lo | W_hh hi | W_hh lo], each [192][64] halves stored as raw bytes in the f32 blob.
             # The exponent scales of the gate non-linearities are folded into rows and biases: the kernel
