@@ -17,7 +17,8 @@
 //   warps 0..15  : wait commit, tcgen05.ld the four gate pre-activations of (row = TMEM lane, 16 units), gate
 //                  math in registers (h_{t-1} never leaves registers), write h_t as FP16 hi/lo operand rows for
 //                  the next step and as FP32 to hcat[b][f][dir*64 + u]; convert the prefetched x_{t+2} tile.
-// The x-part MMAs and the global loads of x are hidden behind the gate math of the previous step.
+// The x-part MMAs and the global loads of x are hidden behind the gate math of the previous step, and the recurrent
+// MMAs of step t+1 are issued per K slice (16 units) as soon as the gate warps have produced that slice of h_t.
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -88,7 +89,7 @@ struct IntraTcParams {
   int tiles;              // ceil(B / 128)
   int B;
 #ifdef ITC_TIMELINE
-  long long* tl;          // [steps][8] SM-clock stamps of CTA 0 (tools/ubench/intra_tc_timeline.cu)
+  long long* tl;          // [steps][12] SM-clock stamps of CTA 0 (tools/ubench/intra_tc_timeline.cu)
 #endif
 };
 
@@ -97,7 +98,7 @@ struct IntraTcParams {
 // volatile shared-memory load, which cannot issue before a pending (deferred-blocking) barrier has released
 #define TL(slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 16 || warp == 5)) { \
     unsigned v_; long long c_; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v_) : "r"(smem_u32(tmem_slot))); \
-    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) : "r"(v_)); p.tl[t * 8 + (slot)] = c_; } } while (0)
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) : "r"(v_)); p.tl[t * 12 + (slot)] = c_; } } while (0)
 #else
 #define TL(slot) do { } while (0)
 #endif
@@ -197,55 +198,65 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   tc_fence_after();
 
   // ---- MMA issue (warp 16, one elected lane) ------------------------------------------------------------------
+  // The recurrent product of step t+1 is issued K-slice by K-slice: slice ks only needs units [16 ks, 16 ks + 16) of
+  // h_t, and the gate warps produce the units in exactly that order (every thread owns 4 units of each slice), so the
+  // tensor core works on slice ks while the gate math of slices ks+1.. is still running.  Only the last slice's six
+  // MMAs and the commit remain on the critical path of a step.
   if (warp == 16) {
     const uint32_t w_base = smem_u32(Wsm), x_base = smem_u32(Xsm);
     constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
-    auto mma3 = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-      const uint64_t dah = DESC0 | (a_hi >> 4), dal = DESC0 | (a_lo >> 4), dbh = DESC0 | (b_hi >> 4), dbl = DESC0 | (b_lo >> 4);
+    auto x_mma = [&](int t) {                                // P[t & 1][0, 192) = x_t * W_ih^T
+      const uint32_t xa = x_base + (t & 1) * 2 * A_IMG, d = tmem + TM_P + (t & 1) * 192;
+      const uint64_t dah = DESC0 | (xa >> 4), dal = DESC0 | ((xa + A_IMG) >> 4);
+      const uint64_t dbh = DESC0 | (w_base >> 4), dbl = DESC0 | ((w_base + W_IMG) >> 4);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {                       // K = 64 in steps of 16 halves = two core matrices = 256 B
-        umma_f16(d, dah + ks * 16, dbh + ks * 16, idesc, accumulate);
-        umma_f16(d, dal + ks * 16, dbh + ks * 16, idesc, 1);
-        umma_f16(d, dah + ks * 16, dbl + ks * 16, idesc, 1);
-        accumulate = 1;
+        umma_f16(d, dah + ks * 16, dbh + ks * 16, idesc_f16(128, 192), ks > 0);
+        umma_f16(d, dal + ks * 16, dbh + ks * 16, idesc_f16(128, 192), 1);
+        umma_f16(d, dah + ks * 16, dbl + ks * 16, idesc_f16(128, 192), 1);
       }
     };
-    auto x_mma = [&](int t) {                                // P[t & 1][0, 192) = x_t * W_ih^T
-      const uint32_t xa = x_base + (t & 1) * 2 * A_IMG;
-      mma3(tmem + TM_P + (t & 1) * 192, xa, xa + A_IMG, w_base, w_base + W_IMG, idesc_f16(128, 192), 0);
-    };
-    // recurrent part: A = h (hi, lo) straight from tensor memory, so the only shared-memory traffic is W_hh
-    auto mma3_ts = [&](uint32_t d, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-      const uint64_t dbh = DESC0 | (b_hi >> 4), dbl = DESC0 | (b_lo >> 4);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {                       // 16 halves of K = 8 columns of the TMEM operand
-        umma_f16_ts(d, tmem + TM_HHI + ks * 8, dbh + ks * 16, idesc, accumulate);
-        umma_f16_ts(d, tmem + TM_HLO + ks * 8, dbh + ks * 16, idesc, 1);
-        umma_f16_ts(d, tmem + TM_HHI + ks * 8, dbl + ks * 16, idesc, 1);
-        accumulate = 1;
-      }
-    };
-    auto h_mma = [&](int t) {
-      const uint32_t whi = w_base + 2 * W_IMG, wlo = w_base + 3 * W_IMG;
-      mma3_ts(tmem + TM_P + (t & 1) * 192, whi, wlo, idesc_f16(128, 128), 1);                 // r, z += h * W_hh[r,z]^T
-      mma3_ts(tmem + TM_HN, whi + 16 * 1024, wlo + 16 * 1024, idesc_f16(128, 64), 0);         // hn = h * W_hh[n]^T
+    // K slice ks of the recurrent part: A = h (hi, lo) straight from tensor memory (16 halves = 8 columns), so the
+    // only shared-memory traffic is W_hh
+    auto h_mma_slice = [&](int t, int ks) {
+      const uint32_t whi = w_base + 2 * W_IMG + ks * 256, wlo = w_base + 3 * W_IMG + ks * 256;
+      const uint64_t rz_h = DESC0 | (whi >> 4), rz_l = DESC0 | (wlo >> 4);
+      const uint64_t n_h = DESC0 | ((whi + 16 * 1024) >> 4), n_l = DESC0 | ((wlo + 16 * 1024) >> 4);
+      const uint32_t ah = tmem + TM_HHI + ks * 8, al = tmem + TM_HLO + ks * 8;
+      const uint32_t drz = tmem + TM_P + (t & 1) * 192, dn = tmem + TM_HN;
+      umma_f16_ts(drz, ah, rz_h, idesc_f16(128, 128), 1);    // r, z += h * W_hh[r,z]^T (on top of the x part)
+      umma_f16_ts(drz, al, rz_h, idesc_f16(128, 128), 1);
+      umma_f16_ts(drz, ah, rz_l, idesc_f16(128, 128), 1);
+      umma_f16_ts(dn, ah, n_h, idesc_f16(128, 64), ks > 0);  // hn = h * W_hh[n]^T
+      umma_f16_ts(dn, al, n_h, idesc_f16(128, 64), 1);
+      umma_f16_ts(dn, ah, n_l, idesc_f16(128, 64), 1);
     };
     if (lane == 0) {
       mbar_wait(bars, 0);                                    // weight images landed (async proxy -> async proxy)
       x_mma(0);
-      h_mma(0);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) h_mma_slice(0, ks);
       umma_commit(bars + 1);
       if (T > 1) x_mma(1);
     }
-    for (int t = 0; t < T; ++t) {
-      asm volatile("bar.sync 1, %0;" ::"n"(ITC_NT) : "memory");     // h_t written (TMEM + staging), P[t & 1] drained, x_{t+2} staged
-      TL(5);
-      if (lane == 0 && t + 1 < T) {
-        tc_fence_after();
-        h_mma(t + 1);
+    for (int t = 0; t + 1 < T; ++t) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        // units of slice ks of h_t are in TMEM (ks == 0: every thread has also drained hn of step t;
+        // ks == 3: P[t & 1] drained and x_{t+2} staged)
+        if (ks == 0) asm volatile("bar.sync 1, %0;" ::"n"(ITC_NT) : "memory");
+        if (ks == 1) asm volatile("bar.sync 2, %0;" ::"n"(ITC_NT) : "memory");
+        if (ks == 2) asm volatile("bar.sync 3, %0;" ::"n"(ITC_NT) : "memory");
+        if (ks == 3) asm volatile("bar.sync 4, %0;" ::"n"(ITC_NT) : "memory");
+        if (ks == 3) TL(5);
+        if (lane == 0) {
+          tc_fence_after();
+          h_mma_slice(t + 1, ks);
+        }
+        __syncwarp();
       }
       if (lane == 0) {
-        if (t + 1 < T) umma_commit(bars + 1);
+        umma_commit(bars + 1);
         TL(6);
 #ifndef ITC_NO_X
         if (t + 2 < T) x_mma(t + 2);
@@ -256,109 +267,120 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
     }
   } else {
     // ---- the sweep (gate warps) -----------------------------------------------------------------------------
+    // thread (row = TMEM lane, g = warp >> 2) owns units 16 ks + 4 g + j  (ks, j = 0..3): four of every K slice
     float h[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) h[i] = 0.f;
     const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16);
-    const uint32_t lane_addr = lane_base + cg * 16;
+    // Write-out of h_s: staging[s & 1] -> hcat[b][f][dir*64 ..], two full 256-byte rows per warp instruction.  It runs
+    // inside step s + 1, under the MUFU-bound gate math: passing the accumulator barrier of step s + 1 proves that every
+    // warp has finished writing staging[s & 1], and the buffer is not rewritten before step s + 2, which no warp can
+    // reach before all warps have handed over the last slice of step s + 1 (after this copy).
+    const int nvalid = min(128, p.B - b0);
+    auto write_out = [&](int s_) {
+      const int f = dir ? T - 1 - s_ : s_;
+      const unsigned char* sbuf = Ssm + (s_ & 1) * ST_BUF;
+      float* gdst = hg + ((size_t)b0 * T + f) * 2 * C + dir * C + (tid & 15) * 4;
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (tid >> 4) + 32 * i;
+        v[i] = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = (tid >> 4) + 32 * i;
+        if (r < nvalid) *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = v[i];
+      }
+    };
     for (int t = 0; t < T; ++t) {
       TL(0);
       if (t + 2 < T) load_x(t + 2, xv);                      // in flight during the wait
       mbar_wait(bars + 1, t & 1);
       tc_fence_after();
       TL(1);
+      // hn is single buffered and slice 0 of the next step overwrites all of it: drain it first
+      uint32_t ghn[4][4];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t gr[8], gz[8], gi[8], gh[8];
-        const uint32_t ta = lane_addr + TM_P + (t & 1) * 192 + half * 8;
-        tmem_ld8_nowait(ta, gr);
-        tmem_ld8_nowait(ta + 64, gz);
-        tmem_ld8_nowait(ta + 128, gi);
-        tmem_ld8_nowait(lane_addr + TM_HN + half * 8, gh);
-        // x_{t+2} item of this half: converted and stored while the TMEM loads are in flight and under the MUFU-bound
-        // gate math (x_mma(t), the reader of this buffer, completed with the commit just waited on)
-#if ITC_XEARLY
-        if (t + 2 < T) store_x1(t & 1, xv, half);
-#endif
-        tmem_ld_wait();
-        if (half == 0) TL(2);
+      for (int ks = 0; ks < 4; ++ks) tmem_ld4_nowait(lane_base + TM_HN + 16 * ks + 4 * cg, ghn[ks]);
+      uint32_t gr[4], gz[4], gi[4];
+      const uint32_t pa = lane_base + TM_P + (t & 1) * 192 + 4 * cg;
+      tmem_ld4_nowait(pa, gr);
+      tmem_ld4_nowait(pa + 64, gz);
+      tmem_ld4_nowait(pa + 128, gi);
+      tmem_ld_wait();
+      TL(2);
+      unsigned char* srow = Ssm + (t & 1) * ST_BUF + row * 256;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int u0 = 16 * ks + 4 * cg;
         // Gate math on unit pairs (packed f32x2 FMA-pipe ops).  The operand images and biases carry the exponent
         // scales (weights.py: r, z rows x -log2(e); n rows x 2 log2(e)), so
         //   r = 1 / (1 + 2^a_r),  z = 1 / (1 + 2^a_z)   (one shared reciprocal),   n = tanh(c) = 1 - 2 / (1 + 2^c')
-        float hn[8];
+        float hn[4];
 #ifdef ITC_NO_MATH
 #pragma unroll
-        for (int e = 0; e < 8; ++e) hn[e] = __uint_as_float(gr[e] ^ gz[e] ^ gi[e] ^ gh[e]) * 1e-30f + h[half * 8 + e];
+        for (int e = 0; e < 4; ++e) hn[e] = __uint_as_float(gr[e] ^ gz[e] ^ gi[e] ^ ghn[ks][e]) * 1e-30f + h[ks * 4 + e];
 #else
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          const float2 b_r = *reinterpret_cast<const float2*>(sb + cg * 16 + half * 8 + e);
-          const float2 b_z = *reinterpret_cast<const float2*>(sb + C + cg * 16 + half * 8 + e);
-          const float2 b_i = *reinterpret_cast<const float2*>(sb + 2 * C + cg * 16 + half * 8 + e);
-          const float2 b_h = *reinterpret_cast<const float2*>(sb + 3 * C + cg * 16 + half * 8 + e);
+        for (int e = 0; e < 4; e += 2) {
+          const float2 b_r = *reinterpret_cast<const float2*>(sb + u0 + e);
+          const float2 b_z = *reinterpret_cast<const float2*>(sb + C + u0 + e);
+          const float2 b_i = *reinterpret_cast<const float2*>(sb + 2 * C + u0 + e);
+          const float2 b_h = *reinterpret_cast<const float2*>(sb + 3 * C + u0 + e);
           const float2 one = make_float2(1.0f, 1.0f);
           const float2 ar = __fadd2_rn(make_float2(__uint_as_float(gr[e]), __uint_as_float(gr[e + 1])), b_r);
           const float2 az = __fadd2_rn(make_float2(__uint_as_float(gz[e]), __uint_as_float(gz[e + 1])), b_z);
-          // 2^60 * 2^60 stays finite in the shared reciprocal; sigmoid(-41) = 1e-18 is already 0 in FP32 terms
 #if ITC_POLY
           const float2 pr = __fadd2_rn(ex2_poly2(make_float2(clampf(ar.x, -125.f, 60.f), clampf(ar.y, -125.f, 60.f))), one);
           const float2 pz = __fadd2_rn(ex2_poly2(make_float2(clampf(az.x, -125.f, 60.f), clampf(az.y, -125.f, 60.f))), one);
 #else
+          // 2^60 * 2^60 stays finite in the shared reciprocal; sigmoid(-41) = 1e-18 is already 0 in FP32 terms
           const float2 pr = __fadd2_rn(make_float2(ex2_ftz(fminf(ar.x, 60.f)), ex2_ftz(fminf(ar.y, 60.f))), one);
           const float2 pz = __fadd2_rn(make_float2(ex2_ftz(fminf(az.x, 60.f)), ex2_ftz(fminf(az.y, 60.f))), one);
 #endif
           const float2 pp = __fmul2_rn(pr, pz);
           const float2 ip = make_float2(rcp_ftz(pp.x), rcp_ftz(pp.y));
           const float2 r = __fmul2_rn(ip, pz), z = __fmul2_rn(ip, pr);
-          const float2 ghn = __fadd2_rn(make_float2(__uint_as_float(gh[e]), __uint_as_float(gh[e + 1])), b_h);
-          const float2 gin = __fadd2_rn(make_float2(__uint_as_float(gi[e]), __uint_as_float(gi[e + 1])), b_i);
-          const float2 c = __ffma2_rn(r, ghn, gin);
+          const float2 vhn = __fadd2_rn(make_float2(__uint_as_float(ghn[ks][e]), __uint_as_float(ghn[ks][e + 1])), b_h);
+          const float2 vin = __fadd2_rn(make_float2(__uint_as_float(gi[e]), __uint_as_float(gi[e + 1])), b_i);
+          const float2 c = __ffma2_rn(r, vhn, vin);
           const float2 pc = __fadd2_rn(make_float2(ex2_ftz(c.x), ex2_ftz(c.y)), one);
           const float2 q = make_float2(rcp_ftz(pc.x), rcp_ftz(pc.y));
           const float2 n = __ffma2_rn(make_float2(-2.0f, -2.0f), q, one);
-          const float2 hp = make_float2(h[half * 8 + e], h[half * 8 + e + 1]);
+          const float2 hp = make_float2(h[ks * 4 + e], h[ks * 4 + e + 1]);
           const float2 hv = __ffma2_rn(z, __fadd2_rn(hp, make_float2(-n.x, -n.y)), n);      // (1 - z) n + z h
           hn[e] = hv.x; hn[e + 1] = hv.y;
-          h[half * 8 + e] = hv.x; h[half * 8 + e + 1] = hv.y;
         }
 #endif
-        uint4 hi, lo;
-        split8_f16(hn, hi, lo);
-        tmem_st4(lane_base + TM_HHI + cg * 8 + half * 4, hi.x, hi.y, hi.z, hi.w);      // units 2c, 2c+1 -> column c
-        tmem_st4(lane_base + TM_HLO + cg * 8 + half * 4, lo.x, lo.y, lo.z, lo.w);
-        unsigned char* srow = Ssm + (t & 1) * ST_BUF + row * 256;
-        const int c0 = cg * 4 + half * 2;
-        *reinterpret_cast<float4*>(srow + (((c0) ^ (row & 15)) << 4)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-        *reinterpret_cast<float4*>(srow + (((c0 + 1) ^ (row & 15)) << 4)) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-      }
-      TL(3);
-#if !ITC_XEARLY
-      if (t + 2 < T) store_x(t & 1, xv);                     // x_mma(t) (reader of this buffer) completed with the commit
-#endif
-      TL(4);
-      tmem_st_wait();
-      fence_async_smem();                                    // generic-proxy smem writes -> visible to the tensor core / TMA
-      tc_fence_before();
-      asm volatile("bar.arrive 1, %0;" ::"n"(ITC_NT) : "memory");     // hand over to the issuer, do not wait
-      // Write-out of h_t while the recurrent MMAs of the next step run (the gate warps would only wait): staging[t & 1]
-      // -> hcat[b][f][dir*64 ..], two full 256-byte rows per warp instruction.  The buffer is rewritten in step t + 2,
-      // which no warp can reach before every warp has passed this point of step t + 1.
-      asm volatile("bar.sync 2, %0;" ::"n"(ITC_GATE) : "memory");     // all staging rows of this step written
-      {
-        const int f = dir ? T - 1 - t : t;
-        const unsigned char* sbuf = Ssm + (t & 1) * ST_BUF;
-        const int nvalid = min(128, p.B - b0);
-        float* gdst = hg + ((size_t)b0 * T + f) * 2 * C + dir * C + (tid & 15) * 4;
-        float4 v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (tid >> 4) + 32 * i;
-          v[i] = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
+        for (int e = 0; e < 4; ++e) h[ks * 4 + e] = hn[e];
+        if (ks < 3) {                                        // next slice's pre-activations: in flight under the stores below
+          tmem_ld4_nowait(pa + 16 * (ks + 1), gr);
+          tmem_ld4_nowait(pa + 64 + 16 * (ks + 1), gz);
+          tmem_ld4_nowait(pa + 128 + 16 * (ks + 1), gi);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (tid >> 4) + 32 * i;
-          if (r < nvalid) *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = v[i];
+        uint32_t hi0, lo0, hi1, lo1;
+        split2_f16(hn[0], hn[1], hi0, lo0);
+        split2_f16(hn[2], hn[3], hi1, lo1);
+        tmem_st2(lane_base + TM_HHI + 8 * ks + 2 * cg, hi0, hi1);          // units 2c, 2c+1 -> column c of the A operand
+        tmem_st2(lane_base + TM_HLO + 8 * ks + 2 * cg, lo0, lo1);
+        *reinterpret_cast<float4*>(srow + (((4 * ks + cg) ^ (row & 15)) << 4)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        if (ks == 1 && t > 0) write_out(t - 1);
+        if (ks == 2 && t + 2 < T) store_x(t & 1, xv);        // x_mma(t) (reader of this buffer) completed with the commit
+        if (ks == 3) {
+          TL(3);
+          TL(4);
+          fence_async_smem();                                // generic-proxy smem writes -> visible to the tensor core
+        }
+        tmem_st_wait();
+        if (ks < 3) tmem_ld_wait();
+        if (t + 1 < T) {                                     // hand slice ks over to the issuer, do not wait
+          tc_fence_before();
+          if (ks == 0) asm volatile("bar.arrive 1, %0;" ::"n"(ITC_NT) : "memory");
+          if (ks == 1) asm volatile("bar.arrive 2, %0;" ::"n"(ITC_NT) : "memory");
+          if (ks == 2) asm volatile("bar.arrive 3, %0;" ::"n"(ITC_NT) : "memory");
+          if (ks == 3) asm volatile("bar.arrive 4, %0;" ::"n"(ITC_NT) : "memory");
         }
       }
     }
@@ -366,6 +388,18 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (warp < 16) {                                           // write-out of the last step (all staging rows visible after the barrier)
+    const int s_ = T - 1, f = dir ? 0 : T - 1;
+    const unsigned char* sbuf = Ssm + (s_ & 1) * ST_BUF;
+    const int nvalid = min(128, p.B - b0);
+    float* gdst = hg + ((size_t)b0 * T + f) * 2 * C + dir * C + (tid & 15) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (tid >> 4) + 32 * i;
+      if (r < nvalid)
+        *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
+    }
+  }
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 

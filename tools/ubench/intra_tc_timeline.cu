@@ -16,11 +16,11 @@ int main(int argc, char** argv) {
   cudaMalloc(&hcat, (size_t)B * T * 128 * 4);
   cudaMalloc(&w, 2 * 4 * 192 * 64 * 2);
   cudaMalloc(&bias, 2 * 4 * 64 * 4);
-  cudaMalloc(&tl, T * 8 * 8);
+  cudaMalloc(&tl, T * 12 * 8);
   cudaMemset(x, 0, (size_t)B * T * 64 * 4);
   cudaMemset(w, 0, 2 * 4 * 192 * 64 * 2);
   cudaMemset(bias, 0, 2 * 4 * 64 * 4);
-  cudaMemset(tl, 0, T * 8 * 8);
+  cudaMemset(tl, 0, T * 12 * 8);
   IntraTcParams p{};
   p.x[0] = p.x[1] = x; p.hcat[0] = p.hcat[1] = hcat; p.Fp[0] = T; p.Fp[1] = 8;
   p.wimg[0] = p.wimg[1] = w; p.bias[0] = p.bias[1] = bias; p.B = B; p.tiles = (B + 127) / 128; p.tl = tl;
@@ -34,14 +34,14 @@ int main(int argc, char** argv) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("launch %d: %s, %.1f us\n", it, cudaGetErrorString(err), ms * 1e3);
   }
-  std::vector<long long> h(T * 8);
-  cudaMemcpy(h.data(), tl, T * 8 * 8, cudaMemcpyDeviceToHost);
+  std::vector<long long> h(T * 12);
+  cudaMemcpy(h.data(), tl, T * 12 * 8, cudaMemcpyDeviceToHost);
   printf("step: [gate warp 5] wait_mma ldtm math(+sts/stg) store_x | [issuer] barrier->h_issued x_issued | step_total  (cycles)\n");
   for (int t = 1; t < T - 1; ++t) {
-    const long long* a = &h[t * 8];
-    const long long* n = &h[(t + 1) * 8];
-    printf("%2d: wait %5lld ldtm %5lld math %5lld stx %5lld | arrive->issuer_wake %5lld h_issue %5lld x_issue %5lld | step %5lld\n", t, a[1] - a[0],
-           a[2] - a[1], a[3] - a[2], a[4] - a[3], a[5] - a[4], a[6] - a[5], a[7] - a[6], n[0] - a[0]);
+    const long long* a = &h[t * 12];
+    const long long* n = &h[(t + 1) * 12];
+    printf("%2d: wait %5lld ldtm %5lld math(+copy,stx) %5lld | last slice handed over -> issuer_wake %5lld h_issue %5lld x_issue %5lld | step %5lld\n", t, a[1] - a[0],
+           a[2] - a[1], a[3] - a[2], a[5] - a[4], a[6] - a[5], a[7] - a[6], n[0] - a[0]);
   }
   return 0;
 }
