@@ -37,11 +37,24 @@ UNIT = "stream-frames/s"
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s burst, source) -- the driver-measured roofline denominators."""
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel: str, model: str, batch: int):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic.json, written from the .ncu-rep by hand per round); None when no capture matches."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None, None
+    for rec in json.loads(p.read_text()):
+        if rec["kernel"] == kernel and rec["model"] == model and rec["batch"] == batch:
+            return rec["dram_bytes_per_launch"], rec["source"]
+    return None, None
 
 
 class ClockSampler:
@@ -171,6 +184,8 @@ def run_ours(args):
         eng.set_option("graph", 0)
     if args.intra_bt:
         eng.set_option("intra_bt", args.intra_bt)
+    if args.lanes >= 0:
+        eng.set_option("lanes", args.lanes)
     if world > 1:   # weights are replicated from the same seed; one tiny collective to line the ranks up
         dist.barrier()
 
@@ -293,15 +308,22 @@ def run_ours(args):
     step_ms_sum = sum(kt.values())
     dom = max(kt, key=kt.get)
     n_dom = {"dprnn_intra": spec.n_blocks, "dprnn_post": spec.n_blocks}.get(dom, 1)
-    peak, peak_src = measured_peaks()
+    peak, peak_tf, peak_src = measured_peaks()
     Fe3, Fd = spec.fe[3], 48
     per_stream_bytes = {
         # algorithmic bytes per stream per LAUNCH (DESIGN.md "kernels"): activations in/out + state touched
         "dprnn_intra": 4 * (Fe3 + Fd) * (64 + 128),
         "dprnn_post": 4 * (Fe3 + Fd) * (128 + 64 + 64 + 2 * 64),
     }.get(dom, spec.algorithmic_bytes_per_frame)
+    per_stream_macs = {
+        # algorithmic MACs per stream per launch (FP32-equivalent: the FP16 hi/lo split issues 3 tensor MACs for each)
+        "dprnn_intra": (Fe3 + Fd) * 2 * 2 * 192 * 64,
+        "dprnn_post": (Fe3 + Fd) * (128 * 64 + 6 * 64 * 64 + 64 * 64),
+    }.get(dom)
     dom_ms = kt[dom] / n_dom
     achieved = per_stream_bytes * B / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom, args.model, B)
+    dom_tf = 2.0 * per_stream_macs * B / (dom_ms * 1e-3) / 1e12 if per_stream_macs else None
     step_bytes = spec.algorithmic_bytes_per_frame
     step_gbs = step_bytes * B / (ms_max / K * 1e-3) / 1e9
     flops = 2.0 * spec.macs_per_frame
@@ -317,7 +339,8 @@ def run_ours(args):
         "config": {"workload": f"{args.model} 16 kHz per-frame hot path (STFT->DPRNN->DF->iSTFT), batch={B} streams/GPU x {K} hops",
                    "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                    "l2": f"no flush: per-step working set {B * 4 * spec.state_size / 1e6:.0f} MB of stream state > 126 MB L2",
-                   "weights": "seeded random (no checkpoint offline), BN stats randomised"},
+                   "weights": "seeded random (no checkpoint offline), BN stats randomised",
+                   "engine": "one CUDA graph per hop; DPRNN on tcgen05 (FP16 hi/lo split, FP32 accumulate); lanes: engine default"},
         "realtime_streams": value / fps,
         "hop_latency_ms": ms_max / K,
         "hop_latency": lat,
@@ -326,9 +349,17 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * hop * 4, "d2h_bytes_per_step": B * hop * 4,
                 "steps": Ke, "api": "dpdf_step_pcm_host (pinned host buffers, H2D + hop + D2H, synchronous)"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "share_of_step": kt[dom] / step_ms_sum,
-                     "launch_ms": dom_ms, "algorithmic_bytes_per_stream_launch": per_stream_bytes,
-                     "note": "dominant kernel is FP32-FMA bound, not HBM bound; see roofline_step / fp32_tflops"},
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "share_of_step": kt[dom] / step_ms_sum, "launch_ms": dom_ms, "launches_per_step": n_dom,
+                     "algorithmic_bytes_per_stream_launch": per_stream_bytes,
+                     "note": "the dominant kernel is a sequential recurrence (F' dependent steps per launch), bound by per-step "
+                             "latency (tensor-core issue + MUFU gate math), not by HBM: its activations stay in L2 (traffic << "
+                             "algorithmic bytes); see roofline_tensor and DESIGN.md section 3"},
+        "roofline_tensor": None if dom_tf is None else {
+            "bound": "tensor", "kernel": dom, "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dom_tf / peak_tf,
+            "algorithmic_macs_per_stream_launch": per_stream_macs,
+            "note": "FP32-equivalent algorithmic FLOPs; every MAC is issued as 3 FP16 tensor MACs (hi*hi + lo*hi + hi*lo), "
+                    "so the tensor pipe executes 3x this rate; peak = measured dense bf16 burst"},
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                           "algorithmic_bytes_per_stream_frame": step_bytes},
         "fp32_tflops": tflops,
@@ -354,11 +385,12 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-batch", type=int, default=128)
-    ap.add_argument("--cpu-hops", type=int, default=20)
+    ap.add_argument("--cpu-hops", type=int, default=100)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-ladder", action="store_true", help="skip the sustained-streams batch ladder")
     ap.add_argument("--ladder", type=int, nargs="*", default=[4096, 6144, 7168, 8192])
     ap.add_argument("--intra-bt", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=-1, help="kernel-chain lanes per step (-1: engine default)")
     ap.add_argument("--profile-only", action="store_true", help="device steps only (for ncu runs)")
     args = ap.parse_args()
     if args.warmup < 3:

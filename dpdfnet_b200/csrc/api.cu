@@ -239,12 +239,17 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
     std::vector<std::pair<float**, size_t>> items;
     State& s = e.st;
     Scratch& c = e.sc;
-    auto add = [&](float*& ptr, size_t per) { items.push_back({&ptr, per * Bm}); };
+    bool in_scratch = false;
+    auto add = [&](float*& ptr, size_t per) {
+      items.push_back({&ptr, per * Bm});
+      if (in_scratch) e.sc_items.push_back({&ptr, per});
+    };
     add(s.mu, d.fe_feat); add(s.s, NDF); add(s.erb_ring, 3 * d.fe_feat); add(s.df_ring, 3 * 2 * NDF);
     add(s.inter_erb, (size_t)std::max(d.N, 1) * d.fe[3] * C); add(s.inter_df, (size_t)std::max(d.N, 1) * (NDF / 2) * C);
     add(s.h_enc, H); add(s.h_erb, 2 * H); add(s.h_df, 2 * H);
     add(s.c0_ring, (size_t)ORD * NDF * C); add(s.mask_ring, 3 * d.F * 2); add(s.coef_ring, 3 * NDF * 2 * ORD);
     add(s.dfspec_ring, (size_t)ORD * d.F * 2); add(s.in_hist, d.hop); add(s.ola, d.hop);
+    in_scratch = true;
     add(c.e0, (size_t)d.fe[0] * C); add(c.e1, (size_t)d.fe[1] * C); add(c.e2, (size_t)d.fe[2] * C); add(c.e3, (size_t)d.fe[3] * C);
     add(c.c0, NDF * C); add(c.c1, (NDF / 2) * C); add(c.xe, (size_t)d.fe[3] * C);
     add(c.hcat_e, (size_t)d.fe[3] * 2 * C); add(c.hcat_d, (NDF / 2) * 2 * C);
@@ -266,10 +271,16 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
     }
     s.pos = reinterpret_cast<int*>(cur);
   }
-  if (cudaMalloc(&e.io_dev, sizeof(IoDesc)) != cudaSuccess || cudaMalloc(&e.slots_dev, max_streams * sizeof(int)) != cudaSuccess ||
+  if (cudaMalloc(&e.io_lanes, Engine::MAX_LANES * sizeof(IoDesc)) != cudaSuccess || cudaMalloc(&e.slots_dev, max_streams * sizeof(int)) != cudaSuccess ||
       cudaMalloc(&e.flags_dev, max_streams * sizeof(int)) != cudaSuccess)
     return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(io) failed"));
+  e.io_dev = e.io_lanes;
   if (cudaStreamCreateWithFlags(&e.own_stream, cudaStreamDefault) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "stream creation failed"));
+  for (int l = 1; l < Engine::MAX_LANES; ++l)
+    if (cudaStreamCreateWithFlags(&e.lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.lane_done[l], cudaEventDisableTiming) != cudaSuccess)
+      return bail(fail(DPDF_ERR_CUDA, "lane stream creation failed"));
+  if (cudaEventCreateWithFlags(&e.lane_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "event creation failed"));
   init_frontend_kernels();
   init_conv_kernels();
   init_dprnn_kernels();
@@ -290,7 +301,12 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
   cudaDeviceSynchronize();
   for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
   for (auto ev : e.tev) cudaEventDestroy(ev);
-  cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_dev);
+  for (int l = 1; l < Engine::MAX_LANES; ++l) {
+    if (e.lane_stream[l]) cudaStreamDestroy(e.lane_stream[l]);
+    if (e.lane_done[l]) cudaEventDestroy(e.lane_done[l]);
+  }
+  if (e.lane_fork) cudaEventDestroy(e.lane_fork);
+  cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_lanes);
   cudaFree(e.slots_dev); cudaFree(e.flags_dev); cudaFree(e.stage_in); cudaFree(e.stage_out);
   if (e.pinned) cudaFreeHost(e.pinned);
   if (e.own_stream) cudaStreamDestroy(e.own_stream);
@@ -349,7 +365,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     RUN("sepconv", launch_sepconv(e, pr, 1, B, st)); ++n;
   }
   for (int i = 0; i < d.N; ++i) {
-    if (e.intra_tc == 1 || (e.intra_tc == 2 && B >= e.intra_tc_min)) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
+    if (e.intra_tc == 1 || (e.intra_tc == 2 && std::max(B, e.total_B) >= e.intra_tc_min)) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
     else { RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); }
     ++n;
     if (e.post_tc) { RUN("dprnn_post", launch_dprnn_post_tc(e, i, B, st)); }
@@ -433,10 +449,54 @@ static int check_batch(Engine& e, int B) {
   return 0;
 }
 
+// Number of lanes of a step over B streams: explicit option, else enough streams per lane to keep the tensor-core
+// kernels' 128-stream tiles full.
+static int lanes_for(const Engine& e, int B) {
+  int L = e.lanes > 0 ? e.lanes : (B >= 2048 ? 2 : (B >= 1024 ? 4 : 1));   // measured: profiles/r01u_lanes.log
+  L = std::min(L, Engine::MAX_LANES);
+  while (L > 1 && B / L < 128) --L;
+  return std::max(L, 1);
+}
+static void lane_range(int B, int L, int l, int* r0, int* n) {
+  const int per = ((B + L - 1) / L + 127) / 128 * 128;          // lane sizes are multiples of the 128-stream MMA tile
+  *r0 = std::min(B, l * per);
+  *n = std::min(B, (l + 1) * per) - *r0;
+}
+
+// Enqueue one hop for B streams: every lane's kernel chain with its row range of the scratch arena and its own
+// I/O descriptor; lanes > 0 run on forked streams (graph capture turns the events into graph dependencies).
+static void enqueue_lanes(Engine& e, int B, cudaStream_t st, bool fork) {
+  const int L = lanes_for(e, B);
+  std::vector<float*> base(e.sc_items.size());
+  for (size_t i = 0; i < base.size(); ++i) base[i] = *e.sc_items[i].first;
+  e.total_B = B;
+  int launches = 0;
+  if (fork && L > 1) cudaEventRecord(e.lane_fork, st);
+  for (int l = 0; l < L; ++l) {
+    int r0, n;
+    lane_range(B, L, l, &r0, &n);
+    if (n <= 0) continue;
+    for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i] + (size_t)r0 * e.sc_items[i].second;
+    e.io_dev = e.io_lanes + l;
+    cudaStream_t ls = (fork && l > 0) ? e.lane_stream[l] : st;
+    if (fork && l > 0) cudaStreamWaitEvent(ls, e.lane_fork, 0);
+    enqueue_step(e, n, ls);
+    launches += e.launches;
+    if (fork && l > 0) {
+      cudaEventRecord(e.lane_done[l], ls);
+      cudaStreamWaitEvent(st, e.lane_done[l], 0);
+    }
+  }
+  for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i];
+  e.io_dev = e.io_lanes;
+  e.total_B = 0;
+  e.launches = launches;
+}
+
 // Launch the kernels of one hop on `st`, through a cached CUDA graph when enabled.
 static int run_step(Engine& e, int B, cudaStream_t st) {
   if (!e.use_graph || e.timing) {
-    enqueue_step(e, B, st);
+    enqueue_lanes(e, B, st, false);
     CU(cudaGetLastError());
     return 0;
   }
@@ -446,7 +506,7 @@ static int run_step(Engine& e, int B, cudaStream_t st) {
     // which cannot be captured; the instantiated graph is then launched on the caller's stream.
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(e.own_stream, cudaStreamCaptureModeRelaxed));
-    enqueue_step(e, B, e.own_stream);
+    enqueue_lanes(e, B, e.own_stream, true);
     cudaError_t err = cudaStreamEndCapture(e.own_stream, &graph);
     if (err != cudaSuccess) return fail(DPDF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(err));
     cudaGraphExec_t exec = nullptr;
@@ -460,11 +520,19 @@ static int run_step(Engine& e, int B, cudaStream_t st) {
 }
 
 static int set_io(Engine& e, const float* in, long long in_stride, float* out, long long out_stride,
-                  const int32_t* slot_ids, const int32_t* flags, int mode, cudaStream_t st) {
-  IoDesc io{};
-  io.in = in; io.out = out; io.in_stride = in_stride; io.out_stride = out_stride;
-  io.slot_ids = slot_ids; io.flags = flags; io.t_in = 0; io.t_out = 0; io.mode = mode;
-  CU(cudaMemcpyAsync(e.io_dev, &io, sizeof(io), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+                  const int32_t* slot_ids, const int32_t* flags, int mode, int B, cudaStream_t st) {
+  IoDesc io[Engine::MAX_LANES] = {};
+  const int L = lanes_for(e, B);
+  const long long rin = mode == 1 ? (long long)e.d.F * 2 : in_stride, rout = mode == 1 ? (long long)e.d.F * 2 : out_stride;
+  for (int l = 0; l < L; ++l) {
+    int r0, n;
+    lane_range(B, L, l, &r0, &n);
+    io[l].in = in + (size_t)r0 * rin; io[l].out = out + (size_t)r0 * rout;
+    io[l].in_stride = in_stride; io[l].out_stride = out_stride;
+    io[l].slot_ids = slot_ids ? slot_ids + r0 : nullptr; io[l].flags = flags ? flags + r0 : nullptr;
+    io[l].t_in = 0; io[l].t_out = 0; io[l].mode = mode; io[l].slot_base = r0;
+  }
+  CU(cudaMemcpyAsync(e.io_lanes, io, sizeof(IoDesc) * L, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
   return 0;
 }
 
@@ -475,7 +543,7 @@ extern "C" int dpdf_step_spec(dpdf_engine* h, const float* spec_in, float* spec_
   if (int rc = check_batch(e, B)) return rc;
   CU(cudaSetDevice(e.device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (int rc = set_io(e, spec_in, 0, spec_out, 0, slot_ids, flags, 1, st)) return rc;
+  if (int rc = set_io(e, spec_in, 0, spec_out, 0, slot_ids, flags, 1, B, st)) return rc;
   e.last_B = B;
   return run_step(e, B, st);
 }
@@ -490,7 +558,7 @@ extern "C" int dpdf_run_pcm(dpdf_engine* h, const float* pcm_in, int64_t in_stri
     return fail(DPDF_ERR_INVALID, "row stride smaller than T*hop");
   CU(cudaSetDevice(e.device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  if (int rc = set_io(e, pcm_in, in_stride, pcm_out, out_stride, slot_ids, flags, 0, st)) return rc;
+  if (int rc = set_io(e, pcm_in, in_stride, pcm_out, out_stride, slot_ids, flags, 0, B, st)) return rc;
   e.last_B = B;
   for (int t = 0; t < T; ++t)
     if (int rc = run_step(e, B, st)) return rc;
@@ -799,6 +867,11 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     }
     for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
     e.graphs.clear();
+  } else if (strcmp(key, "lanes") == 0) {
+    if (value < 0 || value > Engine::MAX_LANES) return fail(DPDF_ERR_INVALID, "lanes must be 0 (auto) .. %d", Engine::MAX_LANES);
+    e.lanes = value;
+    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+    e.graphs.clear();
   } else if (strcmp(key, "post_tc") == 0) {
     e.post_tc = value ? 1 : 0;
     for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
@@ -819,13 +892,17 @@ extern "C" int dpdf_time_kernels(dpdf_engine* h, int32_t B, int32_t iters, float
   if (int rc = ensure_stage(e, n, n)) return rc;
   cudaStream_t st = e.own_stream;
   CU(cudaMemsetAsync(e.stage_in, 0, n * sizeof(float), st));
-  if (int rc = set_io(e, e.stage_in, e.d.hop, e.stage_out, e.d.hop, nullptr, nullptr, 0, st)) return rc;
+  struct OneLane {                           // the whole batch as a single kernel chain: per-kernel times of B streams
+    Engine& e; int saved;
+    explicit OneLane(Engine& e_) : e(e_), saved(e_.lanes) { e.lanes = 1; }
+    ~OneLane() { e.lanes = saved; }
+  } one_lane(e);
   static std::vector<std::string> keep;     // storage for the returned names
   std::vector<double> acc;
   keep.clear();
   e.last_B = B;
   for (int it = 0; it < iters + 1; ++it) {
-    if (int rc = set_io(e, e.stage_in, e.d.hop, e.stage_out, e.d.hop, nullptr, nullptr, 0, st)) return rc;
+    if (int rc = set_io(e, e.stage_in, e.d.hop, e.stage_out, e.d.hop, nullptr, nullptr, 0, B, st)) return rc;
     e.timing = true;
     e.tev.clear();
     e.tnames.clear();

@@ -30,11 +30,11 @@ struct IoDesc {
   int t_in;               // hop index read by the analysis kernel
   int t_out;              // hop index read by the synthesis kernel
   int mode;               // 0 = pcm, 1 = spec
-  int pad;
+  int slot_base;          // identity slot mapping: slot = slot_base + b (lanes of one batched step, api.cu:run_step)
 };
 
 __device__ __forceinline__ int io_slot(const IoDesc* io, int b) {
-  return io->slot_ids ? __ldg(io->slot_ids + b) : b;
+  return io->slot_ids ? __ldg(io->slot_ids + b) : io->slot_base + b;
 }
 __device__ __forceinline__ int io_flags(const IoDesc* io, int b) {
   return io->flags ? __ldg(io->flags + b) : 0;

@@ -144,7 +144,8 @@ struct Engine {
   void* arena = nullptr;
   size_t arena_bytes = 0;
   int* aux_int = nullptr;         // band tables
-  IoDesc* io_dev = nullptr;
+  IoDesc* io_dev = nullptr;       // descriptor the kernel launchers bind (points into io_lanes during a laned step)
+  IoDesc* io_lanes = nullptr;     // [MAX_LANES] device descriptors, one per lane
   IoDesc* io_host = nullptr;      // pinned
   int* slots_dev = nullptr;       // staging for host slot ids / flags
   int* flags_dev = nullptr;
@@ -156,6 +157,16 @@ struct Engine {
   cudaStream_t own_stream = nullptr;
   int last_B = 0;
   int launches = 0;               // kernels launched by the last step
+  // Lanes: a batched step is split into `lanes` row ranges that run as independent kernel chains on forked streams
+  // inside one CUDA graph, so the latency-bound kernels of one lane (the sequential intra-frame GRU sweep occupies
+  // 32 SMs per 1024 streams) overlap with the throughput kernels of the others.  Lanes share the state arena (slots
+  // are global) and use disjoint row ranges of the scratch arena.
+  static constexpr int MAX_LANES = 8;
+  int lanes = 0;                  // 0 = auto by batch size
+  int total_B = 0;                // batch of the whole step while its lanes are enqueued (kernel-variant choice)
+  std::vector<std::pair<float**, size_t>> sc_items;   // scratch pointer members and their floats per stream
+  cudaStream_t lane_stream[MAX_LANES] = {};
+  cudaEvent_t lane_fork = nullptr, lane_done[MAX_LANES] = {};
   int use_graph = 1;
   int intra_bt = 0;               // 0 = auto
   int intra_tc = 2;               // intra-frame GRU on tcgen05 (FP16 split): 0 never, 1 always, 2 = when B >= intra_tc_min

@@ -25,6 +25,10 @@ for l in sys.stdin:
         print(l, end='')
 " | tee -a $OUT/${TAG}_quick.log
       done ;;
+    lanes)   # hop time against the number of lanes
+      for b in 1024 2048 8192; do for L in 1 2 4 8; do
+        timeout 600 python bench.py --steps 60 --warmup 10 --no-ladder --batch $b --lanes $L --profile-only 2>&1 | sed "s/^/B=$b lanes=$L /" | tee -a $OUT/${TAG}_lanes.log
+      done; done ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; tail -2 $OUT/${TAG}_smoke.log ;;
     bench)
