@@ -122,7 +122,10 @@ int dpdf_state_import(dpdf_engine* e, int32_t slot, const float* flat_host);
 int dpdf_debug_tensor(dpdf_engine* e, const char* name, float* out_host, size_t max_floats,
                       size_t* numel_per_stream);    /* stage output of the last step, [B, numel] */
 int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the last step */
-int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value); /* "graph", "intra_bt" */
+/* Options (all default to the measured-best choice): "graph" 0/1 one CUDA graph per hop; "lanes" 0 = auto, 1..8
+ * kernel-chain lanes per batched step; "intra_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch size (>= "intra_tc_min");
+ * "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel. */
+int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value);
 int dpdf_time_kernels(dpdf_engine* e, int32_t B, int32_t iters, float* ms_out, const char** names_out,
                       int32_t max_entries, int32_t* n_entries); /* per-kernel CUDA-event timing */
 const char* dpdf_last_error(void);

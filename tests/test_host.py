@@ -90,3 +90,39 @@ def test_c_spec_matches_python_spec():
         s = c_spec(spec)
         assert s.state_size == spec.state_size and sum(s.erb_widths) == spec.freq_bins
         assert list(s.fe) == list(spec.fe)
+
+
+def test_fp16_split_operand_images():
+    """Host side of the tcgen05 path: hi + lo reproduces FP32 weights to ~2^-22, the K-major SWIZZLE_NONE image puts
+    element (n, k) at byte (n>>3)*SBO + (k>>3)*128 + (n&7)*16 + (k&7)*2, and out-of-range weights are refused."""
+    import pytest
+    from dpdfnet_b200.weights import fp16_split, umma_kmajor16, umma_operand16
+    rng = np.random.default_rng(0)
+    w = (rng.standard_normal((192, 64)) * np.exp(rng.uniform(-8, 2, (192, 64)))).astype(np.float32)
+    hi, lo = fp16_split(w)
+    assert hi.dtype == np.float16 and lo.dtype == np.float16
+    err = np.abs(hi.astype(np.float64) + lo.astype(np.float64) - w)
+    assert np.all(err <= np.maximum(np.abs(w) * 2.0 ** -21, 2.0 ** -24))       # FP16-subnormal floor for tiny weights
+    img = umma_kmajor16(hi).view(np.uint16)
+    sbo = (64 // 8) * 128
+    for n, k in [(0, 0), (7, 7), (8, 0), (13, 42), (191, 63), (100, 8)]:
+        off = (n >> 3) * sbo + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2
+        assert img[off // 2] == hi.view(np.uint16)[n, k]
+    op = umma_operand16(w)
+    assert op.dtype == np.float32 and op.size == 192 * 64                       # hi | lo halves, as raw f32 words
+    with pytest.raises(ValueError):
+        fp16_split(np.array([[7.0e4]], np.float32))
+
+
+def test_packed_blob_carries_tensor_core_images():
+    from dpdfnet_b200.spec import get_spec
+    from dpdfnet_b200.weights import pack_tensors, random_checkpoint, LOG2E
+    spec = get_spec("dpdfnet2")
+    t = pack_tensors(spec, random_checkpoint(spec, 3))
+    for br in ("erb", "df"):
+        for i in range(spec.n_blocks):
+            q = f"enc.dprnn_{br}.{i}"
+            assert t[f"{q}.tc.intra"].size == 2 * 4 * 192 * 64 // 2
+            assert t[f"{q}.tc.gates"].size == 6 * 64 * 64 and t[f"{q}.tc.fc_w"].size == 2 * 64 * 64
+            b, tb = t[f"{q}.intra.bias"].reshape(2, 4, 64), t[f"{q}.tc.intra_bias"].reshape(2, 4, 64)
+            assert np.allclose(tb[:, :2], -LOG2E * b[:, :2], rtol=1e-6) and np.allclose(tb[:, 2:], 2 * LOG2E * b[:, 2:], rtol=1e-6)
