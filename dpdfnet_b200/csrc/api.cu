@@ -81,11 +81,12 @@ static int bind_weights(Engine& e) {
   w.s0 = W("const.s0", NDF);
   w.erb_conv0_w = W("enc.erb_conv0.w", 9 * C);
   w.erb_conv0_b = W("enc.erb_conv0.b", C);
-  auto sep = [&](const std::string& n, int up) { return SepW{W(n + ".dw", (size_t)up * 3 * C), W(n + ".pw", C * C), W(n + ".b", C)}; };
+  auto sep = [&](const std::string& n, int up) { return SepW{W(n + ".dw", (size_t)up * 3 * C), W(n + ".pw", C * C), W(n + ".b", C), W(n + ".tc_pw", C * C)}; };
   for (int i = 0; i < 3; ++i) w.erb_conv[i] = sep("enc.erb_conv" + std::to_string(i + 1), 1);
   w.df_conv0_w = W("enc.df_conv0.w", 9 * C);
   w.df_conv0_pw = W("enc.df_conv0.pw", C * C);
   w.df_conv0_b = W("enc.df_conv0.b", C);
+  w.df_conv0_tc_pw = W("enc.df_conv0.tc_pw", C * C);
   w.df_conv1 = sep("enc.df_conv1", 1);
   for (int br = 0; br < 2; ++br) {
     auto& vec = br ? w.dprnn_df : w.dprnn_erb;
@@ -287,6 +288,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   init_dense_kernels();
   init_dprnn_tc_kernels();
   init_dprnn_intra_tc_kernels();
+  init_conv_tc_kernels();
   launch_reset(e, nullptr, max_streams, e.own_stream);
   if (cudaStreamSynchronize(e.own_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
     return bail(fail(DPDF_ERR_CUDA, "engine initialisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -339,30 +341,35 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   const Weights& w = e.w;
   Scratch& c = e.sc;
   int n = 0;
+  const bool use_sep_tc = e.sep_tc == 1 || (e.sep_tc == 2 && std::max(B, e.total_B) >= e.sep_tc_min);
+  auto sepconv = [&](Engine& en, const SepProblem* probs, int nprob, int Bn, cudaStream_t s_) {
+    if (use_sep_tc) launch_sepconv_tc(en, probs, nprob, Bn, s_);
+    else launch_sepconv(en, probs, nprob, Bn, s_);
+  };
   RUN("analysis", launch_analysis(e, B, st)); ++n;
   RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
   auto sepp = [&](const SepW& sw, const float* in1, const float* in2, int pidx, float* out, int Fin, int Fout, int stride, int up) {
     SepProblem q{};
     q.mode = 0; q.in1 = in1; q.in2 = in2;
     q.pa = in2 ? w.convp_a[pidx] : nullptr; q.pb = in2 ? w.convp_b[pidx] : nullptr;
-    q.dw = sw.dw; q.pw = sw.pw; q.bias = sw.b; q.out = out; q.Fin = Fin; q.Fout = Fout; q.stride = stride; q.up = up;
+    q.dw = sw.dw; q.pw = sw.pw; q.tc_pw = sw.tc_pw; q.bias = sw.b; q.out = out; q.Fin = Fin; q.Fout = Fout; q.stride = stride; q.up = up;
     return q;
   };
   {
     SepProblem pr[2];
     pr[0] = SepProblem{};
-    pr[0].mode = 1; pr[0].dw = w.df_conv0_w; pr[0].pw = w.df_conv0_pw; pr[0].bias = w.df_conv0_b;
+    pr[0].mode = 1; pr[0].dw = w.df_conv0_w; pr[0].pw = w.df_conv0_pw; pr[0].tc_pw = w.df_conv0_tc_pw; pr[0].bias = w.df_conv0_b;
     pr[0].Fin = NDF; pr[0].Fout = NDF; pr[0].stride = 1; pr[0].up = 1; pr[0].out = c.c0;
     pr[1] = sepp(w.erb_conv[0], c.e0, nullptr, 0, c.e1, d.fe[0], d.fe[1], d.stride[0], 1);
-    RUN("sepconv", launch_sepconv(e, pr, 2, B, st)); ++n;
+    RUN("sepconv", sepconv(e, pr, 2, B, st)); ++n;
   }
   {
     SepProblem pr[2];
     pr[0] = sepp(w.df_conv1, c.c0, nullptr, 0, c.c1, NDF, NDF / 2, 2, 1);
     pr[1] = sepp(w.erb_conv[1], c.e1, nullptr, 0, c.e2, d.fe[1], d.fe[2], d.stride[1], 1);
-    RUN("sepconv", launch_sepconv(e, pr, 2, B, st)); ++n;
+    RUN("sepconv", sepconv(e, pr, 2, B, st)); ++n;
     pr[0] = sepp(w.erb_conv[2], c.e2, nullptr, 0, c.e3, d.fe[2], d.fe[3], d.stride[2], 1);
-    RUN("sepconv", launch_sepconv(e, pr, 1, B, st)); ++n;
+    RUN("sepconv", sepconv(e, pr, 1, B, st)); ++n;
   }
   for (int i = 0; i < d.N; ++i) {
     if (e.intra_tc == 1 || (e.intra_tc == 2 && std::max(B, e.total_B) >= e.intra_tc_min)) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
@@ -426,11 +433,11 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   {
     const float* edv = d.hr48 ? c.ed2 : c.ed;
     SepProblem q = sepp(w.convt[0], edv, c.e3, 0, c.d3, d.fe[3], d.fe[3] * d.up[0], 1, d.up[0]);
-    RUN("sepconv", launch_sepconv(e, &q, 1, B, st)); ++n;
+    RUN("sepconv", sepconv(e, &q, 1, B, st)); ++n;
     q = sepp(w.convt[1], c.d3, c.e2, 1, c.d2, d.fe[2], d.fe[2] * d.up[1], 1, d.up[1]);
-    RUN("sepconv", launch_sepconv(e, &q, 1, B, st)); ++n;
+    RUN("sepconv", sepconv(e, &q, 1, B, st)); ++n;
     q = sepp(w.convt[2], c.d2, c.e1, 2, c.d1, d.fe[1], d.fe[1] * d.up[2], 1, d.up[2]);
-    RUN("sepconv", launch_sepconv(e, &q, 1, B, st)); ++n;
+    RUN("sepconv", sepconv(e, &q, 1, B, st)); ++n;
   }
   RUN("conv0_out", launch_conv0_out(e, B, st)); ++n;
   RUN("df_pathway", launch_df_pathway(e, B, st)); ++n;
@@ -865,6 +872,11 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     } else {
       e.intra_tc_min = value;
     }
+    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+    e.graphs.clear();
+  } else if (strcmp(key, "sep_tc") == 0) {
+    if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "sep_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
+    e.sep_tc = value;
     for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
     e.graphs.clear();
   } else if (strcmp(key, "lanes") == 0) {

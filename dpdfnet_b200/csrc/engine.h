@@ -51,7 +51,7 @@ struct Scratch {         // all [max_streams][...]
   float *d3, *d2, *d1, *m;
 };
 
-struct SepW { const float *dw, *pw, *b; };
+struct SepW { const float *dw, *pw, *b, *tc_pw; };     // tc_pw: FP16 hi/lo tcgen05 image of pw (weights.py:umma_operand16)
 struct GLW { const float *w, *b; int G, Ng, Kg; };
 struct GRUW { const float *wih, *whh, *bias; };
 struct DprnnW {
@@ -66,7 +66,7 @@ struct Weights {
   const float *dft_fwd, *dft_inv, *mu0, *s0;
   const float *erb_conv0_w, *erb_conv0_b;
   SepW erb_conv[3], df_conv1, convt[3];
-  const float *df_conv0_w, *df_conv0_pw, *df_conv0_b;
+  const float *df_conv0_w, *df_conv0_pw, *df_conv0_b, *df_conv0_tc_pw;
   std::vector<DprnnW> dprnn_erb, dprnn_df;
   GLW erb_fc_emb, df_fc_emb, enc_in, enc_out, erbdec_in, erbdec_out, erbdec_fc, dfdec_in, df_skip, df_out;
   GRUW enc_gru, erb_gru[2], df_gru[2];
@@ -94,11 +94,13 @@ struct SepProblem {
   const float* in2;         // pathway source [B][Fin][64] or nullptr
   const float *pa, *pb;     // pathway affine
   const float *dw, *pw, *bias;
+  const float* tc_pw;       // tensor-core image of pw (launch_sepconv_tc)
   float* out;               // [B][Fout][64]  (mode 1: c0 ring slot)
   int Fin, Fout, stride, up;
   int tile0;                // first tile index of this problem in the launch
 };
 void launch_sepconv(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st);
+void launch_sepconv_tc(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st);
 void launch_conv0_out(Engine& e, int B, cudaStream_t st);
 void launch_df_pathway(Engine& e, int B, cudaStream_t st);
 
@@ -171,6 +173,8 @@ struct Engine {
   int intra_bt = 0;               // 0 = auto
   int intra_tc = 2;               // intra-frame GRU on tcgen05 (FP16 split): 0 never, 1 always, 2 = when B >= intra_tc_min
   int intra_tc_min = 1024;
+  int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min
+  int sep_tc_min = 256;
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
   std::map<int, cudaGraphExec_t> graphs;     // keyed by B
   std::vector<std::pair<std::string, float>> ktimes;
@@ -185,6 +189,7 @@ void init_dprnn_kernels();
 void init_dense_kernels();
 void init_dprnn_tc_kernels();
 void init_dprnn_intra_tc_kernels();
+void init_conv_tc_kernels();
 void enqueue_step(Engine& e, int B, cudaStream_t st);    // all kernels of one hop, in order
 
 }  // namespace dpdf

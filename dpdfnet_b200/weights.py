@@ -238,6 +238,7 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
         sc, sh = _bn_affine(sd, bn_prefix)
         t[f"{prefix_out}.dw"] = np.stack(dws, 0)
         t[f"{prefix_out}.pw"] = sd[pw_key][:, :, 0, 0].astype(np.float64) * sc[:, None]
+        t[f"{prefix_out}.tc_pw"] = umma_operand16(t[f"{prefix_out}.pw"].astype(np.float32))     # k_sepconv_tc
         t[f"{prefix_out}.b"] = sh
 
     # --- encoder -----------------------------------------------------------
@@ -251,6 +252,7 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
     t["enc.df_conv0.w"] = gw.reshape(C, 9).T                                            # [9, C]; ch<32 <- re, else im
     sc, sh = _bn_affine(sd, "enc.df_conv0.3")
     t["enc.df_conv0.pw"] = sd["enc.df_conv0.2.weight"][:, :, 0, 0].astype(np.float64) * sc[:, None]
+    t["enc.df_conv0.tc_pw"] = umma_operand16(t["enc.df_conv0.pw"].astype(np.float32))
     t["enc.df_conv0.b"] = sh
     sep("enc.df_conv1", ["enc.df_conv1.0.weight"], "enc.df_conv1.1.weight", "enc.df_conv1.2")
 
