@@ -109,7 +109,7 @@ static int bind_weights(Engine& e) {
     }
   }
   auto gl = [&](const std::string& n, int G, int Ng, int Kg) { return GLW{W(n + ".w", (size_t)G * Ng * Kg), W(n + ".b", (size_t)G * Ng), G, Ng, Kg}; };
-  auto gru = [&](const std::string& n) { return GRUW{W(n + ".wih", 3 * H * H), W(n + ".whh", 3 * H * H), W(n + ".bias", 4 * H)}; };
+  auto gru = [&](const std::string& n) { return GRUW{W(n + ".wih", 3 * H * H), W(n + ".whh", 3 * H * H), W(n + ".bias", 4 * H), W(n + ".tc_w", 2 * 3 * H * H)}; };
   const int kfc = C * d.fe[3] / 32;
   if (d.hr48) {
     w.erb_fc_emb = gl("enc.erb_fc_emb", 32, 16, kfc);
@@ -289,6 +289,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   init_dprnn_tc_kernels();
   init_dprnn_intra_tc_kernels();
   init_conv_tc_kernels();
+  init_gru_tc_kernels();
   launch_reset(e, nullptr, max_streams, e.own_stream);
   if (cudaStreamSynchronize(e.own_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
     return bail(fail(DPDF_ERR_CUDA, "engine initialisation kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -346,6 +347,11 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     if (use_sep_tc) launch_sepconv_tc(en, probs, nprob, Bn, s_);
     else launch_sepconv(en, probs, nprob, Bn, s_);
   };
+  const bool use_gru_tc = e.gru_tc == 1 || (e.gru_tc == 2 && std::max(B, e.total_B) >= e.gru_tc_min);
+  auto gru_cells = [&](Engine& en, const GRUProblem* probs, int nprob, int Bn, cudaStream_t s_) {
+    if (use_gru_tc) launch_gru_tc(en, probs, nprob, Bn, s_);
+    else launch_gru(en, probs, nprob, Bn, s_);
+  };
   RUN("analysis", launch_analysis(e, B, st)); ++n;
   RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
   auto sepp = [&](const SepW& sw, const float* in1, const float* in2, int pidx, float* out, int Fin, int Fout, int stride, int up) {
@@ -400,7 +406,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   }
   {
     GRUProblem g{c.g0, e.st.h_enc, H, w.enc_gru, c.henc};
-    RUN("gru", launch_gru(e, &g, 1, B, st)); ++n;
+    RUN("gru", gru_cells(e, &g, 1, B, st)); ++n;
   }
   {
     GLProblem q = glp(w.enc_out, c.henc, H, c.emb, 512, 1);
@@ -412,9 +418,9 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   }
   {
     GRUProblem g[2] = {{c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1}};
-    RUN("gru", launch_gru(e, g, 2, B, st)); ++n;
+    RUN("gru", gru_cells(e, g, 2, B, st)); ++n;
     GRUProblem g2[2] = {{c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
-    RUN("gru", launch_gru(e, g2, 2, B, st)); ++n;
+    RUN("gru", gru_cells(e, g2, 2, B, st)); ++n;
     GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc}, g[0], g[1], g2[0], g2[1]};
     RUN("gru_commit", launch_gru_commit(e, all, 5, B, st)); ++n;
   }
@@ -872,6 +878,11 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     } else {
       e.intra_tc_min = value;
     }
+    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+    e.graphs.clear();
+  } else if (strcmp(key, "gru_tc") == 0) {
+    if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "gru_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
+    e.gru_tc = value;
     for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
     e.graphs.clear();
   } else if (strcmp(key, "sep_tc") == 0) {

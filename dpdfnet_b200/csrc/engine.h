@@ -53,7 +53,7 @@ struct Scratch {         // all [max_streams][...]
 
 struct SepW { const float *dw, *pw, *b, *tc_pw; };     // tc_pw: FP16 hi/lo tcgen05 image of pw (weights.py:umma_operand16)
 struct GLW { const float *w, *b; int G, Ng, Kg; };
-struct GRUW { const float *wih, *whh, *bias; };
+struct GRUW { const float *wih, *whh, *bias, *tc_w; };   // tc_w: FP16 hi/lo slab images for k_gru_tc (weights.py:gru_tc_images)
 struct DprnnW {
   const float *i_wih, *i_whh, *i_bias, *fc_w, *fc_b, *ln_g, *ln_b;
   const float *r_wih, *r_whh, *r_bias, *fc2_w, *fc2_b, *ln2_g, *ln2_b;
@@ -128,6 +128,7 @@ struct GRUProblem {
   float* hout;      // [B][256]
 };
 void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st);
+void launch_gru_tc(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st);
 void launch_gru_commit(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st);   // nprob <= 5
 
 // ---- the engine -----------------------------------------------------------------------------
@@ -173,6 +174,8 @@ struct Engine {
   int intra_bt = 0;               // 0 = auto
   int intra_tc = 2;               // intra-frame GRU on tcgen05 (FP16 split): 0 never, 1 always, 2 = when B >= intra_tc_min
   int intra_tc_min = 1024;
+  int gru_tc = 2;                 // GRUCell(256) gate GEMMs on tcgen05: 0 never, 1 always, 2 = when B >= gru_tc_min
+  int gru_tc_min = 256;
   int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min
   int sep_tc_min = 256;
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
@@ -190,6 +193,7 @@ void init_dense_kernels();
 void init_dprnn_tc_kernels();
 void init_dprnn_intra_tc_kernels();
 void init_conv_tc_kernels();
+void init_gru_tc_kernels();
 void enqueue_step(Engine& e, int B, cudaStream_t st);    // all kernels of one hop, in order
 
 }  // namespace dpdf

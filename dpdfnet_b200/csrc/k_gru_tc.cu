@@ -1,0 +1,194 @@
+// k_gru_tc: GRUCell(256) (a8 - a10: the embedding GRU and the two decoder GRU stacks; layers.py:1117-1188,
+// torch.nn.GRUCell semantics) with both gate GEMMs on the tensor cores.
+//
+// One CTA = (tile of 128 streams, chunk of 64 hidden units, cell of the launch): gate pre-activations
+//     [128 x 256] = x[128 x 256] * W_ih[chunk]^T  (r | z | in)  +  h[128 x 256] * W_hh[chunk]^T  (r, z on top; hn apart)
+// as a K-pipelined chain of tcgen05.mma.kind::f16 instructions (FP16 hi/lo split, FP32 accumulate in TMEM, see
+// tc_common.cuh).  K = 512 is walked in eight 64-wide stages: the eight converter warps load the FP32 activation
+// chunk, split it and store it as K-major operand images (2-deep ring), the issuer warp streams the matching
+// 48 KB weight slab ([192 gate rows][64 k], hi | lo; weights.py: tc_w) through a 3-deep ring of bulk copies and
+// fires 24 MMAs per stage; stage completion (tcgen05.commit) frees both rings.  Epilogue: thread = (TMEM lane =
+// stream, 32 units): gates, h' = (1 - z) n + z h  ->  hout (the state itself is committed by k_gru_commit).
+#include "engine.h"
+#include "tc_common.cuh"
+
+namespace dpdf {
+
+namespace {
+
+using namespace tc;
+
+constexpr int GT_CONV = 256;                 // converter / epilogue threads
+constexpr int GT_NT = GT_CONV + 32;          // + issuer warp
+constexpr int GT_AIMG = 128 * 64 * 2;        // one FP16 [128][64] image
+constexpr int GT_WSLAB = 2 * 192 * 64 * 2;   // [192][64] hi | lo
+constexpr int GT_OFF_W = 2 * 2 * GT_AIMG;    // A ring: 2 stages x (hi | lo)
+constexpr int GT_OFF_MISC = GT_OFF_W + 3 * GT_WSLAB;
+constexpr size_t GRU_TC_SMEM = GT_OFF_MISC + 1024 + 128;   // + slot offsets [128] int64 ... barriers
+
+}  // namespace
+
+struct GRUTcParams {
+  const IoDesc* io;
+  GRUProblem prob[2];
+  int B;
+};
+
+__global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* Asm = smem_raw;
+  unsigned char* Wsm = smem_raw + GT_OFF_W;
+  long long* s_hoff = reinterpret_cast<long long*>(smem_raw + GT_OFF_MISC);
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem_raw + GT_OFF_MISC + 1024);   // [3]
+  uint64_t* done = full_w + 3;                                                     // [8], one per stage, single use
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 8);
+
+  const GRUProblem& q = p.prob[blockIdx.z];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * 128;
+  const int uc = blockIdx.y;                                  // unit chunk: hidden units [64 uc, 64 uc + 64)
+  const int valid = min(128, p.B - b0);
+
+  if (tid < 128) s_hoff[tid] = tid < valid ? (long long)io_slot(p.io, b0 + tid) * q.hs_stride : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < 11; ++i) mbar_init(full_w + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ---- issuer warp: weight slab ring + MMAs -----------------------------------------------------------------
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(q.w.tc_w) + (size_t)uc * 8 * GT_WSLAB;
+    auto load_w = [&](int s) {
+      mbar_expect_tx(full_w + s % 3, GT_WSLAB);
+      bulk_g2s(Wsm + (s % 3) * GT_WSLAB, wsrc + (size_t)s * GT_WSLAB, GT_WSLAB, full_w + s % 3);
+    };
+    if (lane == 0) { load_w(0); load_w(1); load_w(2); }
+    for (int s = 0; s < 8; ++s) {
+      const int buf = s & 1;
+      if (buf == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT_NT) : "memory");      // A images of stage s written
+      else asm volatile("bar.sync 2, %0;" ::"n"(GT_NT) : "memory");
+      if (lane == 0) {
+        tc_fence_after();
+        mbar_wait(full_w + s % 3, (s / 3) & 1);
+        const uint32_t ah = smem_u32(Asm) + buf * 2 * GT_AIMG, al = ah + GT_AIMG;
+        const uint32_t bh = smem_u32(Wsm) + (s % 3) * GT_WSLAB, bl = bh + GT_WSLAB / 2;
+        const bool hpart = s >= 4;
+        const uint32_t ncol = hpart ? 192u : 128u;           // in (x part) / hn (h part)
+        const uint32_t nfirst = (s & 3) == 0 ? 0u : 1u;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t dah = umma_desc(ah + ks * 256, 1024), dal = umma_desc(al + ks * 256, 1024);
+          const uint64_t dbh = umma_desc(bh + ks * 256, 1024), dbl = umma_desc(bl + ks * 256, 1024);
+          const uint64_t dnh = umma_desc(bh + 16 * 1024 + ks * 256, 1024), dnl = umma_desc(bl + 16 * 1024 + ks * 256, 1024);
+          umma_f16(tmem, dah, dbh, idesc_f16(128, 128), (s > 0 || ks > 0) ? 1u : 0u);   // r | z: x and h parts add up
+          umma_f16(tmem, dal, dbh, idesc_f16(128, 128), 1);
+          umma_f16(tmem, dah, dbl, idesc_f16(128, 128), 1);
+          umma_f16(tmem + ncol, dah, dnh, idesc_f16(128, 64), ks > 0 ? 1u : nfirst);
+          umma_f16(tmem + ncol, dal, dnh, idesc_f16(128, 64), 1);
+          umma_f16(tmem + ncol, dah, dnl, idesc_f16(128, 64), 1);
+        }
+        umma_commit(done + s);
+        if (s >= 1 && s + 2 < 8) {                            // slab ring slot of stage s - 1 is free once its MMAs are done
+          mbar_wait(done + s - 1, 0);
+          load_w(s + 2);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- converter warps: activation chunk -> operand images ---------------------------------------------------
+    // thread = (k quad g, row r & 7 ...): the 8 lanes of a k quad write 8 consecutive rows of one 16-byte chunk column,
+    // so a warp's 8-byte stores fill two whole 128-byte core matrices
+    const int g = (tid >> 3) & 15;
+    const int rsub = (tid & 7) | ((tid >> 7) << 3);
+    for (int s = 0; s < 8; ++s) {
+      const int buf = s & 1, k0 = (s & 3) * 64 + g * 4;
+      const bool hpart = s >= 4;
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 16 * i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < valid) v[i] = __ldg(reinterpret_cast<const float4*>((hpart ? q.hstate + s_hoff[r] : q.x + (size_t)(b0 + r) * H) + k0));
+      }
+      if (s >= 2) mbar_wait(done + s - 2, 0);                 // MMAs that read this image pair are complete
+      unsigned char* img = Asm + buf * 2 * GT_AIMG;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 16 * i;
+        uint2 h, l;
+        split2_f16(v[i].x, v[i].y, h.x, l.x);
+        split2_f16(v[i].z, v[i].w, h.y, l.y);
+        unsigned char* dst = img + (r >> 3) * 1024 + (g >> 1) * 128 + (r & 7) * 16 + (g & 1) * 8;
+        *reinterpret_cast<uint2*>(dst) = h;
+        *reinterpret_cast<uint2*>(dst + GT_AIMG) = l;
+      }
+      fence_async_smem();
+      if (buf == 0) asm volatile("bar.arrive 1, %0;" ::"n"(GT_NT) : "memory");
+      else asm volatile("bar.arrive 2, %0;" ::"n"(GT_NT) : "memory");
+    }
+    // ---- epilogue: thread = (stream row = TMEM lane, 32 units) ----------------------------------------------------
+    mbar_wait(done + 7, 0);
+    tc_fence_after();
+    const int qd = warp & 3, half = warp >> 2, row = qd * 32 + lane;
+    const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + half * 32;
+    const float* bias = q.w.bias;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t gr[8], gz[8], gi[8], gh[8];
+      tmem_ld8_nowait(ta + c * 8, gr);
+      tmem_ld8_nowait(ta + 64 + c * 8, gz);
+      tmem_ld8_nowait(ta + 128 + c * 8, gi);
+      tmem_ld8_nowait(ta + 192 + c * 8, gh);
+      const int u = uc * 64 + half * 32 + c * 8;
+      float hp[8];
+      if (row < valid) {
+        const float4 a = *reinterpret_cast<const float4*>(q.hstate + s_hoff[row] + u);
+        const float4 b = *reinterpret_cast<const float4*>(q.hstate + s_hoff[row] + u + 4);
+        hp[0] = a.x; hp[1] = a.y; hp[2] = a.z; hp[3] = a.w; hp[4] = b.x; hp[5] = b.y; hp[6] = b.z; hp[7] = b.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) hp[e] = 0.f;
+      }
+      tmem_ld_wait();
+      float hn[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float rg = sigmoidf_(__uint_as_float(gr[e]) + __ldg(bias + u + e));
+        const float zg = sigmoidf_(__uint_as_float(gz[e]) + __ldg(bias + H + u + e));
+        const float ng = tanhf_(__uint_as_float(gi[e]) + __ldg(bias + 2 * H + u + e) + rg * (__uint_as_float(gh[e]) + __ldg(bias + 3 * H + u + e)));
+        hn[e] = (1.0f - zg) * ng + zg * hp[e];
+      }
+      if (row < valid) {
+        float* dst = q.hout + (size_t)(b0 + row) * H + u;
+        *reinterpret_cast<float4*>(dst) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+void launch_gru_tc(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st) {
+  GRUTcParams p{};
+  p.io = e.io_dev;
+  p.B = B;
+  for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
+  dim3 grid((B + 127) / 128, H / 64, nprob);
+  k_gru_tc<<<grid, GT_NT, GRU_TC_SMEM, st>>>(p);
+}
+
+void init_gru_tc_kernels() {
+  cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRU_TC_SMEM);
+}
+
+}  // namespace dpdf

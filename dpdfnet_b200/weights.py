@@ -301,6 +301,7 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             t[f"{out}.{l}.wih"] = sd[f"{prefix}.weight_ih_l{l}"]
             t[f"{out}.{l}.whh"] = sd[f"{prefix}.weight_hh_l{l}"]
             t[f"{out}.{l}.bias"] = _gru_bias(sd[f"{prefix}.bias_ih_l{l}"], sd[f"{prefix}.bias_hh_l{l}"])
+            t[f"{out}.{l}.tc_w"] = gru_tc_images(t[f"{out}.{l}.wih"], t[f"{out}.{l}.whh"])
 
     if spec.hr48:
         gl("enc.erb_fc_emb", "enc.erb_fc_emb.0", 32)
@@ -392,6 +393,19 @@ def umma_operand16(mat: np.ndarray) -> np.ndarray:
     """hi image then lo image of a weight matrix [N, K] in FP16, returned as float32 words (raw bytes)."""
     hi, lo = fp16_split(mat)
     return np.concatenate([umma_kmajor16(hi), umma_kmajor16(lo)]).view(np.float32)
+
+
+def gru_tc_images(wih: np.ndarray, whh: np.ndarray) -> np.ndarray:
+    """Weight slabs of k_gru_tc: for each chunk of 64 hidden units, for W_ih then W_hh, for each 64-wide K chunk, the
+    [192][64] matrix of the chunk's r, z and n gate rows as FP16 hi | lo operand images (48 KB per slab)."""
+    Hh = wih.shape[1]
+    out = []
+    for u in range(Hh // 64):
+        rows = np.concatenate([np.arange(g * Hh + 64 * u, g * Hh + 64 * u + 64) for g in range(3)])
+        for m in (wih, whh):
+            for kc in range(Hh // 64):
+                out.append(umma_operand16(np.ascontiguousarray(m[rows, 64 * kc:64 * kc + 64], dtype=np.float32)))
+    return np.concatenate(out)
 
 
 def serialize(tensors: Mapping[str, np.ndarray]) -> bytes:

@@ -74,7 +74,8 @@ def test_stages_vs_oracle(torch_cuda, name, B, intra_tc):
     eng = _engine(name, 11, B + 3)
     eng.set_option("graph", 0)
     eng.set_option("intra_tc", intra_tc)
-    eng.set_option("sep_tc", intra_tc)          # the separable convs on the same arm: FFMA2 / tcgen05
+    eng.set_option("sep_tc", intra_tc)          # the separable convs and the GRU(256) cells on the same arm: FFMA2 / tcgen05
+    eng.set_option("gru_tc", intra_tc)
     ora = _oracle(name, 11, B + 3)
     spec = eng.spec
     rng = np.random.default_rng(2)
