@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid < 256) sb[tid] = __ldg((br ? p.bias[1] : p.bias[0]) + dir * 4 * C + tid);
+  for (int i = tid; i < ST_BUF / 16; i += ITC_NT) reinterpret_cast<uint4*>(Ssm + ST_BUF)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0 (read back as h_prev of step 0)
   __syncthreads();                                           // barriers initialised
   if (tid == 0) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(br ? p.wimg[1] : p.wimg[0]) + (size_t)dir * 4 * W_IMG;
@@ -268,9 +269,6 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   } else {
     // ---- the sweep (gate warps) -----------------------------------------------------------------------------
     // thread (row = TMEM lane, g = warp >> 2) owns units 16 ks + 4 g + j  (ks, j = 0..3): four of every K slice
-    float h[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) h[i] = 0.f;
     const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16);
     // Write-out of h_s: staging[s & 1] -> hcat[b][f][dir*64 ..], two full 256-byte rows per warp instruction.  It runs
     // inside step s + 1, under the MUFU-bound gate math: passing the accumulator barrier of step s + 1 proves that every
@@ -303,34 +301,30 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
       uint32_t ghn[4][4];
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) tmem_ld4_nowait(lane_base + TM_HN + 16 * ks + 4 * cg, ghn[ks]);
-      uint32_t gr[4], gz[4], gi[4];
+      // r, z pre-activations run one slice ahead of in / hn: the sigmoid stage of slice ks+1 is software pipelined
+      // with the tanh stage of slice ks (four independent MUFU chains per thread instead of two)
+      uint32_t grz[2][2][4], gi[4];
       const uint32_t pa = lane_base + TM_P + (t & 1) * 192 + 4 * cg;
-      tmem_ld4_nowait(pa, gr);
-      tmem_ld4_nowait(pa + 64, gz);
+      tmem_ld4_nowait(pa, grz[0][0]);
+      tmem_ld4_nowait(pa + 64, grz[0][1]);
+      tmem_ld4_nowait(pa + 16, grz[1][0]);
+      tmem_ld4_nowait(pa + 64 + 16, grz[1][1]);
       tmem_ld4_nowait(pa + 128, gi);
       tmem_ld_wait();
       TL(2);
       unsigned char* srow = Ssm + (t & 1) * ST_BUF + row * 256;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      const unsigned char* prow = Ssm + ((t + 1) & 1) * ST_BUF + row * 256;      // h_{t-1} of this thread's units (FP32)
+      const float2 one = make_float2(1.0f, 1.0f);
+      // sigmoid stage: r = 1 / (1 + 2^a_r), z = 1 / (1 + 2^a_z) with one shared reciprocal.  The operand images and
+      // biases carry the exponent scales (weights.py: r, z rows x -log2(e); n rows x 2 log2(e)).
+      auto stage_a = [&](int ks, const uint32_t (&g_r)[4], const uint32_t (&g_z)[4], float2 (&r)[2], float2 (&z)[2]) {
         const int u0 = 16 * ks + 4 * cg;
-        // Gate math on unit pairs (packed f32x2 FMA-pipe ops).  The operand images and biases carry the exponent
-        // scales (weights.py: r, z rows x -log2(e); n rows x 2 log2(e)), so
-        //   r = 1 / (1 + 2^a_r),  z = 1 / (1 + 2^a_z)   (one shared reciprocal),   n = tanh(c) = 1 - 2 / (1 + 2^c')
-        float hn[4];
-#ifdef ITC_NO_MATH
 #pragma unroll
-        for (int e = 0; e < 4; ++e) hn[e] = __uint_as_float(gr[e] ^ gz[e] ^ gi[e] ^ ghn[ks][e]) * 1e-30f + h[ks * 4 + e];
-#else
-#pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-          const float2 b_r = *reinterpret_cast<const float2*>(sb + u0 + e);
-          const float2 b_z = *reinterpret_cast<const float2*>(sb + C + u0 + e);
-          const float2 b_i = *reinterpret_cast<const float2*>(sb + 2 * C + u0 + e);
-          const float2 b_h = *reinterpret_cast<const float2*>(sb + 3 * C + u0 + e);
-          const float2 one = make_float2(1.0f, 1.0f);
-          const float2 ar = __fadd2_rn(make_float2(__uint_as_float(gr[e]), __uint_as_float(gr[e + 1])), b_r);
-          const float2 az = __fadd2_rn(make_float2(__uint_as_float(gz[e]), __uint_as_float(gz[e + 1])), b_z);
+        for (int e = 0; e < 2; ++e) {
+          const float2 b_r = *reinterpret_cast<const float2*>(sb + u0 + 2 * e);
+          const float2 b_z = *reinterpret_cast<const float2*>(sb + C + u0 + 2 * e);
+          const float2 ar = __fadd2_rn(make_float2(__uint_as_float(g_r[2 * e]), __uint_as_float(g_r[2 * e + 1])), b_r);
+          const float2 az = __fadd2_rn(make_float2(__uint_as_float(g_z[2 * e]), __uint_as_float(g_z[2 * e + 1])), b_z);
 #if ITC_POLY
           const float2 pr = __fadd2_rn(ex2_poly2(make_float2(clampf(ar.x, -125.f, 60.f), clampf(ar.y, -125.f, 60.f))), one);
           const float2 pz = __fadd2_rn(ex2_poly2(make_float2(clampf(az.x, -125.f, 60.f), clampf(az.y, -125.f, 60.f))), one);
@@ -341,24 +335,45 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
 #endif
           const float2 pp = __fmul2_rn(pr, pz);
           const float2 ip = make_float2(rcp_ftz(pp.x), rcp_ftz(pp.y));
-          const float2 r = __fmul2_rn(ip, pz), z = __fmul2_rn(ip, pr);
-          const float2 vhn = __fadd2_rn(make_float2(__uint_as_float(ghn[ks][e]), __uint_as_float(ghn[ks][e + 1])), b_h);
-          const float2 vin = __fadd2_rn(make_float2(__uint_as_float(gi[e]), __uint_as_float(gi[e + 1])), b_i);
-          const float2 c = __ffma2_rn(r, vhn, vin);
+          r[e] = __fmul2_rn(ip, pz);
+          z[e] = __fmul2_rn(ip, pr);
+        }
+      };
+      float2 rc[2], zc[2];
+      stage_a(0, grz[0][0], grz[0][1], rc, zc);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int u0 = 16 * ks + 4 * cg;
+        float2 rn[2], zn[2];
+        if (ks < 3) stage_a(ks + 1, grz[(ks + 1) & 1][0], grz[(ks + 1) & 1][1], rn, zn);
+        // tanh stage: n = tanh(c) = 1 - 2 / (1 + 2^c'),  h' = (1 - z) n + z h
+        const float4 hp4 = *reinterpret_cast<const float4*>(prow + (((4 * ks + cg) ^ (row & 15)) << 4));
+        float hn[4];
+#ifdef ITC_NO_MATH
+        hn[0] = rc[0].x * 1e-30f + hp4.x; hn[1] = zc[0].y * 1e-30f + hp4.y; hn[2] = __uint_as_float(gi[2] ^ ghn[ks][2]) * 1e-30f + hp4.z; hn[3] = hp4.w;
+#else
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float2 b_i = *reinterpret_cast<const float2*>(sb + 2 * C + u0 + 2 * e);
+          const float2 b_h = *reinterpret_cast<const float2*>(sb + 3 * C + u0 + 2 * e);
+          const float2 vhn = __fadd2_rn(make_float2(__uint_as_float(ghn[ks][2 * e]), __uint_as_float(ghn[ks][2 * e + 1])), b_h);
+          const float2 vin = __fadd2_rn(make_float2(__uint_as_float(gi[2 * e]), __uint_as_float(gi[2 * e + 1])), b_i);
+          const float2 c = __ffma2_rn(rc[e], vhn, vin);
           const float2 pc = __fadd2_rn(make_float2(ex2_ftz(c.x), ex2_ftz(c.y)), one);
           const float2 q = make_float2(rcp_ftz(pc.x), rcp_ftz(pc.y));
           const float2 n = __ffma2_rn(make_float2(-2.0f, -2.0f), q, one);
-          const float2 hp = make_float2(h[ks * 4 + e], h[ks * 4 + e + 1]);
-          const float2 hv = __ffma2_rn(z, __fadd2_rn(hp, make_float2(-n.x, -n.y)), n);      // (1 - z) n + z h
-          hn[e] = hv.x; hn[e + 1] = hv.y;
+          const float2 hp = e ? make_float2(hp4.z, hp4.w) : make_float2(hp4.x, hp4.y);
+          const float2 hv = __ffma2_rn(zc[e], __fadd2_rn(hp, make_float2(-n.x, -n.y)), n);
+          hn[2 * e] = hv.x; hn[2 * e + 1] = hv.y;
         }
 #endif
-#pragma unroll
-        for (int e = 0; e < 4; ++e) h[ks * 4 + e] = hn[e];
-        if (ks < 3) {                                        // next slice's pre-activations: in flight under the stores below
-          tmem_ld4_nowait(pa + 16 * (ks + 1), gr);
-          tmem_ld4_nowait(pa + 64 + 16 * (ks + 1), gz);
+        if (ks < 3) {                                        // pre-activations of the coming slices: in flight under the stores below
           tmem_ld4_nowait(pa + 128 + 16 * (ks + 1), gi);
+          if (ks < 2) {
+            tmem_ld4_nowait(pa + 16 * (ks + 2), grz[ks & 1][0]);
+            tmem_ld4_nowait(pa + 64 + 16 * (ks + 2), grz[ks & 1][1]);
+          }
+          rc[0] = rn[0]; rc[1] = rn[1]; zc[0] = zn[0]; zc[1] = zn[1];
         }
         uint32_t hi0, lo0, hi1, lo1;
         split2_f16(hn[0], hn[1], hi0, lo0);
