@@ -385,10 +385,10 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-batch", type=int, default=128)
-    ap.add_argument("--cpu-hops", type=int, default=100)
+    ap.add_argument("--cpu-hops", type=int, default=60)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-ladder", action="store_true", help="skip the sustained-streams batch ladder")
-    ap.add_argument("--ladder", type=int, nargs="*", default=[4096, 6144, 7168, 8192])
+    ap.add_argument("--ladder", type=int, nargs="*", default=[4096, 8192, 12288, 16384, 20480])
     ap.add_argument("--intra-bt", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=-1, help="kernel-chain lanes per step (-1: engine default)")
     ap.add_argument("--profile-only", action="store_true", help="device steps only (for ncu runs)")

@@ -277,7 +277,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
     return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(io) failed"));
   e.io_dev = e.io_lanes;
   if (cudaStreamCreateWithFlags(&e.own_stream, cudaStreamDefault) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "stream creation failed"));
-  for (int l = 1; l < Engine::MAX_LANES; ++l)
+  for (int l = 0; l < Engine::MAX_LANES; ++l)
     if (cudaStreamCreateWithFlags(&e.lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.lane_done[l], cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(DPDF_ERR_CUDA, "lane stream creation failed"));
@@ -304,7 +304,8 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
   cudaDeviceSynchronize();
   for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
   for (auto ev : e.tev) cudaEventDestroy(ev);
-  for (int l = 1; l < Engine::MAX_LANES; ++l) {
+  for (auto& g : e.lane_graphs) cudaGraphExecDestroy(g.second);
+  for (int l = 0; l < Engine::MAX_LANES; ++l) {
     if (e.lane_stream[l]) cudaStreamDestroy(e.lane_stream[l]);
     if (e.lane_done[l]) cudaEventDestroy(e.lane_done[l]);
   }
@@ -462,10 +463,17 @@ static int check_batch(Engine& e, int B) {
   return 0;
 }
 
+static void drop_graphs(Engine& e) {
+  for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
+  for (auto& g : e.lane_graphs) cudaGraphExecDestroy(g.second);
+  e.graphs.clear();
+  e.lane_graphs.clear();
+}
+
 // Number of lanes of a step over B streams: explicit option, else enough streams per lane to keep the tensor-core
 // kernels' 128-stream tiles full.
 static int lanes_for(const Engine& e, int B) {
-  int L = e.lanes > 0 ? e.lanes : (B >= 2048 ? 2 : (B >= 1024 ? 4 : 1));   // measured: profiles/r01u_lanes.log
+  int L = e.lanes > 0 ? e.lanes : (B >= 2048 ? 8 : (B >= 1024 ? 4 : 1));   // measured: profiles/r01B_lanes.log
   L = std::min(L, Engine::MAX_LANES);
   while (L > 1 && B / L < 128) --L;
   return std::max(L, 1);
@@ -532,6 +540,58 @@ static int run_step(Engine& e, int B, cudaStream_t st) {
   return 0;
 }
 
+// T hops with free-running lanes: the lanes of a batch share nothing inside a hop and nothing across hops but their
+// own slots, so every lane replays its own one-hop graph T times on its own stream and the caller's stream joins them
+// once at the end.  The lanes drift out of lock step, which is the point: the latency-bound recurrence kernels of one
+// lane overlap with the throughput kernels of the others for the whole run, not just inside one hop.
+static int run_hops_free(Engine& e, int B, int T, cudaStream_t st) {
+  const int L = lanes_for(e, B);
+  std::vector<float*> base(e.sc_items.size());
+  for (size_t i = 0; i < base.size(); ++i) base[i] = *e.sc_items[i].first;
+  cudaGraphExec_t exec[Engine::MAX_LANES] = {};
+  int launches = 0, rc = 0;
+  e.total_B = B;
+  for (int l = 0; l < L && rc == 0; ++l) {
+    int r0, n;
+    lane_range(B, L, l, &r0, &n);
+    if (n <= 0) continue;
+    auto it = e.lane_graphs.find(B * Engine::MAX_LANES + l);
+    if (it == e.lane_graphs.end()) {
+      for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i] + (size_t)r0 * e.sc_items[i].second;
+      e.io_dev = e.io_lanes + l;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(e.own_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = fail(DPDF_ERR_CUDA, "graph capture failed"); break; }
+      enqueue_step(e, n, e.own_stream);
+      cudaError_t err = cudaStreamEndCapture(e.own_stream, &graph);
+      cudaGraphExec_t ex = nullptr;
+      if (err == cudaSuccess) err = cudaGraphInstantiate(&ex, graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (err != cudaSuccess) { rc = fail(DPDF_ERR_CUDA, "lane graph failed: %s", cudaGetErrorString(err)); break; }
+      it = e.lane_graphs.emplace(B * Engine::MAX_LANES + l, ex).first;
+      e.launches_per_lane = e.launches;
+    }
+    exec[l] = it->second;
+    launches += e.launches_per_lane;
+  }
+  for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i];
+  e.io_dev = e.io_lanes;
+  e.total_B = 0;
+  if (rc) return rc;
+  e.launches = launches;
+  CU(cudaEventRecord(e.lane_fork, st));
+  for (int l = 0; l < L; ++l)
+    if (exec[l]) CU(cudaStreamWaitEvent(e.lane_stream[l], e.lane_fork, 0));
+  for (int t = 0; t < T; ++t)
+    for (int l = 0; l < L; ++l)
+      if (exec[l]) CU(cudaGraphLaunch(exec[l], e.lane_stream[l]));
+  for (int l = 0; l < L; ++l)
+    if (exec[l]) {
+      CU(cudaEventRecord(e.lane_done[l], e.lane_stream[l]));
+      CU(cudaStreamWaitEvent(st, e.lane_done[l], 0));
+    }
+  return 0;
+}
+
 static int set_io(Engine& e, const float* in, long long in_stride, float* out, long long out_stride,
                   const int32_t* slot_ids, const int32_t* flags, int mode, int B, cudaStream_t st) {
   IoDesc io[Engine::MAX_LANES] = {};
@@ -573,6 +633,7 @@ extern "C" int dpdf_run_pcm(dpdf_engine* h, const float* pcm_in, int64_t in_stri
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (int rc = set_io(e, pcm_in, in_stride, pcm_out, out_stride, slot_ids, flags, 0, B, st)) return rc;
   e.last_B = B;
+  if (T > 1 && e.use_graph && !e.timing && e.free_lanes && lanes_for(e, B) > 1) return run_hops_free(e, B, T, st);
   for (int t = 0; t < T; ++t)
     if (int rc = run_step(e, B, st)) return rc;
   return 0;
@@ -869,8 +930,7 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   else if (strcmp(key, "intra_bt") == 0) {
     if (value != 0 && value != 8 && value != 16 && value != 32) return fail(DPDF_ERR_INVALID, "intra_bt must be 0, 8, 16 or 32");
     e.intra_bt = value;
-    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
-    e.graphs.clear();
+    drop_graphs(e);
   } else if (strcmp(key, "intra_tc") == 0 || strcmp(key, "intra_tc_min") == 0) {
     if (key[8] == 0) {
       if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "intra_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
@@ -878,27 +938,24 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     } else {
       e.intra_tc_min = value;
     }
-    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
-    e.graphs.clear();
+    drop_graphs(e);
   } else if (strcmp(key, "gru_tc") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "gru_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
     e.gru_tc = value;
-    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
-    e.graphs.clear();
+    drop_graphs(e);
   } else if (strcmp(key, "sep_tc") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "sep_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
     e.sep_tc = value;
-    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
-    e.graphs.clear();
+    drop_graphs(e);
+  } else if (strcmp(key, "free_lanes") == 0) {
+    e.free_lanes = value ? 1 : 0;
   } else if (strcmp(key, "lanes") == 0) {
     if (value < 0 || value > Engine::MAX_LANES) return fail(DPDF_ERR_INVALID, "lanes must be 0 (auto) .. %d", Engine::MAX_LANES);
     e.lanes = value;
-    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
-    e.graphs.clear();
+    drop_graphs(e);
   } else if (strcmp(key, "post_tc") == 0) {
     e.post_tc = value ? 1 : 0;
-    for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
-    e.graphs.clear();
+    drop_graphs(e);
   } else return fail(DPDF_ERR_INVALID, "unknown option '%s'", key);
   return 0;
 }

@@ -168,7 +168,7 @@ struct Engine {
   int lanes = 0;                  // 0 = auto by batch size
   int total_B = 0;                // batch of the whole step while its lanes are enqueued (kernel-variant choice)
   std::vector<std::pair<float**, size_t>> sc_items;   // scratch pointer members and their floats per stream
-  cudaStream_t lane_stream[MAX_LANES] = {};
+  cudaStream_t lane_stream[MAX_LANES] = {};  // [0] is used by free-running multi-hop runs only
   cudaEvent_t lane_fork = nullptr, lane_done[MAX_LANES] = {};
   int use_graph = 1;
   int intra_bt = 0;               // 0 = auto
@@ -179,7 +179,10 @@ struct Engine {
   int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min
   int sep_tc_min = 256;
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
-  std::map<int, cudaGraphExec_t> graphs;     // keyed by B
+  std::map<int, cudaGraphExec_t> graphs;     // keyed by B: one hop of all lanes (forked chains, joined)
+  std::map<int, cudaGraphExec_t> lane_graphs; // keyed by B * MAX_LANES + lane: one hop of one lane (free-running lanes of a multi-hop run)
+  int launches_per_lane = 0;
+  int free_lanes = 1;             // multi-hop runs: every lane replays its own graph on its own stream, joined once at the end
   std::vector<std::pair<std::string, float>> ktimes;
   bool timing = false;
   std::vector<cudaEvent_t> tev;

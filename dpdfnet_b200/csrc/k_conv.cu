@@ -19,21 +19,23 @@ struct Conv0Params {
   int fe0, fe_feat, B;
 };
 
+// thread = (b, f, 4 channels): the nine ring taps are read once per thread (broadcast within the 16 threads of a
+// position), weights as float4, one 16-byte store
 __global__ void __launch_bounds__(256) k_erb_conv0(Conv0Params p) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {      // hop counter tick (see IoDesc)
     p.io->t_out = p.io->t_in;
     p.io->t_in = p.io->t_in + 1;
   }
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)p.B * p.fe0 * C;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;      // < 2^32: B * fe0 * 16
+  const unsigned total = (unsigned)p.B * p.fe0 * (C / 4);
   if (idx >= total) return;
-  const int c = idx % C;
-  const int f = (idx / C) % p.fe0;
-  const int b = idx / ((long long)C * p.fe0);
+  const int c = (idx & 15) * 4;
+  const unsigned bf = idx >> 4;
+  const int f = bf % p.fe0, b = bf / p.fe0;
   const int slot = io_slot(p.io, b);
   const int pos = p.st.pos[slot];
   const float* ring = p.st.erb_ring + (size_t)slot * 3 * p.fe_feat;
-  float acc = 0.f;
+  float4 acc = __ldg(reinterpret_cast<const float4*>(p.bias + c));
 #pragma unroll
   for (int kt = 0; kt < 3; ++kt) {
     const float* row = ring + ((pos + 1 + kt) % 3) * p.fe_feat;
@@ -41,15 +43,17 @@ __global__ void __launch_bounds__(256) k_erb_conv0(Conv0Params p) {
     for (int kf = 0; kf < 3; ++kf) {
       const int fi = f + kf - 1;
       const float x = (fi >= 0 && fi < p.fe0) ? row[fi] : 0.f;
-      acc = fmaf(__ldg(p.w + (kt * 3 + kf) * C + c), x, acc);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (kt * 3 + kf) * C + c));
+      acc.x = fmaf(w.x, x, acc.x); acc.y = fmaf(w.y, x, acc.y); acc.z = fmaf(w.z, x, acc.z); acc.w = fmaf(w.w, x, acc.w);
     }
   }
-  p.e0[idx] = fmaxf(acc + __ldg(p.bias + c), 0.f);
+  *reinterpret_cast<float4*>(p.e0 + (size_t)bf * C + c) =
+      make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
 }
 
 void launch_erb_conv0(Engine& e, int B, cudaStream_t st) {
   Conv0Params p{e.io_dev, e.st, e.w.erb_conv0_w, e.w.erb_conv0_b, e.sc.e0, e.d.fe[0], e.d.fe_feat, B};
-  const long long total = (long long)B * e.d.fe[0] * C;
+  const long long total = (long long)B * e.d.fe[0] * (C / 4);
   k_erb_conv0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
 }
 

@@ -168,6 +168,9 @@ def test_lanes_match_single_chain(torch_cuda, intra_tc):
         st = eng.state_export(int(slots[B - 1]))
         outs.append((a, b, st))
         assert eng.kernel_launches >= min(lanes, 2) * 20            # 400 streams fill two 256-stream lanes
+    eng.set_option("free_lanes", 0)                                     # lanes forked and joined inside every hop
+    eng.reset()
+    assert np.array_equal(eng.run_pcm_host(pcm), outs[0][0])
     for a, b, st in outs[1:]:
         assert np.array_equal(a, outs[0][0])
         assert np.array_equal(b, outs[0][1])
