@@ -41,13 +41,13 @@ for l in sys.stdin:
       # 5 warm-up hops skipped by -s (launches per hop printed by the bench), one hop listed; graph off so
       # every node is a plain launch
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 120 --csv \
-        --log-file $OUT/${TAG}_launches.csv python bench.py --steps 8 --warmup 8 --no-graph --profile-only \
+        --log-file $OUT/${TAG}_launches.csv python bench.py --steps 8 --warmup 8 --no-graph --profile-only --lanes 1 ${BENCH_ARGS:-} \
         > $OUT/${TAG}_launches.log 2>&1
       echo "launches exit $?" ;;
     ncu)
       for k in ${NCU_KERNELS:-k_dprnn_intra k_dprnn_post_tc}; do
         timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 2 \
-          -f -o $OUT/${TAG}_$k python bench.py --steps 4 --warmup 4 --no-graph --profile-only ${BENCH_ARGS:-} \
+          -f -o $OUT/${TAG}_$k python bench.py --steps 4 --warmup 4 --no-graph --profile-only --lanes 1 ${BENCH_ARGS:-} \
           > $OUT/${TAG}_ncu_$k.log 2>&1
         echo "ncu $k exit $?"
       done ;;
