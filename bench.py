@@ -152,7 +152,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.model} 16 kHz per-frame hot path, batch={args.batch} streams/GPU", "cpu_sample": sample},
+            "config": {"workload": f"{args.model} {spec.sample_rate // 1000} kHz per-frame hot path, batch={args.batch} streams/GPU", "cpu_sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "oracle/oracle_np.py: numpy restatement of onnx_model/dpdfnet.py + stream.py DSP, OpenBLAS threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -336,7 +336,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} 16 kHz per-frame hot path (STFT->DPRNN->DF->iSTFT), batch={B} streams/GPU x {K} hops",
+        "config": {"workload": f"{args.model} {spec.sample_rate // 1000} kHz per-frame hot path (STFT->DPRNN->DF->iSTFT), batch={B} streams/GPU x {K} hops",
                    "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
                    "l2": f"no flush: per-step working set {B * 4 * spec.state_size / 1e6:.0f} MB of stream state > 126 MB L2",
                    "weights": "seeded random (no checkpoint offline), BN stats randomised",

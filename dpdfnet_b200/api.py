@@ -60,16 +60,24 @@ def enhance(audio: np.ndarray, sample_rate: int, *, model: str = DEFAULT_MODEL,
                                  attn_limit_db=attn_limit_db, progress_callback=progress_callback)
 
 
+def fit_to(y: np.ndarray, n: int) -> np.ndarray:
+    return y[:n] if y.size >= n else np.pad(y, (0, n - y.size))
+
+
 def enhance_batch(clips: Sequence[np.ndarray], sample_rate: int, *, model: str = DEFAULT_MODEL,
-                  onnx_path: Optional[Union[str, Path]] = None, engine=None, exact_offline: bool = True) -> List[np.ndarray]:
+                  onnx_path: Optional[Union[str, Path]] = None, engine=None, exact_offline: bool = True,
+                  attn_limit_db: Optional[float] = None) -> List[np.ndarray]:
     """Enhance many mono clips at once on one engine (streams = clips, ragged lengths allowed).
 
-    With ``exact_offline`` the result equals the reference's offline PyTorch model
-    (``model/dpdfnet.py``) on every clip; clips are zero-padded to the longest one for the batched run,
-    which does not change earlier samples because the model is causal apart from its 4-frame look-ahead.
+    With ``exact_offline`` the result equals the reference's offline PyTorch model (``model/dpdfnet.py``) on every
+    clip: each stream follows its own reflect padding and flush schedule (``offline.py:enhance_offline_exact_ragged``),
+    so a short clip batched with long ones gets the same samples it gets alone.  ``attn_limit_db`` limits the
+    attenuation like the reference (``audio.py:50-76``: ``alpha * noisy + (1 - alpha) * enhanced``, alpha =
+    10^(-dB/20)); the offline-exact output is sample-aligned with its input and the STFT pair reconstructs exactly, so
+    the blend is done on the waveform.
     """
     from .audio import ensure_sample_rate, to_mono
-    from .offline import enhance_offline_exact
+    from .offline import enhance_offline_exact_ragged
     from .onnx_backend import create_session
     resolved = resolve_model(model=model, onnx_path=onnx_path)
     waves = [ensure_sample_rate(to_mono(np.asarray(c, dtype=np.float32)), int(sample_rate), resolved.info.sample_rate) for c in clips]
@@ -77,17 +85,23 @@ def enhance_batch(clips: Sequence[np.ndarray], sample_rate: int, *, model: str =
         return []
     if engine is None:
         engine = create_session(resolved.onnx_path, max_streams=len(waves)).engine
-    hop = engine.spec.hop
-    n = max(w.size for w in waves)
-    n = max((n + 4 * hop + hop - 1) // hop * hop, 2 * hop)             # room for the look-ahead tail
-    batch = np.zeros((len(waves), n), dtype=np.float32)
-    for i, w in enumerate(waves):
-        batch[i, :w.size] = w
     if not exact_offline:
         raise NotImplementedError("only the offline-exact schedule is implemented for batches")
-    out = enhance_offline_exact(engine, batch)
+    if attn_limit_db is not None and attn_limit_db < 0:
+        raise ValueError("attn_limit_db must be >= 0.")                        # audio.py:45-46
+    hop = engine.spec.hop
+    short = [i for i, w in enumerate(waves) if w.size <= hop]
+    outs = enhance_offline_exact_ragged(engine, [w for w in waves if w.size > hop])
+    it = iter(outs)
     res = []
     for i, w in enumerate(waves):
-        y = ensure_sample_rate(out[i, :w.size], resolved.info.sample_rate, int(sample_rate))
-        res.append(np.ascontiguousarray(y[:np.asarray(clips[i]).shape[0]], dtype=np.float32))
+        y = np.zeros(w.size, np.float32)
+        if i not in short:
+            e = next(it)
+            y[:e.size] = e
+            if attn_limit_db is not None:
+                alpha = np.float32(10.0 ** (-float(attn_limit_db) / 20.0))
+                y[:e.size] = alpha * w[:e.size] + (np.float32(1.0) - alpha) * y[:e.size]
+        y = ensure_sample_rate(y, resolved.info.sample_rate, int(sample_rate))
+        res.append(np.ascontiguousarray(fit_to(y, np.asarray(clips[i]).shape[0]), dtype=np.float32))
     return res

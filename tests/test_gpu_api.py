@@ -98,13 +98,25 @@ def test_enhance_matches_host_pipeline_on_oracle(random_weights):
 
 
 def test_enhance_batch_ragged_clips_match_offline_golden(random_weights, golden_dir):
+    """Ragged clips in one batched run: every clip gets exactly what the offline model gives it alone (own reflect
+    padding, own flush hops), the full-length one equals the reference PyTorch model's golden output end to end."""
     import dpdfnet_b200
+    from dpdfnet_b200.offline import enhance_offline_exact
+    from dpdfnet_b200.onnx_backend import create_session
+    from dpdfnet_b200.models import resolve_model
     g = np.load(golden_dir / "offline_dpdfnet2.npz")
-    clips = [g["wave_in"][0], g["wave_in"][1][:20000]]
+    clips = [g["wave_in"][0], g["wave_in"][1][:20000], g["wave_in"][1][:7531], g["wave_in"][0][:100]]
     out = dpdfnet_b200.enhance_batch(clips, 16000, model="dpdfnet2")
-    assert out[0].shape == clips[0].shape and out[1].shape == clips[1].shape
-    # clips are zero-extended to the batch length (the lone-clip offline model reflect-pads its end), and
-    # the model is causal apart from 4 look-ahead frames + one window: everything before that tail agrees
-    for i, n in enumerate((32000, 20000)):
-        keep = n - 7 * 160
-        assert np.abs(out[i][:keep] - g["wave_out"][i][:keep]).max() < 1e-4
+    assert [o.shape for o in out] == [c.shape for c in clips]
+    assert np.abs(out[0] - g["wave_out"][0]).max() < 1e-4                    # whole clip, including its reflect-padded tail
+    eng = create_session(resolve_model("dpdfnet2").onnx_path, max_streams=1).engine
+    for i in (1, 2):
+        alone = enhance_offline_exact(eng, clips[i][None])[0]
+        assert np.abs(out[i][:alone.size] - alone).max() < 1e-6
+        assert not out[i][alone.size:].any()                                 # the sub-hop remainder is not synthesised
+    assert not out[3].any()                                                  # shorter than a hop: nothing to enhance
+    lim = dpdfnet_b200.enhance_batch(clips[:2], 16000, model="dpdfnet2", attn_limit_db=12.0)
+    alpha = 10.0 ** (-12.0 / 20.0)
+    assert np.abs(lim[1] - (alpha * clips[1] + (1 - alpha) * out[1])).max() < 1e-6
+    with pytest.raises(ValueError):
+        dpdfnet_b200.enhance_batch(clips[:1], 16000, model="dpdfnet2", attn_limit_db=-1.0)

@@ -29,6 +29,18 @@ for l in sys.stdin:
       for b in 1024 2048 8192; do for L in 1 2 4 8; do
         timeout 600 python bench.py --steps 60 --warmup 10 --no-ladder --batch $b --lanes $L --profile-only 2>&1 | sed "s/^/B=$b lanes=$L /" | tee -a $OUT/${TAG}_lanes.log
       done; done ;;
+    configs)   # BASELINE.json configs[2..4]: other model sizes / 48 kHz (device-resident throughput + kernel table)
+      for cfg in "dpdfnet8 4096" "dpdfnet2_48khz_hr 2048" "dpdfnet8_48khz_hr 2048" "dpdfnet2 1024"; do
+        set -- $cfg
+        timeout 600 python bench.py --steps 40 --warmup 10 --no-ladder --model $1 --batch $2 --cpu-hops 2 --cpu-batch 16 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('$1 B=$2', round(d['ms_per_step'], 4), 'ms/hop', int(d['value']), 'sf/s', 'realtime', int(d['realtime_streams']), d['kernel_ms'])
+    else:
+        print(l, end='')
+" | tee -a $OUT/${TAG}_configs.log
+      done ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; tail -2 $OUT/${TAG}_smoke.log ;;
     bench)
