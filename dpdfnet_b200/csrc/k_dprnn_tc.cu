@@ -51,7 +51,16 @@ struct PostTcParams {
   const IoDesc* io;
   PostTcBranch br[2];
   int tiles0, B;
+#ifdef PT_TIMELINE
+  long long* tl;          // [16] SM-clock stamps of CTA 0 (tools/ubench/post_tc_timeline.cu)
+#endif
 };
+
+#ifdef PT_TIMELINE
+#define PTL(slot) do { if (blockIdx.x == 0 && tid == 64) p.tl[slot] = clock64(); } while (0)
+#else
+#define PTL(slot) do { } while (0)
+#endif
 
 constexpr int PT_OFF_W = 4 * IMG;                       // two weight slab buffers
 constexpr int PT_OFF_SP = PT_OFF_W + 2 * WSLAB;         // 640 floats of small parameters
@@ -124,6 +133,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     bulk_g2s(RW + buf * WSLAB, slab_src(i), WSLAB, bars + buf);
   };
   if (tid == 0) { load_slab(0); load_slab(1); }
+  PTL(0);
 
   // ---- stage the hcat tile as two K=64 operand image pairs (split on the fly) --------------------------------
   // a warp instruction covers 8 rows x 16 floats; thread = (row rr of the group, float4 cc): its four halves are
@@ -162,6 +172,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  PTL(1);
   const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16) + cg * 16;
   constexpr uint32_t IDESC = idesc_f16(128, 64);
   const uint32_t a_base = smem_u32(RA), w_base = smem_u32(RW);
@@ -170,15 +181,14 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   auto run_slab = [&](int i, int a_img, uint32_t col, uint32_t accumulate) {
     const int buf = i & 1;
     mbar_wait(bars + buf, (i >> 1) & 1);                   // slab landed (async proxy write -> async proxy read)
-    const uint32_t ah = a_base + a_img * IMG, al = ah + IMG;
-    const uint32_t bh = w_base + buf * WSLAB, bl = bh + WSLAB / 2;
+    constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint32_t ah = a_base + a_img * IMG, bh = w_base + buf * WSLAB;
+    const uint64_t dah = DESC0 | (ah >> 4), dal = dah + (IMG >> 4), dbh = DESC0 | (bh >> 4), dbl = dbh + (WSLAB / 2 >> 4);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t dah = umma_desc(ah + ks * 256, 1024), dal = umma_desc(al + ks * 256, 1024);
-      const uint64_t dbh = umma_desc(bh + ks * 256, 1024), dbl = umma_desc(bl + ks * 256, 1024);
-      umma_f16(tmem + col, dah, dbh, IDESC, accumulate);
-      umma_f16(tmem + col, dal, dbh, IDESC, 1);
-      umma_f16(tmem + col, dah, dbl, IDESC, 1);
+    for (int ks = 0; ks < 4; ++ks) {                       // 16 halves of K per step = two core matrices = 256 B
+      umma_f16(tmem + col, dah + ks * 16, dbh + ks * 16, IDESC, accumulate);
+      umma_f16(tmem + col, dal + ks * 16, dbh + ks * 16, IDESC, 1);
+      umma_f16(tmem + col, dah + ks * 16, dbl + ks * 16, IDESC, 1);
       accumulate = 1;
     }
     umma_commit(bars + 2 + buf);
@@ -192,8 +202,16 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     load_slab(2);
     load_slab(3);
   }
+  float4 hv[4];                                            // h_prev tile: its latency hides behind the phase-1 MMAs
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                            // 64 blocks of 8 rows x 16 floats, 4 per warp
+    const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+    const int r = rg * 8 + rr;
+    hv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   mbar_wait(bars + 4, 0);
   tc_fence_after();
+  PTL(2);
 
   unsigned char* y_hi = RA;                                // images 0, 1: y = block input of the inter-frame half
   unsigned char* h_hi = RA + 2 * IMG;                      // images 2, 3: h_prev, then h_new
@@ -215,13 +233,6 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * g[cg * 16 + i] + b[cg * 16 + i];
   };
   {
-    float4 hv[4];                                          // h_prev tile: in flight under the LayerNorm (the other CTA of the SM covers the rest)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {                          // 64 blocks of 8 rows x 16 floats, 4 per warp
-      const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
-      const int r = rg * 8 + rr;
-      hv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
     float v[16];
     tmem_ld16(lane_base, v);
 #pragma unroll
@@ -254,6 +265,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   __syncthreads();
   tc_fence_after();
 
+  PTL(3);
   // ---- phase 2: GRU gate pre-activations in TMEM: r [0,64) z [64,128) in [128,192) hn [192,256) ---------------
   if (tid == 0) {
     run_slab(2, 0, 0, 0);     // Wih_r * y
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   }
   mbar_wait(bars + 4, 1);
   tc_fence_after();
+  PTL(4);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {                             // two chunks of 8 units: bounded register footprint (2 CTAs / SM)
     uint32_t gr[8], gz[8], gi[8], gh[8];
@@ -301,6 +314,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   __syncthreads();
   tc_fence_after();
 
+  PTL(5);
   // ---- phase 3: acc[0,64) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena --------------
   if (tid == 0) {
     run_slab(8, 2, 0, 0);
@@ -328,6 +342,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   }
   mbar_wait(bars + 4, 0);
   tc_fence_after();
+  PTL(6);
   {
     float v[16];
     tmem_ld16(lane_base, v);
@@ -349,6 +364,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     if (r < valid)
       *reinterpret_cast<float4*>(xo + (size_t)r * C + ch * 4) = *reinterpret_cast<const float4*>(RA + r * 256 + ((ch ^ (r & 15)) << 4));
   }
+  PTL(7);
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 

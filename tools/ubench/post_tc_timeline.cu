@@ -1,0 +1,44 @@
+// Phase timeline of k_dprnn_post_tc (SM clock stamps of CTA 0) and launch time against the tile count.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DPT_TIMELINE tools/ubench/post_tc_timeline.cu -o tools/ubench/post_tc_timeline
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../dpdfnet_b200/csrc/k_dprnn_tc.cu"
+
+int main(int argc, char** argv) {
+  using namespace dpdf;
+  const int B = argc > 1 ? atoi(argv[1]) : 1024, Fp = 48;
+  init_dprnn_tc_kernels();
+  const size_t rows = (size_t)B * Fp;
+  float *hcat, *x, *out, *hstate, *w, *small;
+  IoDesc* io;
+  long long* tl;
+  cudaMalloc(&hcat, rows * 128 * 4); cudaMalloc(&x, rows * 64 * 4); cudaMalloc(&out, rows * 64 * 4);
+  cudaMalloc(&hstate, rows * 64 * 4); cudaMalloc(&w, 9 * 16384); cudaMalloc(&small, 1024 * 4);
+  cudaMalloc(&io, sizeof(IoDesc)); cudaMalloc(&tl, 16 * 8);
+  cudaMemset(hcat, 0, rows * 128 * 4); cudaMemset(x, 0, rows * 64 * 4); cudaMemset(hstate, 0, rows * 64 * 4);
+  cudaMemset(w, 0, 9 * 16384); cudaMemset(small, 0, 4096); cudaMemset(io, 0, sizeof(IoDesc)); cudaMemset(tl, 0, 128);
+  PostTcParams p{};
+  p.io = io; p.B = B; p.tl = tl;
+  PostTcBranch& b = p.br[0];
+  b.hcat = hcat; b.xin = x; b.xout = out; b.hstate = hstate; b.per_slot = (long long)Fp * 64; b.Fp = Fp;
+  b.tc_fc_w = w; b.tc_gates = w + 2 * 4096; b.tc_fc2_w = w + 8 * 4096;
+  b.fc_b = small; b.ln_g = small + 64; b.ln_b = small + 128; b.bias = small + 192; b.fc2_b = small + 448; b.ln2_g = small + 512; b.ln2_b = small + 576;
+  p.br[1] = b;
+  p.tiles0 = (int)((rows + 127) / 128);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int it = 0; it < 3; ++it) {
+    cudaEventRecord(e0);
+    k_dprnn_post_tc<<<p.tiles0, TC_NT, POST_TC_SMEM>>>(p);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("B=%d tiles=%d launch %d: %s, %.1f us\n", B, p.tiles0, it, cudaGetErrorString(err), ms * 1e3);
+  }
+  long long h[16];
+  cudaMemcpy(h, tl, 128, cudaMemcpyDeviceToHost);
+  printf("cycles: hcat staged+sync %lld | phase1 mma %lld | epilogue1 %lld | phase2 mma %lld | epilogue2 %lld | phase3 mma %lld | epilogue3+store %lld | total %lld\n",
+         h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
+  return 0;
+}
