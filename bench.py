@@ -285,7 +285,18 @@ def run_ours(args):
             tl = torch.tensor([a.elapsed_time(b_) / 25.0], device="cuda")
             if world > 1:
                 dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-            ladder.append({"streams_per_gpu": Bl, "ms_per_hop": float(tl.item()), "stream_frames_per_s": world * Bl / (float(tl.item()) * 1e-3)})
+            rec = {"streams_per_gpu": Bl, "ms_per_hop": float(tl.item()), "stream_frames_per_s": world * Bl / (float(tl.item()) * 1e-3)}
+            # lock-step hop latency at this batch: one graph launch per hop, CUDA events around each (BASELINE configs[4]:
+            # "10 ms-hop latency histogram at max concurrent streams")
+            evl = [torch.cuda.Event(enable_timing=True) for _ in range(41)]
+            evl[0].record(stream)
+            for t_ in range(40):
+                engl.step_pcm(xl[:, (t_ % 25 + 5) * hop:(t_ % 25 + 6) * hop], out=yl[:, :hop])
+                evl[t_ + 1].record(stream)
+            torch.cuda.synchronize()
+            hl = np.array([evl[i].elapsed_time(evl[i + 1]) for i in range(40)])
+            rec["hop_latency_ms"] = {"p50": float(np.percentile(hl, 50)), "p99": float(np.percentile(hl, 99)), "max": float(hl.max())}
+            ladder.append(rec)
             engl.close()
             del engl, xl, yl
         ok = [r for r in ladder if r["ms_per_hop"] < 1e3 / fps]

@@ -60,6 +60,25 @@ def enhance(audio: np.ndarray, sample_rate: int, *, model: str = DEFAULT_MODEL,
                                  attn_limit_db=attn_limit_db, progress_callback=progress_callback)
 
 
+def _batch_resample(waves: List[np.ndarray], sr_in: int, sr_out: int, device: int) -> List[np.ndarray]:
+    """All clips through the device resampler in one call (zero-extended to the longest: a polyphase FIR sees zeros
+    past the end of a clip either way, so every clip gets exactly its own ``resample_poly`` result)."""
+    if sr_in == sr_out or not waves:
+        return waves
+    import torch
+    from .resample import BatchResampler
+    n = max(w.size for w in waves)
+    if n == 0:
+        return waves
+    x = np.zeros((len(waves), n), np.float32)
+    for i, w in enumerate(waves):
+        x[i, :w.size] = w
+    rs = BatchResampler(sr_in, sr_out, max_streams=len(waves), device=device)
+    y = rs.resample(torch.from_numpy(x).to(f"cuda:{device}")).cpu().numpy()
+    rs.close()
+    return [y[i, :-(-w.size * rs.up // rs.down)].copy() for i, w in enumerate(waves)]
+
+
 def fit_to(y: np.ndarray, n: int) -> np.ndarray:
     return y[:n] if y.size >= n else np.pad(y, (0, n - y.size))
 
@@ -80,11 +99,12 @@ def enhance_batch(clips: Sequence[np.ndarray], sample_rate: int, *, model: str =
     from .offline import enhance_offline_exact_ragged
     from .onnx_backend import create_session
     resolved = resolve_model(model=model, onnx_path=onnx_path)
-    waves = [ensure_sample_rate(to_mono(np.asarray(c, dtype=np.float32)), int(sample_rate), resolved.info.sample_rate) for c in clips]
-    if not waves:
+    if not len(clips):
         return []
     if engine is None:
-        engine = create_session(resolved.onnx_path, max_streams=len(waves)).engine
+        engine = create_session(resolved.onnx_path, max_streams=len(clips)).engine
+    model_sr = resolved.info.sample_rate
+    waves = _batch_resample([to_mono(np.asarray(c, dtype=np.float32)) for c in clips], int(sample_rate), model_sr, engine.device)
     if not exact_offline:
         raise NotImplementedError("only the offline-exact schedule is implemented for batches")
     if attn_limit_db is not None and attn_limit_db < 0:
@@ -102,6 +122,6 @@ def enhance_batch(clips: Sequence[np.ndarray], sample_rate: int, *, model: str =
             if attn_limit_db is not None:
                 alpha = np.float32(10.0 ** (-float(attn_limit_db) / 20.0))
                 y[:e.size] = alpha * w[:e.size] + (np.float32(1.0) - alpha) * y[:e.size]
-        y = ensure_sample_rate(y, resolved.info.sample_rate, int(sample_rate))
-        res.append(np.ascontiguousarray(fit_to(y, np.asarray(clips[i]).shape[0]), dtype=np.float32))
-    return res
+        res.append(y)
+    res = _batch_resample(res, model_sr, int(sample_rate), engine.device)
+    return [np.ascontiguousarray(fit_to(y, np.asarray(clips[i]).shape[0]), dtype=np.float32) for i, y in enumerate(res)]

@@ -26,8 +26,15 @@ static int fail(int code, const char* fmt, ...) {
       return fail(DPDF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
   } while (0)
 
+namespace dpdf {
+int set_error(int code, const char* msg) {      // for the other translation units behind the same ABI
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+}  // namespace dpdf
+
 extern "C" const char* dpdf_last_error(void) { return g_err; }
-extern "C" const char* dpdf_version(void) { return "dpdfnet_b200 0.1 (sm_100a, fp32 FFMA2)"; }
+extern "C" const char* dpdf_version(void) { return "dpdfnet_b200 0.2 (sm_100a, tcgen05 FP16-split + FFMA2)"; }
 
 // ---------------------------------------------------------------------------------------------
 // weight blob

@@ -189,6 +189,7 @@ struct Engine {
   std::vector<std::string> tnames;
 };
 
+int set_error(int code, const char* msg);   // thread-local message behind dpdf_last_error()
 void init_frontend_kernels();
 void init_conv_kernels();
 void init_dprnn_kernels();

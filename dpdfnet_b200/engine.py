@@ -57,6 +57,14 @@ C_API = {
     "dpdf_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int32]),
     "dpdf_time_kernels": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
+    "dpdf_resampler_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                             ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    "dpdf_resampler_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "dpdf_resampler_reset": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dpdf_resampler_pending": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32]),
+    "dpdf_resampler_process": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                              ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64),
+                                              ctypes.c_void_p]),
     "dpdf_last_error": (ctypes.c_char_p, []),
     "dpdf_version": (ctypes.c_char_p, []),
 }

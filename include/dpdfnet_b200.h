@@ -123,11 +123,28 @@ int dpdf_debug_tensor(dpdf_engine* e, const char* name, float* out_host, size_t 
                       size_t* numel_per_stream);    /* stage output of the last step, [B, numel] */
 int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the last step */
 /* Options (all default to the measured-best choice): "graph" 0/1 one CUDA graph per hop; "lanes" 0 = auto, 1..8
- * kernel-chain lanes per batched step; "intra_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch size (>= "intra_tc_min");
- * "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel. */
+ * kernel-chain lanes per batched step; "free_lanes" 0/1 lanes of a multi-hop run replay their own graphs on their own
+ * streams; "intra_tc" / "sep_tc" / "gru_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch size; "post_tc" 0/1; "intra_bt"
+ * 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel. */
 int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value);
 int dpdf_time_kernels(dpdf_engine* e, int32_t B, int32_t iters, float* ms_out, const char** names_out,
                       int32_t max_entries, int32_t* n_entries); /* per-kernel CUDA-event timing */
+/* ---- batched streaming resampler (device) ----------------------------------------------------------------
+ * Replaces the per-chunk host resampling around the path (reference: audio.py:20-27 ensure_sample_rate ->
+ * librosa.resample, called by stream.py:112,163-164 and api.py:86,110) for B streams in lock step:
+ *     y[m] = sum_j x[j] * taps[ntaps/2 + m*down - j*up]
+ * (the arithmetic of scipy.signal.resample_poly; the zero-phase FIR `taps`, odd length, is designed by the caller,
+ * dpdfnet_b200/resample.py).  State per stream: the last few input samples, so chunked output == one-shot output.
+ * `n_out` (host) receives the samples written per row; dpdf_resampler_pending() tells it in advance. */
+typedef struct dpdf_resampler dpdf_resampler;
+int dpdf_resampler_create(int32_t up, int32_t down, const float* taps_host, int32_t ntaps, int32_t max_streams,
+                          int32_t device, dpdf_resampler** out);
+int dpdf_resampler_destroy(dpdf_resampler* r);
+int dpdf_resampler_reset(dpdf_resampler* r, void* cuda_stream);
+int64_t dpdf_resampler_pending(const dpdf_resampler* r, int32_t n_new, int32_t flush);
+int dpdf_resampler_process(dpdf_resampler* r, const float* in_dev, int64_t in_stride, int32_t n_new, float* out_dev,
+                           int64_t out_stride, int32_t B, int32_t flush, int64_t* n_out, void* cuda_stream);
+
 const char* dpdf_last_error(void);
 const char* dpdf_version(void);
 

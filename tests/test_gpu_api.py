@@ -120,3 +120,20 @@ def test_enhance_batch_ragged_clips_match_offline_golden(random_weights, golden_
     assert np.abs(lim[1] - (alpha * clips[1] + (1 - alpha) * out[1])).max() < 1e-6
     with pytest.raises(ValueError):
         dpdfnet_b200.enhance_batch(clips[:1], 16000, model="dpdfnet2", attn_limit_db=-1.0)
+
+
+def test_enhance_batch_resamples_on_the_device(random_weights):
+    """48 kHz clips through a 16 kHz model: device polyphase resampling in and out equals the host helper
+    (scipy.signal.resample_poly) around the same engine run."""
+    import dpdfnet_b200
+    from dpdfnet_b200.audio import ensure_sample_rate
+    rng = np.random.default_rng(5)
+    clips = [(rng.standard_normal(n) * 0.1).astype(np.float32) for n in (24000, 15011)]
+    got = dpdfnet_b200.enhance_batch(clips, 48000, model="dpdfnet2")
+    assert [g.shape for g in got] == [c.shape for c in clips]
+    down = [ensure_sample_rate(c, 48000, 16000) for c in clips]
+    mid = dpdfnet_b200.enhance_batch(down, 16000, model="dpdfnet2")
+    for g, m, c in zip(got, mid, clips):
+        ref = ensure_sample_rate(m, 16000, 48000)
+        n = min(ref.size, c.size)
+        assert np.abs(g[:n] - ref[:n]).max() < 1e-4

@@ -41,6 +41,25 @@ for l in sys.stdin:
         print(l, end='')
 " | tee -a $OUT/${TAG}_configs.log
       done ;;
+    resample)  # device resampler throughput (HBM-bound: 4 B in + 4*up/down B out per input sample)
+      timeout 300 python - <<'PYEOF' 2>&1 | tee $OUT/${TAG}_resample.log
+import torch, time
+from dpdfnet_b200.resample import BatchResampler
+for sr_in, sr_out in ((48000, 16000), (16000, 48000), (44100, 16000)):
+    B, n = 2048, 48000
+    rs = BatchResampler(sr_in, sr_out, B)
+    x = torch.randn(B, n, device="cuda")
+    for _ in range(3): rs.resample(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): y = rs.resample(x)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gb = (x.numel() + y.numel()) * 4 / 1e9
+    print(f"{sr_in}->{sr_out}: {B} streams x {n} samples in {ms:.3f} ms = {B * n / ms / 1e6:.1f} G input samples/s, {gb / ms * 1e3:.0f} GB/s of algorithmic traffic")
+PYEOF
+      ;;
     smoke)
       timeout 300 python __graft_entry__.py --smoke > $OUT/${TAG}_smoke.log 2>&1; tail -2 $OUT/${TAG}_smoke.log ;;
     bench)
