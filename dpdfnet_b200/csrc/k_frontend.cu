@@ -24,15 +24,21 @@ struct AnaParams {
   int B;
 };
 
-__global__ void __launch_bounds__(512) k_analysis(AnaParams p) {
+// The DFT sum over the win samples is split over `ksplit` thread groups (group g = n range [g win / ksplit, ...)):
+// the per-thread chain of win dependent load + FFMA2 rounds is what bounds this kernel at every batch size, and
+// the partial spectra are added through shared memory in a fixed order (g = 0 first).
+__global__ void __launch_bounds__(1024) k_analysis(AnaParams p, int ksplit) {
   extern __shared__ __align__(16) float smem[];
   const int win = p.d.win, hop = p.d.hop, F = p.d.F;
   float2* xs2 = reinterpret_cast<float2*>(smem);                 // [win][ABT] {x,x}
   float* pws = smem + 2 * win * ABT;                              // [ABT][F]
+  float2* part = reinterpret_cast<float2*>(pws + ABT * F);        // [ksplit - 1][ABT][F] partial spectra of groups 1..
   const IoDesc* io = p.io;
   const int b0 = blockIdx.x * ABT;
   const int nb = min(ABT, p.B - b0);
-  const int tid = threadIdx.x, NT = blockDim.x;
+  const int NT = blockDim.x, NTg = NT / ksplit;
+  const int grp = threadIdx.x / NTg;
+  const int tid = threadIdx.x;
   const bool pcm_mode = io->mode == 0;
 
   __shared__ int s_slot[ABT], s_flag[ABT], s_pos[ABT];
@@ -64,10 +70,12 @@ __global__ void __launch_bounds__(512) k_analysis(AnaParams p) {
       int bb = i / hop, n = i % hop;
       p.st.in_hist[(size_t)s_slot[bb] * hop + n] = xs2[(n + hop) * ABT + bb].x;
     }
-    if (tid < F) {
+    const int kb = tid - grp * NTg;                               // bin of this thread inside its group
+    if (kb < F) {
       // the (cos, sin) basis streams from L2 (412 KB at 16 kHz, larger than L1): keep 16 loads in flight
-      const float2* basis = reinterpret_cast<const float2*>(p.dft_fwd) + tid;
-      for (int n0 = 0; n0 < win; n0 += 16) {
+      const float2* basis = reinterpret_cast<const float2*>(p.dft_fwd) + kb;
+      const int nper = win / ksplit;
+      for (int n0 = grp * nper; n0 < (grp + 1) * nper; n0 += 16) {
         float2 cs[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) cs[u] = __ldg(basis + (size_t)(n0 + u) * F);
@@ -81,6 +89,21 @@ __global__ void __launch_bounds__(512) k_analysis(AnaParams p) {
             X[2 * q + 1] = ffma2(cs[u], hi2(xx), X[2 * q + 1]);
           }
         }
+      }
+      if (grp > 0) {
+#pragma unroll
+        for (int bb = 0; bb < ABT; ++bb) part[((grp - 1) * ABT + bb) * F + kb] = X[bb];
+      }
+    }
+    if (ksplit > 1) {
+      __syncthreads();
+      if (tid < F) {
+        for (int g = 1; g < ksplit; ++g)
+#pragma unroll
+          for (int bb = 0; bb < ABT; ++bb) {
+            const float2 v = part[((g - 1) * ABT + bb) * F + tid];
+            X[bb].x += v.x; X[bb].y += v.y;
+          }
       }
     }
   } else if (tid < F) {
@@ -303,9 +326,12 @@ void launch_reset(Engine& e, const int* slots_dev, int n, cudaStream_t st) {
 
 void launch_analysis(Engine& e, int B, cudaStream_t st) {
   AnaParams p{e.io_dev, e.d, e.st, e.w.dft_fwd, e.w.band_inv_w, e.w.band_start, B};
-  const int nt = (e.d.F + 31) / 32 * 32;
-  const size_t smem = (size_t)(2 * e.d.win * ABT + ABT * e.d.F) * sizeof(float);
-  k_analysis<<<(B + ABT - 1) / ABT, nt, smem, st>>>(p);
+  const int ntg = (e.d.F + 31) / 32 * 32;
+  // latency bound below ~2 CTAs per SM (split the sum: 5 groups at 16 kHz, 2 at 48 kHz), throughput bound above
+  int ksplit = (B + ABT - 1) / ABT <= 2 * e.num_sms ? 1024 / ntg : 1;
+  while (ksplit > 1 && ((e.d.win / 16) % ksplit != 0)) --ksplit; // every group walks whole 16-sample rounds
+  const size_t smem = (size_t)(2 * e.d.win * ABT + ABT * e.d.F + 2 * (ksplit - 1) * ABT * e.d.F) * sizeof(float);
+  k_analysis<<<(B + ABT - 1) / ABT, ntg * ksplit, smem, st>>>(p, ksplit);
 }
 
 void launch_synthesis(Engine& e, int B, cudaStream_t st) {
@@ -316,7 +342,7 @@ void launch_synthesis(Engine& e, int B, cudaStream_t st) {
 }
 
 void init_frontend_kernels() {
-  cudaFuncSetAttribute(k_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
 }  // namespace dpdf
