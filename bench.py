@@ -299,12 +299,15 @@ def run_ours(args):
             ladder.append(rec)
             engl.close()
             del engl, xl, yl
-        ok = [r for r in ladder if r["ms_per_hop"] < 1e3 / fps]
+        # a batch is sustained in real time when even its p99 lock-step hop latency stays inside the hop period
+        ok = [r for r in ladder if max(r["ms_per_hop"], r["hop_latency_ms"]["p99"]) < 1e3 / fps]
         best = max(ok, key=lambda r: r["streams_per_gpu"]) if ok else None
         sustained = {"ladder": ladder, "hop_budget_ms": 1e3 / fps,
                      "realtime_streams_per_gpu": best["streams_per_gpu"] if best else None,
                      "realtime_streams_total": world * best["streams_per_gpu"] if best else None,
-                     "ms_per_hop_at_that_batch": best["ms_per_hop"] if best else None}
+                     "ms_per_hop_at_that_batch": best["ms_per_hop"] if best else None,
+                     "p99_hop_latency_ms_at_that_batch": best["hop_latency_ms"]["p99"] if best else None,
+                     "criterion": "largest ladder batch whose mean AND p99 lock-step hop latency are below the hop period"}
         eng = Engine(spec, ck, max_streams=B, device=local)
 
     if rank != 0:
@@ -399,7 +402,7 @@ def main():
     ap.add_argument("--cpu-hops", type=int, default=60)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-ladder", action="store_true", help="skip the sustained-streams batch ladder")
-    ap.add_argument("--ladder", type=int, nargs="*", default=[4096, 8192, 12288, 16384, 20480])
+    ap.add_argument("--ladder", type=int, nargs="*", default=[4096, 8192, 12288, 16384, 18432, 20480])
     ap.add_argument("--intra-bt", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=-1, help="kernel-chain lanes per step (-1: engine default)")
     ap.add_argument("--profile-only", action="store_true", help="device steps only (for ncu runs)")
