@@ -38,11 +38,14 @@ def _oracle(name, seed, B):
     return OracleEngine(spec, pack_tensors(spec, random_checkpoint(spec, seed)), B)
 
 
+@pytest.mark.parametrize("tc", [0, 1])
 @pytest.mark.parametrize("name", ["dpdfnet2", "dpdfnet4", "dpdfnet2_48khz_hr"])
-def test_stream_golden(torch_cuda, golden_dir, name):
-    """Per-frame ONNX-shaped call with HOST buffers vs the reference streaming model's outputs."""
+def test_stream_golden(torch_cuda, golden_dir, name, tc):
+    """Per-frame ONNX-shaped call with HOST buffers vs the reference streaming model's outputs (both kernel arms)."""
     g = np.load(golden_dir / f"stream_{name}.npz")
     eng = _engine(name, int(g["seed"]), 2)
+    for opt in ("intra_tc", "post_tc", "sep_tc", "gru_tc"):
+        eng.set_option(opt, tc)
     for t in range(g["spec_in"].shape[0]):
         y = eng.step_spec_host(g["spec_in"][t][None], slot_ids=[1])
         assert np.isfinite(y).all()
@@ -55,12 +58,17 @@ def test_stream_golden(torch_cuda, golden_dir, name):
     assert np.count_nonzero(init[eng.spec.fe_feat + 96:]) == 0
 
 
+@pytest.mark.parametrize("tc", [0, 1])
 @pytest.mark.parametrize("name", ["dpdfnet2", "dpdfnet4", "dpdfnet2_48khz_hr"])
-def test_offline_golden(torch_cuda, golden_dir, name):
-    """BASELINE configs[0]-style check: whole clip vs model/dpdfnet.py output, 1e-4 max-abs."""
+def test_offline_golden(torch_cuda, golden_dir, name, tc):
+    """BASELINE configs[0]-style check: whole clip vs model/dpdfnet.py output, 1e-4 max-abs -- on the small-batch
+    FFMA2 kernels (tc=0) and with every tensor-core kernel forced on (tc=1: the WARMUP / ZERO_FEAT / ZERO_SPEC
+    schedule flags go through the tcgen05 intra-GRU, post, separable-conv and GRU(256) kernels)."""
     from dpdfnet_b200.offline import enhance_offline_exact
     g = np.load(golden_dir / f"offline_{name}.npz")
     eng = _engine(name, int(g["seed"]), g["wave_in"].shape[0])
+    for opt in ("intra_tc", "post_tc", "sep_tc", "gru_tc"):
+        eng.set_option(opt, tc)
     out = enhance_offline_exact(eng, g["wave_in"])
     assert out.shape == g["wave_out"].shape
     assert np.abs(out - g["wave_out"]).max() < WAVE_TOL
