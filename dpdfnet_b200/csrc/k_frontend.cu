@@ -7,6 +7,8 @@
 // synthesis: ERB / per-bin mask on the 2-frame-delayed spectrum, 5-tap complex deep filter with
 //            2-frame-delayed coefficients, inverse real DFT x window, overlap-add.
 //            reference: layers.py:414-445, onnx_model/multiframe.py:140-154,200-232, stream.py:138-156
+#include <algorithm>
+
 #include "engine.h"
 
 namespace dpdf {
@@ -328,7 +330,7 @@ void launch_analysis(Engine& e, int B, cudaStream_t st) {
   AnaParams p{e.io_dev, e.d, e.st, e.w.dft_fwd, e.w.band_inv_w, e.w.band_start, B};
   const int ntg = (e.d.F + 31) / 32 * 32;
   // latency bound below ~2 CTAs per SM (split the sum: 5 groups at 16 kHz, 2 at 48 kHz), throughput bound above
-  int ksplit = (B + ABT - 1) / ABT <= 2 * e.num_sms ? 1024 / ntg : 1;
+  int ksplit = (std::max(B, e.total_B) + ABT - 1) / ABT <= 2 * e.num_sms ? 1024 / ntg : 1;   // total_B: all lanes of the step
   while (ksplit > 1 && ((e.d.win / 16) % ksplit != 0)) --ksplit; // every group walks whole 16-sample rounds
   const size_t smem = (size_t)(2 * e.d.win * ABT + ABT * e.d.F + 2 * (ksplit - 1) * ABT * e.d.F) * sizeof(float);
   k_analysis<<<(B + ABT - 1) / ABT, ntg * ksplit, smem, st>>>(p, ksplit);
