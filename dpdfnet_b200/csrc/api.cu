@@ -283,6 +283,10 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
       cudaMalloc(&e.flags_dev, max_streams * sizeof(int)) != cudaSuccess)
     return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(io) failed"));
   e.io_dev = e.io_lanes;
+  e.progress_tiles = (max_streams + 127) / 128 + 1;
+  if (cudaMalloc(&e.progress_dev, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int)) != cudaSuccess)
+    return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(progress) failed"));
+  cudaMemset(e.progress_dev, 0, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int));
   if (cudaStreamCreateWithFlags(&e.own_stream, cudaStreamDefault) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "stream creation failed"));
   for (int l = 0; l < Engine::MAX_LANES; ++l)
     if (cudaStreamCreateWithFlags(&e.lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
@@ -317,7 +321,7 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
     if (e.lane_done[l]) cudaEventDestroy(e.lane_done[l]);
   }
   if (e.lane_fork) cudaEventDestroy(e.lane_fork);
-  cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_lanes);
+  cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_lanes); cudaFree(e.progress_dev);
   cudaFree(e.slots_dev); cudaFree(e.flags_dev); cudaFree(e.stage_in); cudaFree(e.stage_out);
   if (e.pinned) cudaFreeHost(e.pinned);
   if (e.own_stream) cudaStreamDestroy(e.own_stream);
@@ -385,8 +389,10 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     pr[0] = sepp(w.erb_conv[2], c.e2, nullptr, 0, c.e3, d.fe[2], d.fe[3], d.stride[2], 1);
     RUN("sepconv", sepconv(e, pr, 1, B, st)); ++n;
   }
+  const bool intra_on_tc = e.intra_tc == 1 || (e.intra_tc == 2 && std::max(B, e.total_B) >= e.intra_tc_min);
+  e.overlap_now = e.overlap_now && intra_on_tc && !e.timing;        // requested by the caller (enqueue_lanes / run_hops_free)
   for (int i = 0; i < d.N; ++i) {
-    if (e.intra_tc == 1 || (e.intra_tc == 2 && std::max(B, e.total_B) >= e.intra_tc_min)) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
+    if (intra_on_tc) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
     else { RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); }
     ++n;
     if (e.post_tc) { RUN("dprnn_post", launch_dprnn_post_tc(e, i, B, st)); }
@@ -479,7 +485,14 @@ static void drop_graphs(Engine& e) {
 
 // Number of lanes of a step over B streams: explicit option, else enough streams per lane to keep the tensor-core
 // kernels' 128-stream tiles full.
+// The overlapped post kernel and lanes exclude each other: post CTAs waiting for their sweep would
+// hold the SMs another lane's sweep needs.  Measured (profiles/r01O_lanes.log): one chain + overlap wins below 4096
+// streams, eight free-running lanes without overlap above.
+static bool overlap_applies(const Engine& e, int B) {
+  return e.overlap && e.post_tc && (e.intra_tc == 1 || (e.intra_tc == 2 && B >= e.intra_tc_min)) && B < e.overlap_max && e.lanes <= 1;
+}
 static int lanes_for(const Engine& e, int B) {
+  if (overlap_applies(e, B)) return 1;
   int L = e.lanes > 0 ? e.lanes : (B >= 2048 ? 8 : (B >= 1024 ? 4 : 1));   // measured: profiles/r01B_lanes.log
   L = std::min(L, Engine::MAX_LANES);
   while (L > 1 && B / L < 128) --L;
@@ -498,6 +511,7 @@ static void enqueue_lanes(Engine& e, int B, cudaStream_t st, bool fork) {
   std::vector<float*> base(e.sc_items.size());
   for (size_t i = 0; i < base.size(); ++i) base[i] = *e.sc_items[i].first;
   e.total_B = B;
+  e.overlap_now = L == 1 && overlap_applies(e, B);
   int launches = 0;
   if (fork && L > 1) cudaEventRecord(e.lane_fork, st);
   for (int l = 0; l < L; ++l) {
@@ -506,6 +520,7 @@ static void enqueue_lanes(Engine& e, int B, cudaStream_t st, bool fork) {
     if (n <= 0) continue;
     for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i] + (size_t)r0 * e.sc_items[i].second;
     e.io_dev = e.io_lanes + l;
+    e.cur_lane = l;
     cudaStream_t ls = (fork && l > 0) ? e.lane_stream[l] : st;
     if (fork && l > 0) cudaStreamWaitEvent(ls, e.lane_fork, 0);
     enqueue_step(e, n, ls);
@@ -518,6 +533,7 @@ static void enqueue_lanes(Engine& e, int B, cudaStream_t st, bool fork) {
   for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i];
   e.io_dev = e.io_lanes;
   e.total_B = 0;
+  e.overlap_now = false;
   e.launches = launches;
 }
 
@@ -566,6 +582,7 @@ static int run_hops_free(Engine& e, int B, int T, cudaStream_t st) {
     if (it == e.lane_graphs.end()) {
       for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i] + (size_t)r0 * e.sc_items[i].second;
       e.io_dev = e.io_lanes + l;
+      e.cur_lane = l;
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(e.own_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { rc = fail(DPDF_ERR_CUDA, "graph capture failed"); break; }
       enqueue_step(e, n, e.own_stream);
@@ -953,6 +970,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "sep_tc") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "sep_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
     e.sep_tc = value;
+    drop_graphs(e);
+  } else if (strcmp(key, "overlap") == 0 || strcmp(key, "overlap_max") == 0) {
+    if (key[7] == 0) e.overlap = value ? 1 : 0;
+    else e.overlap_max = value;
     drop_graphs(e);
   } else if (strcmp(key, "free_lanes") == 0) {
     e.free_lanes = value ? 1 : 0;

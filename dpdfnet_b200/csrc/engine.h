@@ -182,6 +182,13 @@ struct Engine {
   std::map<int, cudaGraphExec_t> graphs;     // keyed by B: one hop of all lanes (forked chains, joined)
   std::map<int, cudaGraphExec_t> lane_graphs; // keyed by B * MAX_LANES + lane: one hop of one lane (free-running lanes of a multi-hop run)
   int launches_per_lane = 0;
+  // post kernel overlapped with the intra sweep: per-lane progress counters [lane][2][2][tiles]
+  int overlap = 1;                // option: 0 off, 1 on whenever both DPRNN kernels run on tcgen05, lanes are not forced and
+  int overlap_max = 4097;         //         the step has fewer than overlap_max streams
+  bool overlap_now = false;       // decided per enqueue_step
+  int cur_lane = 0;
+  int* progress_dev = nullptr;
+  int progress_tiles = 0;
   int free_lanes = 1;             // multi-hop runs: every lane replays its own graph on its own stream, joined once at the end
   std::vector<std::pair<std::string, float>> ktimes;
   bool timing = false;

@@ -88,6 +88,7 @@ struct IntraTcParams {
   const float* bias[2];   // [2][4][64], exponent scales folded in (weights.py: tc.intra_bias)
   int tiles;              // ceil(B / 128)
   int B;
+  int* progress;          // [2 branches][2 dirs][tiles] completed steps of each CTA, or nullptr (overlapped post kernel)
 #ifdef ITC_TIMELINE
   long long* tl;          // [steps][12] SM-clock stamps of CTA 0 (tools/ubench/intra_tc_timeline.cu)
 #endif
@@ -135,7 +136,13 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid < 256) sb[tid] = __ldg((br ? p.bias[1] : p.bias[0]) + dir * 4 * C + tid);
   for (int i = tid; i < ST_BUF / 16; i += ITC_NT) reinterpret_cast<uint4*>(Ssm + ST_BUF)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0 (read back as h_prev of step 0)
+  int* my_progress = p.progress ? p.progress + (br * 2 + dir) * p.tiles + tile : nullptr;
+  if (my_progress && tid == 0) {
+    *reinterpret_cast<volatile int*>(my_progress) = 0;       // visible before any consumer CTA of the dependent launch starts
+    __threadfence();
+  }
   __syncthreads();                                           // barriers initialised
+  if (my_progress) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // every CTA of this grid is resident or done
   if (tid == 0) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(br ? p.wimg[1] : p.wimg[0]) + (size_t)dir * 4 * W_IMG;
     mbar_expect_tx(bars, 4 * W_IMG);
@@ -263,6 +270,12 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
         if (t + 2 < T) x_mma(t + 2);
 #endif
         TL(7);
+        if (my_progress) {
+          // every gate warp issued the write-out of h_{t-1} before it handed over slice 1 of step t (named barriers are
+          // CTA-scope synchronisation; the fence below makes those stores visible device-wide before the count)
+          __threadfence();
+          *reinterpret_cast<volatile int*>(my_progress) = t;
+        }
       }
       __syncwarp();
     }
@@ -415,6 +428,11 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
         *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
     }
   }
+  if (my_progress) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile int*>(my_progress) = T;
+  }
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
@@ -430,6 +448,7 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.wimg[1] = e.w.dprnn_erb[blk].tc_intra; p.bias[1] = e.w.dprnn_erb[blk].tc_intra_bias;
   p.B = B;
   p.tiles = (B + 127) / 128;
+  p.progress = e.overlap_now ? e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles : nullptr;
   k_dprnn_intra_tc<<<4 * p.tiles, ITC_NT, INTRA_TC_SMEM, st>>>(p);
 }
 

@@ -51,6 +51,10 @@ struct PostTcParams {
   const IoDesc* io;
   PostTcBranch br[2];
   int tiles0, B;
+  // overlapped mode: tile = (position f, 128-stream tile), erb tiles first, positions middle-out (the
+  // order in which both sweep directions complete them); the CTA waits for the two intra CTAs it depends on
+  const int* progress;    // [2 branches][2 dirs][stiles] completed steps, nullptr = row-major tiles of a finished sweep
+  int stiles;             // ceil(B / 128)
 #ifdef PT_TIMELINE
   long long* tl;          // [16] SM-clock stamps of CTA 0 (tools/ubench/post_tc_timeline.cu)
 #endif
@@ -88,18 +92,40 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
-  const int bi = (int)blockIdx.x >= p.tiles0 ? 1 : 0;
+  int bi, valid, fpos = 0;
+  long long rbase, rstride;
+  if (p.progress) {
+    const int tiles_e = p.br[1].Fp * p.stiles;
+    bi = (int)blockIdx.x < tiles_e ? 1 : 0;
+    const int local = (int)blockIdx.x - (bi ? 0 : tiles_e);
+    const int k = local / p.stiles, stile = local % p.stiles, T = p.br[bi].Fp;
+    fpos = (T - 1) / 2 + ((k & 1) ? (k + 1) / 2 : -(k / 2));
+    rbase = (long long)stile * 128 * T + fpos;
+    rstride = T;
+    valid = min(128, p.B - stile * 128);
+    if (tid == 0) {
+      const volatile int* fw = p.progress + (bi * 2 + 0) * p.stiles + stile;   // branch index as in the intra kernel: 0 = df, 1 = erb
+      const volatile int* bw = p.progress + (bi * 2 + 1) * p.stiles + stile;
+      // the forward CTA has finished position f after f + 1 steps, the backward one after T - f; bounded wait (~2 s):
+      // a broken producer must show up as a failed parity test, not as a hung GPU
+      for (long long spin = 0; (*fw < fpos + 1 || *bw < T - fpos) && spin < (1ll << 23); ++spin) __nanosleep(256);
+      __threadfence();                                     // acquire: the rows those counts cover are visible (loads below bypass L1)
+    }
+  } else {
+    bi = (int)blockIdx.x >= p.tiles0 ? 1 : 0;
+    rbase = (long long)(blockIdx.x - (bi ? p.tiles0 : 0)) * 128;
+    rstride = 1;
+    valid = (int)min((long long)128, (long long)p.B * p.br[bi].Fp - rbase);
+  }
   const PostTcBranch& q = p.br[bi];
-  const long long row0 = (long long)(blockIdx.x - (bi ? p.tiles0 : 0)) * 128;
-  const long long nrows = (long long)p.B * q.Fp;
-  const int valid = (int)min((long long)128, nrows - row0);
 
   if (tid < 128) {
     long long off = 0;
     int commit = 0;
     if (tid < valid) {
-      const long long r = row0 + tid;
-      const int b = (int)(r / q.Fp), f = (int)(r % q.Fp);
+      int b, f;
+      if (p.progress) { b = (int)(rbase / q.Fp) + tid; f = fpos; }
+      else { const long long r = rbase + tid; b = (int)(r / q.Fp); f = (int)(r % q.Fp); }
       off = (long long)io_slot(p.io, b) * q.per_slot + (long long)f * C;
       commit = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) ? 0 : 1;
     }
@@ -141,13 +167,13 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   const int rr = lane >> 2, cc = lane & 3;
   const int sub_off = (cc >> 1) * 128 + rr * 16 + (cc & 1) * 8;      // inside a [8 rows][16 k] block of an image
   {
-    const float* hc = q.hcat + row0 * 2 * C;
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {                          // 128 blocks of 8 rows x 16 floats, 8 per warp, all in flight
       const int blk = warp + 16 * i, rg = blk >> 3, kb = blk & 7;
       const int r = rg * 8 + rr;
-      v[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(hc + (size_t)r * 2 * C + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = r < valid ? __ldcg(reinterpret_cast<const float4*>(q.hcat + (rbase + r * rstride) * 2 * C + kb * 16 + cc * 4))   // L2: written by a concurrent kernel
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -163,7 +189,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   // prefetch what the first epilogue needs while the tensor core works: the residual input
   float4 xv[4];
   {
-    const float* xr = q.xin + (size_t)(row0 + row) * C + cg * 16;
+    const float* xr = q.xin + (rbase + row * rstride) * C + cg * 16;
 #pragma unroll
     for (int c = 0; c < 4; ++c) xv[c] = row < valid ? __ldg(reinterpret_cast<const float4*>(xr + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -357,12 +383,11 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  float* xo = q.xout + row0 * C;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {                             // coalesced write-out of the block output: two rows per warp instruction
     const int r = (tid >> 4) + 32 * i, ch = tid & 15;
     if (r < valid)
-      *reinterpret_cast<float4*>(xo + (size_t)r * C + ch * 4) = *reinterpret_cast<const float4*>(RA + r * 256 + ((ch ^ (r & 15)) << 4));
+      *reinterpret_cast<float4*>(q.xout + (rbase + r * rstride) * C + ch * 4) = *reinterpret_cast<const float4*>(RA + r * 256 + ((ch ^ (r & 15)) << 4));
   }
   PTL(7);
   if (warp == 0) tmem_dealloc<256>(tmem);
@@ -384,7 +409,26 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   fill(p.br[1], e.w.dprnn_erb[blk], e.sc.hcat_e, blk == 0 ? e.sc.e3 : e.sc.xe, e.sc.xe, e.st.inter_erb, e.d.fe[3]);
   p.tiles0 = (int)(((long long)B * (NDF / 2) + 127) / 128);
   const int tiles1 = (int)(((long long)B * e.d.fe[3] + 127) / 128);
-  k_dprnn_post_tc<<<p.tiles0 + tiles1, TC_NT, POST_TC_SMEM, st>>>(p);
+  if (!e.overlap_now) {
+    k_dprnn_post_tc<<<p.tiles0 + tiles1, TC_NT, POST_TC_SMEM, st>>>(p);
+    return;
+  }
+  // Overlapped with the sweep that feeds it: launched as a programmatic dependent of the intra kernel (it may start as
+  // soon as every intra CTA has started, i.e. none of them can be starved of an SM by a waiting post CTA) and
+  // synchronised with it through the per-CTA progress counters only.
+  p.progress = e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles;
+  p.stiles = (B + 127) / 128;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(p.stiles * (NDF / 2 + e.d.fe[3])));
+  cfg.blockDim = dim3(TC_NT);
+  cfg.dynamicSmemBytes = POST_TC_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_dprnn_post_tc, p);
 }
 
 void init_dprnn_tc_kernels() {

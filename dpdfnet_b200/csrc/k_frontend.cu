@@ -29,7 +29,8 @@ struct AnaParams {
 // The DFT sum over the win samples is split over `ksplit` thread groups (group g = n range [g win / ksplit, ...)):
 // the per-thread chain of win dependent load + FFMA2 rounds is what bounds this kernel at every batch size, and
 // the partial spectra are added through shared memory in a fixed order (g = 0 first).
-__global__ void __launch_bounds__(1024) k_analysis(AnaParams p, int ksplit) {
+template <int MAXT>      // 512: one group (full register budget for the 16-deep basis prefetch), 1024: split sum
+__global__ void __launch_bounds__(MAXT) k_analysis(AnaParams p, int ksplit) {
   extern __shared__ __align__(16) float smem[];
   const int win = p.d.win, hop = p.d.hop, F = p.d.F;
   float2* xs2 = reinterpret_cast<float2*>(smem);                 // [win][ABT] {x,x}
@@ -333,7 +334,8 @@ void launch_analysis(Engine& e, int B, cudaStream_t st) {
   int ksplit = (std::max(B, e.total_B) + ABT - 1) / ABT <= 2 * e.num_sms ? 1024 / ntg : 1;   // total_B: all lanes of the step
   while (ksplit > 1 && ((e.d.win / 16) % ksplit != 0)) --ksplit; // every group walks whole 16-sample rounds
   const size_t smem = (size_t)(2 * e.d.win * ABT + ABT * e.d.F + 2 * (ksplit - 1) * ABT * e.d.F) * sizeof(float);
-  k_analysis<<<(B + ABT - 1) / ABT, ntg * ksplit, smem, st>>>(p, ksplit);
+  if (ksplit > 1) k_analysis<1024><<<(B + ABT - 1) / ABT, ntg * ksplit, smem, st>>>(p, ksplit);
+  else k_analysis<512><<<(B + ABT - 1) / ABT, ntg, smem, st>>>(p, 1);
 }
 
 void launch_synthesis(Engine& e, int B, cudaStream_t st) {
@@ -344,7 +346,8 @@ void launch_synthesis(Engine& e, int B, cudaStream_t st) {
 }
 
 void init_frontend_kernels() {
-  cudaFuncSetAttribute(k_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_analysis<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_analysis<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
 }  // namespace dpdf
