@@ -26,6 +26,125 @@ struct AnaParams {
   int B;
 };
 
+// Single-group form (throughput-bound grids): thread = bin over all win samples.
+__global__ void __launch_bounds__(512) k_analysis_one(AnaParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int win = p.d.win, hop = p.d.hop, F = p.d.F;
+  float2* xs2 = reinterpret_cast<float2*>(smem);                 // [win][ABT] {x,x}
+  float* pws = smem + 2 * win * ABT;                              // [ABT][F]
+  const IoDesc* io = p.io;
+  const int b0 = blockIdx.x * ABT;
+  const int nb = min(ABT, p.B - b0);
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const bool pcm_mode = io->mode == 0;
+
+  __shared__ int s_slot[ABT], s_flag[ABT], s_pos[ABT];
+  if (tid < ABT) {
+    int b = b0 + tid;
+    s_slot[tid] = b < p.B ? io_slot(io, b) : 0;
+    s_flag[tid] = b < p.B ? io_flags(io, b) : 0;
+    s_pos[tid] = b < p.B ? p.st.pos[s_slot[tid]] : 0;
+  }
+  __syncthreads();
+
+  float2 X[ABT];
+#pragma unroll
+  for (int bb = 0; bb < ABT; ++bb) X[bb] = make_float2(0.f, 0.f);
+
+  if (pcm_mode) {
+    const long long toff = (long long)io->t_in * hop;
+    for (int i = tid; i < ABT * win; i += NT) {
+      int bb = i / win, n = i % win;
+      float v = 0.f;
+      if (bb < nb) {
+        v = n < hop ? p.st.in_hist[(size_t)s_slot[bb] * hop + n]
+                    : __ldg(io->in + (size_t)(b0 + bb) * io->in_stride + toff + (n - hop));
+      }
+      xs2[n * ABT + bb] = make_float2(v, v);
+    }
+    __syncthreads();
+    for (int i = tid; i < nb * hop; i += NT) {      // history <- this hop (after all reads above)
+      int bb = i / hop, n = i % hop;
+      p.st.in_hist[(size_t)s_slot[bb] * hop + n] = xs2[(n + hop) * ABT + bb].x;
+    }
+    if (tid < F) {
+      // the (cos, sin) basis streams from L2 (412 KB at 16 kHz, larger than L1): keep 16 loads in flight
+      const float2* basis = reinterpret_cast<const float2*>(p.dft_fwd) + tid;
+      for (int n0 = 0; n0 < win; n0 += 16) {
+        float2 cs[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) cs[u] = __ldg(basis + (size_t)(n0 + u) * F);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float4* xr = reinterpret_cast<const float4*>(xs2 + (n0 + u) * ABT);
+#pragma unroll
+          for (int q = 0; q < ABT / 2; ++q) {
+            float4 xx = xr[q];
+            X[2 * q] = ffma2(cs[u], lo2(xx), X[2 * q]);
+            X[2 * q + 1] = ffma2(cs[u], hi2(xx), X[2 * q + 1]);
+          }
+        }
+      }
+    }
+  } else if (tid < F) {
+    for (int bb = 0; bb < nb; ++bb) {
+      float2 v = __ldg(reinterpret_cast<const float2*>(io->in) + (size_t)(b0 + bb) * F + tid);
+      X[bb] = make_float2(v.x * p.d.wnorm, v.y * p.d.wnorm);
+    }
+  }
+
+  const float a = 0.98f, one_m_a = 0.02f;     // float32(0.98), float32(1 - 0.98)
+  if (tid < F) {
+    const int k = tid;
+#pragma unroll
+    for (int bb = 0; bb < ABT; ++bb) {
+      if (bb >= nb) break;
+      const int slot = s_slot[bb], fl = s_flag[bb], pos = s_pos[bb];
+      if (fl & DPDF_FLAG_ZERO_SPEC_) X[bb] = make_float2(0.f, 0.f);
+      const float re = X[bb].x, im = X[bb].y;
+      reinterpret_cast<float2*>(p.st.mask_ring)[((size_t)slot * 3 + pos % 3) * F + k] = X[bb];
+      const float pw = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+      const bool kill = (fl & (DPDF_FLAG_WARMUP_ | DPDF_FLAG_ZERO_FEAT_)) != 0;
+      if (p.d.hr48) {
+        const float feat = 10.0f * log10f(sqrtf(pw) + 1e-10f);
+        float* mup = p.st.mu + (size_t)slot * p.d.fe_feat + k;
+        const float mu = __fadd_rn(__fmul_rn(a, *mup), __fmul_rn(one_m_a, feat));
+        *mup = mu;
+        p.st.erb_ring[((size_t)slot * 3 + pos % 3) * p.d.fe_feat + k] = kill ? 0.f : (feat - mu) / 40.0f;
+      } else {
+        pws[bb * F + k] = pw;
+      }
+      if (k < NDF) {
+        const float mag = sqrtf(pw);
+        float* sp = p.st.s + (size_t)slot * NDF + k;
+        const float s = __fadd_rn(__fmul_rn(a, *sp), __fmul_rn(one_m_a, mag));
+        *sp = s;
+        const float den = sqrtf(s + 1e-12f);
+        float* ring = p.st.df_ring + ((size_t)slot * 3 + pos % 3) * 2 * NDF;
+        ring[k] = kill ? 0.f : re / den;
+        ring[NDF + k] = kill ? 0.f : im / den;
+      }
+    }
+  }
+  if (!p.d.hr48) {
+    __syncthreads();
+    for (int i = tid; i < nb * 32; i += NT) {
+      const int bb = i >> 5, band = i & 31;
+      const int slot = s_slot[bb], fl = s_flag[bb], pos = s_pos[bb];
+      const int k0 = p.band_start[band], k1 = p.band_start[band + 1];
+      const float iw = p.band_inv_w[band];
+      float acc = 0.f;
+      for (int k = k0; k < k1; ++k) acc = __fadd_rn(acc, __fmul_rn(pws[bb * F + k], iw));
+      const float feat = 10.0f * log10f(acc + 1e-10f);
+      float* mup = p.st.mu + (size_t)slot * 32 + band;
+      const float mu = __fadd_rn(__fmul_rn(a, *mup), __fmul_rn(one_m_a, feat));
+      *mup = mu;
+      const bool kill = (fl & (DPDF_FLAG_WARMUP_ | DPDF_FLAG_ZERO_FEAT_)) != 0;
+      p.st.erb_ring[((size_t)slot * 3 + pos % 3) * 32 + band] = kill ? 0.f : (feat - mu) / 40.0f;
+    }
+  }
+}
+
 // The DFT sum over the win samples is split over `ksplit` thread groups (group g = n range [g win / ksplit, ...)):
 // the per-thread chain of win dependent load + FFMA2 rounds is what bounds this kernel at every batch size, and
 // the partial spectra are added through shared memory in a fixed order (g = 0 first).
@@ -335,7 +454,7 @@ void launch_analysis(Engine& e, int B, cudaStream_t st) {
   while (ksplit > 1 && ((e.d.win / 16) % ksplit != 0)) --ksplit; // every group walks whole 16-sample rounds
   const size_t smem = (size_t)(2 * e.d.win * ABT + ABT * e.d.F + 2 * (ksplit - 1) * ABT * e.d.F) * sizeof(float);
   if (ksplit > 1) k_analysis<1024><<<(B + ABT - 1) / ABT, ntg * ksplit, smem, st>>>(p, ksplit);
-  else k_analysis<512><<<(B + ABT - 1) / ABT, ntg, smem, st>>>(p, 1);
+  else k_analysis_one<<<(B + ABT - 1) / ABT, ntg, smem, st>>>(p);
 }
 
 void launch_synthesis(Engine& e, int B, cudaStream_t st) {
@@ -346,7 +465,7 @@ void launch_synthesis(Engine& e, int B, cudaStream_t st) {
 }
 
 void init_frontend_kernels() {
-  cudaFuncSetAttribute(k_analysis<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_analysis_one, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_analysis<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
 }
 
