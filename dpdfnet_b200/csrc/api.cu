@@ -354,6 +354,8 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   const Weights& w = e.w;
   Scratch& c = e.sc;
   int n = 0;
+  e.pdl_now = e.pdl && !e.timing;
+  e.pdl_first = true;                                      // the analysis kernel follows a copy / an event, not a kernel
   const bool use_sep_tc = e.sep_tc == 1 || (e.sep_tc == 2 && std::max(B, e.total_B) >= e.sep_tc_min);
   auto sepconv = [&](Engine& en, const SepProblem* probs, int nprob, int Bn, cudaStream_t s_) {
     if (use_sep_tc) launch_sepconv_tc(en, probs, nprob, Bn, s_);
@@ -365,6 +367,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     else launch_gru(en, probs, nprob, Bn, s_);
   };
   RUN("analysis", launch_analysis(e, B, st)); ++n;
+  e.pdl_first = false;
   RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
   auto sepp = [&](const SepW& sw, const float* in1, const float* in2, int pidx, float* out, int Fin, int Fout, int stride, int up) {
     SepProblem q{};
@@ -462,6 +465,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   RUN("conv0_out", launch_conv0_out(e, B, st)); ++n;
   RUN("df_pathway", launch_df_pathway(e, B, st)); ++n;
   RUN("synthesis", launch_synthesis(e, B, st)); ++n;
+  e.pdl_now = false;
   e.launches = n;
 }
 
@@ -970,6 +974,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "sep_tc") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "sep_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
     e.sep_tc = value;
+    drop_graphs(e);
+  } else if (strcmp(key, "pdl") == 0) {
+    e.pdl = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "overlap") == 0 || strcmp(key, "overlap_max") == 0) {
     if (key[7] == 0) e.overlap = value ? 1 : 0;

@@ -40,6 +40,13 @@ __device__ __forceinline__ int io_flags(const IoDesc* io, int b) {
   return io->flags ? __ldg(io->flags + b) : 0;
 }
 
+// ---- programmatic dependent launch (engine.h:launch_k) ------------------------------------------------------
+// Every kernel of a hop opens with pdl_trigger(); pdl_wait();  -- the trigger lets the next kernel of the chain become
+// resident (launch latency, prologue) while this one runs, the wait blocks until the kernel before this one has
+// completed and flushed its writes.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- packed FP32 math (Blackwell FFMA2: two FMAs per lane per issue) ------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }

@@ -183,6 +183,9 @@ struct Engine {
   std::map<int, cudaGraphExec_t> lane_graphs; // keyed by B * MAX_LANES + lane: one hop of one lane (free-running lanes of a multi-hop run)
   int launches_per_lane = 0;
   // post kernel overlapped with the intra sweep: per-lane progress counters [lane][2][2][tiles]
+  int pdl = 0;                    // option: chain ALL kernels of a hop with programmatic dependent launches (measured slower: early-resident waiters crowd the running kernel)
+  bool pdl_now = false;           // decided per enqueue_step (off while timing with events)
+  bool pdl_first = false;         // next launch is the first kernel of a chain: plain launch
   int overlap = 1;                // option: 0 off, 1 on whenever both DPRNN kernels run on tcgen05, lanes are not forced and
   int overlap_max = 4097;         //         the step has fewer than overlap_max streams
   bool overlap_now = false;       // decided per enqueue_step
@@ -196,7 +199,24 @@ struct Engine {
   std::vector<std::string> tnames;
 };
 
+// Kernel launch with the programmatic-stream-serialization attribute when the engine runs its hop as a PDL chain
+// (Engine::pdl_now); `first` marks the first kernel of a chain, whose predecessor is not a kernel.
+template <typename... KArgs, typename... Args>
+inline void launch_k(const Engine& e, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args);
+
 int set_error(int code, const char* msg);   // thread-local message behind dpdf_last_error()
+template <typename... KArgs, typename... Args>
+inline void launch_k(const Engine& e, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (e.pdl_now && !e.pdl_first) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 void init_frontend_kernels();
 void init_conv_kernels();
 void init_dprnn_kernels();

@@ -22,6 +22,8 @@ struct Conv0Params {
 // thread = (b, f, 4 channels): the nine ring taps are read once per thread (broadcast within the 16 threads of a
 // position), weights as float4, one 16-byte store
 __global__ void __launch_bounds__(256) k_erb_conv0(Conv0Params p) {
+  pdl_trigger();
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) {      // hop counter tick (see IoDesc)
     p.io->t_out = p.io->t_in;
     p.io->t_in = p.io->t_in + 1;
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(256) k_erb_conv0(Conv0Params p) {
 void launch_erb_conv0(Engine& e, int B, cudaStream_t st) {
   Conv0Params p{e.io_dev, e.st, e.w.erb_conv0_w, e.w.erb_conv0_b, e.sc.e0, e.d.fe[0], e.d.fe_feat, B};
   const long long total = (long long)B * e.d.fe[0] * (C / 4);
-  k_erb_conv0<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+  launch_k(e, k_erb_conv0, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -71,6 +73,8 @@ constexpr int SEP_ROWS = 32 * SEP_TM;
 constexpr size_t SEP_SMEM = (size_t)(SEP_ROWS * SEP_LD + 64 * SEP_LD + 64) * sizeof(float);
 
 __global__ void __launch_bounds__(256, 2) k_sepconv(SepParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float* As = smem;                    // [SEP_ROWS][68]
   float* Ws = As + SEP_ROWS * SEP_LD;  // [64][68]
@@ -203,7 +207,7 @@ void launch_sepconv(Engine& e, const SepProblem* probs, int nprob, int B, cudaSt
     p.prob[i].tile0 = tiles;
     tiles += (int)(((long long)B * probs[i].Fout + SEP_ROWS - 1) / SEP_ROWS);
   }
-  k_sepconv<<<tiles, 256, SEP_SMEM, st>>>(p);
+  launch_k(e, k_sepconv, dim3(tiles), dim3(256), SEP_SMEM, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -214,6 +218,8 @@ struct Conv0OutParams {
 };
 
 __global__ void __launch_bounds__(256) k_conv0_out(Conv0OutParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= p.B * p.fe0) return;
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(256) k_conv0_out(Conv0OutParams p) {
 void launch_conv0_out(Engine& e, int B, cudaStream_t st) {
   Conv0OutParams p{e.sc.e0, e.sc.d1, e.w.convp_a[3], e.w.convp_b[3], e.w.conv0_out_w, e.w.conv0_out_b, e.sc.m, e.d.fe[0], B};
   const long long warps = (long long)B * e.d.fe[0];
-  k_conv0_out<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+  launch_k(e, k_conv0_out, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -258,6 +264,8 @@ struct DfPathParams {
 // is a fully used 128-byte line per bin, weights are broadcast float4 from shared memory, the 8 chunk-lanes of a
 // bin are reduced with xor shuffles.  HBM-bound on the ring (120 KB per stream-frame).
 __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float ws[2 * ORD * 8 * 5 * 4];        // [g][kt][ci/4][o][4]
   __shared__ float pws[100], bs[10];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
 void launch_df_pathway(Engine& e, int B, cudaStream_t st) {
   DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B};
   const long long threads = (long long)B * (NDF / 4) * 32;
-  k_df_pathway<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p);
+  launch_k(e, k_df_pathway, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
 }
 
 void init_conv_kernels() {

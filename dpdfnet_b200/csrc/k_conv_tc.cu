@@ -36,6 +36,8 @@ struct SepTcParams {
 };
 
 __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* Aimg = smem_raw;                               // hi image | lo image; later the FP32 output staging
   unsigned char* Wsm = smem_raw + SCT_OFF_W;
@@ -210,7 +212,7 @@ void launch_sepconv_tc(Engine& e, const SepProblem* probs, int nprob, int B, cud
     p.prob[i].tile0 = tiles;
     tiles += (int)(((long long)B * probs[i].Fout + SCT_ROWS - 1) / SCT_ROWS);
   }
-  k_sepconv_tc<<<tiles, SCT_NT, SCT_SMEM, st>>>(p);
+  launch_k(e, k_sepconv_tc, dim3(tiles), dim3(SCT_NT), SCT_SMEM, st, p);
 }
 
 void init_conv_tc_kernels() {

@@ -17,6 +17,8 @@ struct GLParams {
 
 template <int NJ>
 __global__ void __launch_bounds__(256) k_gl(GLParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   int pi = 0;
 #pragma unroll
@@ -100,10 +102,10 @@ void launch_gl(Engine& e, const GLProblem* probs, int nprob, int B, cudaStream_t
   }
   p.g0[nprob] = groups;
   dim3 grid((B + 63) / 64, groups);
-  if (maxnj <= 4) k_gl<4><<<grid, 256, smem, st>>>(p);
-  else if (maxnj <= 8) k_gl<8><<<grid, 256, smem, st>>>(p);
-  else if (maxnj <= 16) k_gl<16><<<grid, 256, smem, st>>>(p);
-  else k_gl<20><<<grid, 256, smem, st>>>(p);
+  if (maxnj <= 4) launch_k(e, k_gl<4>, dim3(grid), dim3(256), smem, st, p);
+  else if (maxnj <= 8) launch_k(e, k_gl<8>, dim3(grid), dim3(256), smem, st, p);
+  else if (maxnj <= 16) launch_k(e, k_gl<16>, dim3(grid), dim3(256), smem, st, p);
+  else launch_k(e, k_gl<20>, dim3(grid), dim3(256), smem, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -123,6 +125,8 @@ constexpr size_t gru_smem() { return (size_t)(2 * (32 * TM + 96) * G_LD) * sizeo
 // feed 96 packed FFMA2 per 4 k (TM = 4).
 template <int TM>
 __global__ void __launch_bounds__(256, 1) k_gru(GRUParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int ROWS = 32 * TM;
   extern __shared__ __align__(16) float smem[];
   float* Abuf = smem;                          // [2][ROWS][68]
@@ -228,6 +232,8 @@ struct GRUCommitParams {
 // Every unit-chunk CTA of a cell reads the full h_prev rows, and nothing else reads the GRU states inside a
 // hop, so all five cells' new states are written back by one launch at the end of the hop.
 __global__ void k_gru_commit(GRUCommitParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index within one cell
   if (idx >= p.B * (H / 4)) return;
   const int b = idx / (H / 4), c = (idx % (H / 4)) * 4;
@@ -245,10 +251,10 @@ void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream
   for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
   if (B >= 4 * e.num_sms) {          // enough streams to fill the chip with 128-row tiles
     dim3 grid((B + 127) / 128, H / 32, nprob);
-    k_gru<4><<<grid, 256, gru_smem<4>(), st>>>(p);
+    launch_k(e, k_gru<4>, dim3(grid), dim3(256), gru_smem<4>(), st, p);
   } else {
     dim3 grid((B + 63) / 64, H / 32, nprob);
-    k_gru<2><<<grid, 256, gru_smem<2>(), st>>>(p);
+    launch_k(e, k_gru<2>, dim3(grid), dim3(256), gru_smem<2>(), st, p);
   }
 }
 
@@ -259,7 +265,7 @@ void launch_gru_commit(Engine& e, const GRUProblem* probs, int nprob, int B, cud
   p.B = B;
   for (int i = 0; i < nprob; ++i) { p.hout[i] = probs[i].hout; p.hstate[i] = probs[i].hstate; p.stride[i] = probs[i].hs_stride; }
   dim3 grid((B * (H / 4) + 255) / 256, nprob);
-  k_gru_commit<<<grid, 256, 0, st>>>(p);
+  launch_k(e, k_gru_commit, dim3(grid), dim3(256), 0, st, p);
 }
 
 void init_dense_kernels() {

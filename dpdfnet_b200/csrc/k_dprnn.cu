@@ -34,6 +34,8 @@ __device__ __forceinline__ int row_pos(int k) { return ((k >> 2) & 1) * 32 + (k 
 
 template <int BT>
 __global__ void __launch_bounds__(256, 1) k_dprnn_intra(IntraParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float xs[2][BT][ILD];
   __shared__ __align__(16) float hs[2][BT][ILD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -216,9 +218,9 @@ void launch_dprnn_intra(Engine& e, int blk, int B, cudaStream_t st) {
     bt = B <= 4 * e.num_sms ? 8 : (B <= 16 * e.num_sms ? 16 : 32);
   p.tiles = (B + bt - 1) / bt;
   const int grid = 4 * p.tiles;
-  if (bt == 8) k_dprnn_intra<8><<<grid, 256, 0, st>>>(p);
-  else if (bt == 16) k_dprnn_intra<16><<<grid, 256, 0, st>>>(p);
-  else k_dprnn_intra<32><<<grid, 256, 0, st>>>(p);
+  if (bt == 8) launch_k(e, k_dprnn_intra<8>, dim3(grid), dim3(256), 0, st, p);
+  else if (bt == 16) launch_k(e, k_dprnn_intra<16>, dim3(grid), dim3(256), 0, st, p);
+  else launch_k(e, k_dprnn_intra<32>, dim3(grid), dim3(256), 0, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -245,6 +247,8 @@ constexpr size_t POST_SMEM = (size_t)(P_RA + 2 * P_RX + 640) * sizeof(float) + 1
 static_assert(128 * P_LDH + 64 * P_LDH <= P_RA, "phase-1 operands must fit the weight region");
 
 __global__ void __launch_bounds__(256, 1) k_dprnn_post(PostParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float* RA = smem;
   float* RX = RA + P_RA;
@@ -400,7 +404,7 @@ void launch_dprnn_post(Engine& e, int blk, int B, cudaStream_t st) {
   fill(p.br[1], e.w.dprnn_erb[blk], e.sc.hcat_e, blk == 0 ? e.sc.e3 : e.sc.xe, e.sc.xe, e.st.inter_erb, e.d.fe[3]);
   p.tiles0 = (int)(((long long)B * (NDF / 2) + 127) / 128);
   const int tiles1 = (int)(((long long)B * e.d.fe[3] + 127) / 128);
-  k_dprnn_post<<<p.tiles0 + tiles1, 256, POST_SMEM, st>>>(p);
+  launch_k(e, k_dprnn_post, dim3(p.tiles0 + tiles1), dim3(256), POST_SMEM, st, p);
 }
 
 void init_dprnn_kernels() {

@@ -137,12 +137,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   if (tid < 256) sb[tid] = __ldg((br ? p.bias[1] : p.bias[0]) + dir * 4 * C + tid);
   for (int i = tid; i < ST_BUF / 16; i += ITC_NT) reinterpret_cast<uint4*>(Ssm + ST_BUF)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0 (read back as h_prev of step 0)
   int* my_progress = p.progress ? p.progress + (br * 2 + dir) * p.tiles + tile : nullptr;
-  if (my_progress && tid == 0) {
-    *reinterpret_cast<volatile int*>(my_progress) = 0;       // visible before any consumer CTA of the dependent launch starts
-    __threadfence();
-  }
   __syncthreads();                                           // barriers initialised
-  if (my_progress) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // every CTA of this grid is resident or done
   if (tid == 0) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(br ? p.wimg[1] : p.wimg[0]) + (size_t)dir * 4 * W_IMG;
     mbar_expect_tx(bars, 4 * W_IMG);
@@ -181,6 +176,14 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
     store_x1(buf, v, 0);
     store_x1(buf, v, 1);
   };
+  // Everything above (barriers, TMEM, the 96 KB of weight images) overlaps with the tail of the previous kernel.
+  pdl_wait();
+  if (my_progress && tid == 0) {
+    *reinterpret_cast<volatile int*>(my_progress) = 0;       // the previous consumer of these counters has completed
+    __threadfence();
+  }
+  __syncthreads();
+  pdl_trigger();                                             // every CTA of this grid is resident (or done): dependents may launch
   float xv[2][8];
   if (warp < 16) {
     load_x(0, xv);
@@ -449,7 +452,7 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.B = B;
   p.tiles = (B + 127) / 128;
   p.progress = e.overlap_now ? e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles : nullptr;
-  k_dprnn_intra_tc<<<4 * p.tiles, ITC_NT, INTRA_TC_SMEM, st>>>(p);
+  launch_k(e, k_dprnn_intra_tc, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
 }
 
 void init_dprnn_intra_tc_kernels() {

@@ -80,6 +80,8 @@ constexpr size_t POST_TC_SMEM = PT_OFF_BAR + 64;
 // TMEM columns: [0,64) fc_intra, then the gate pre-activations r [0,64) z [64,128) in [128,192) hn [192,256),
 // then fc_inter in [0,64) again (each phase is drained by all threads before the next one is issued).
 __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
+  pdl_trigger();
+  if (!p.progress) pdl_wait();      // overlapped mode synchronises with the sweep through its progress counters instead
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* RA = smem_raw;                     // four activation operand images
   unsigned char* RW = smem_raw + PT_OFF_W;
@@ -410,7 +412,7 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.tiles0 = (int)(((long long)B * (NDF / 2) + 127) / 128);
   const int tiles1 = (int)(((long long)B * e.d.fe[3] + 127) / 128);
   if (!e.overlap_now) {
-    k_dprnn_post_tc<<<p.tiles0 + tiles1, TC_NT, POST_TC_SMEM, st>>>(p);
+    launch_k(e, k_dprnn_post_tc, dim3(p.tiles0 + tiles1), dim3(TC_NT), POST_TC_SMEM, st, p);
     return;
   }
   // Overlapped with the sweep that feeds it: launched as a programmatic dependent of the intra kernel (it may start as

@@ -28,6 +28,8 @@ struct AnaParams {
 
 // Single-group form (throughput-bound grids): thread = bin over all win samples.
 __global__ void __launch_bounds__(512) k_analysis_one(AnaParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   const int win = p.d.win, hop = p.d.hop, F = p.d.F;
   float2* xs2 = reinterpret_cast<float2*>(smem);                 // [win][ABT] {x,x}
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(512) k_analysis_one(AnaParams p) {
 // the partial spectra are added through shared memory in a fixed order (g = 0 first).
 template <int MAXT>      // 512: one group (full register budget for the 16-deep basis prefetch), 1024: split sum
 __global__ void __launch_bounds__(MAXT) k_analysis(AnaParams p, int ksplit) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   const int win = p.d.win, hop = p.d.hop, F = p.d.F;
   float2* xs2 = reinterpret_cast<float2*>(smem);                 // [win][ABT] {x,x}
@@ -298,6 +302,8 @@ struct SynParams {
 };
 
 __global__ void __launch_bounds__(1024) k_synthesis(SynParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float2* Ys = reinterpret_cast<float2*>(smem);          // [F][SBT]
   const int win = p.d.win, hop = p.d.hop, F = p.d.F;
@@ -415,7 +421,7 @@ __global__ void k_reset(ResetParams p) {
 
 // ---- launchers --------------------------------------------------------------------------------
 void launch_prime(Engine& e, const float* pcm, long long stride, const int* slot_ids, int B, cudaStream_t st) {
-  k_prime<<<B, 128, 0, st>>>(e.st, e.d.hop, pcm, stride, slot_ids, B);
+  launch_k(e, k_prime, dim3(B), dim3(128), 0, st, e.st, e.d.hop, pcm, stride, slot_ids, B);
 }
 
 void launch_reset(Engine& e, const int* slots_dev, int n, cudaStream_t st) {
@@ -443,7 +449,7 @@ void launch_reset(Engine& e, const int* slots_dev, int n, cudaStream_t st) {
   p.nseg = i;
   p.pos = e.st.pos;
   p.slots = slots_dev;
-  k_reset<<<n, 256, 0, st>>>(p);
+  launch_k(e, k_reset, dim3(n), dim3(256), 0, st, p);
 }
 
 void launch_analysis(Engine& e, int B, cudaStream_t st) {
@@ -453,15 +459,15 @@ void launch_analysis(Engine& e, int B, cudaStream_t st) {
   int ksplit = (std::max(B, e.total_B) + ABT - 1) / ABT <= 2 * e.num_sms ? 1024 / ntg : 1;   // total_B: all lanes of the step
   while (ksplit > 1 && ((e.d.win / 16) % ksplit != 0)) --ksplit; // every group walks whole 16-sample rounds
   const size_t smem = (size_t)(2 * e.d.win * ABT + ABT * e.d.F + 2 * (ksplit - 1) * ABT * e.d.F) * sizeof(float);
-  if (ksplit > 1) k_analysis<1024><<<(B + ABT - 1) / ABT, ntg * ksplit, smem, st>>>(p, ksplit);
-  else k_analysis_one<<<(B + ABT - 1) / ABT, ntg, smem, st>>>(p);
+  if (ksplit > 1) launch_k(e, k_analysis<1024>, dim3((B + ABT - 1) / ABT), dim3(ntg * ksplit), smem, st, p, ksplit);
+  else launch_k(e, k_analysis_one, dim3((B + ABT - 1) / ABT), dim3(ntg), smem, st, p);
 }
 
 void launch_synthesis(Engine& e, int B, cudaStream_t st) {
   SynParams p{e.io_dev, e.d, e.st, e.w.dft_inv, e.sc.m, e.w.band_of_bin, B};
   const int nt = (e.d.win + 31) / 32 * 32;
   const size_t smem = (size_t)(2 * e.d.F * SBT) * sizeof(float);
-  k_synthesis<<<(B + SBT - 1) / SBT, nt, smem, st>>>(p);
+  launch_k(e, k_synthesis, dim3((B + SBT - 1) / SBT), dim3(nt), smem, st, p);
 }
 
 void init_frontend_kernels() {

@@ -35,6 +35,8 @@ struct GRUTcParams {
 };
 
 __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* Asm = smem_raw;
   unsigned char* Wsm = smem_raw + GT_OFF_W;
@@ -184,7 +186,7 @@ void launch_gru_tc(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStr
   p.B = B;
   for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
   dim3 grid((B + 127) / 128, H / 64, nprob);
-  k_gru_tc<<<grid, GT_NT, GRU_TC_SMEM, st>>>(p);
+  launch_k(e, k_gru_tc, dim3(grid), dim3(GT_NT), GRU_TC_SMEM, st, p);
 }
 
 void init_gru_tc_kernels() {
