@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid < 256) sb[tid] = __ldg((br ? p.bias[1] : p.bias[0]) + dir * 4 * C + tid);
   for (int i = tid; i < ST_BUF / 16; i += ITC_NT) reinterpret_cast<uint4*>(Ssm + ST_BUF)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0 (read back as h_prev of step 0)
-  int* my_progress = p.progress ? p.progress + (br * 2 + dir) * p.tiles + tile : nullptr;
+  // progress counter of this CTA (recomputed where it is used: it must not cost the gate warps a live register)
+  auto progress_ptr = [&]() -> int* { return p.progress ? p.progress + (br * 2 + dir) * p.tiles + tile : nullptr; };
   __syncthreads();                                           // barriers initialised
   if (tid == 0) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(br ? p.wimg[1] : p.wimg[0]) + (size_t)dir * 4 * W_IMG;
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   };
   // Everything above (barriers, TMEM, the 96 KB of weight images) overlaps with the tail of the previous kernel.
   pdl_wait();
-  if (my_progress && tid == 0) {
-    *reinterpret_cast<volatile int*>(my_progress) = 0;       // the previous consumer of these counters has completed
+  if (tid == 0 && p.progress) {
+    *reinterpret_cast<volatile int*>(progress_ptr()) = 0;    // the previous consumer of these counters has completed
     __threadfence();
   }
   __syncthreads();
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   // tensor core works on slice ks while the gate math of slices ks+1.. is still running.  Only the last slice's six
   // MMAs and the commit remain on the critical path of a step.
   if (warp == 16) {
+    int* my_progress = progress_ptr();
     const uint32_t w_base = smem_u32(Wsm), x_base = smem_u32(Xsm);
     constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
     auto x_mma = [&](int t) {                                // P[t & 1][0, 192) = x_t * W_ih^T
@@ -431,10 +433,10 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
         *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
     }
   }
-  if (my_progress) {
+  if (p.progress) {
     __threadfence();
     __syncthreads();
-    if (tid == 0) *reinterpret_cast<volatile int*>(my_progress) = T;
+    if (tid == 0) *reinterpret_cast<volatile int*>(progress_ptr()) = T;
   }
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
