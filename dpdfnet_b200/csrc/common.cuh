@@ -44,8 +44,13 @@ __device__ __forceinline__ int io_flags(const IoDesc* io, int b) {
 // Every kernel of a hop opens with pdl_trigger(); pdl_wait();  -- the trigger lets the next kernel of the chain become
 // resident (launch latency, prologue) while this one runs, the wait blocks until the kernel before this one has
 // completed and flushed its writes.  Both are no-ops for a kernel launched without the attribute.
+#ifdef DPDF_NO_PDL      // microbenchmark switch (tools/ubench): what the two instructions cost a plainly launched kernel
+__device__ __forceinline__ void pdl_trigger() {}
+__device__ __forceinline__ void pdl_wait() {}
+#else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // ---- packed FP32 math (Blackwell FFMA2: two FMAs per lane per issue) ------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }

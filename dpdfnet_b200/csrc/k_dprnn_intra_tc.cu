@@ -137,7 +137,11 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   if (tid < 256) sb[tid] = __ldg((br ? p.bias[1] : p.bias[0]) + dir * 4 * C + tid);
   for (int i = tid; i < ST_BUF / 16; i += ITC_NT) reinterpret_cast<uint4*>(Ssm + ST_BUF)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0 (read back as h_prev of step 0)
   // progress counter of this CTA (recomputed where it is used: it must not cost the gate warps a live register)
+#ifdef ITC_NO_PROGRESS
+  auto progress_ptr = [&]() -> int* { return nullptr; };
+#else
   auto progress_ptr = [&]() -> int* { return p.progress ? p.progress + (br * 2 + dir) * p.tiles + tile : nullptr; };
+#endif
   __syncthreads();                                           // barriers initialised
   if (tid == 0) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(br ? p.wimg[1] : p.wimg[0]) + (size_t)dir * 4 * W_IMG;
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   };
   // Everything above (barriers, TMEM, the 96 KB of weight images) overlaps with the tail of the previous kernel.
   pdl_wait();
-  if (tid == 0 && p.progress) {
+  if (tid == 0 && progress_ptr()) {
     *reinterpret_cast<volatile int*>(progress_ptr()) = 0;    // the previous consumer of these counters has completed
     __threadfence();
   }
@@ -433,7 +437,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
         *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
     }
   }
-  if (p.progress) {
+  if (progress_ptr()) {
     __threadfence();
     __syncthreads();
     if (tid == 0) *reinterpret_cast<volatile int*>(progress_ptr()) = T;
