@@ -33,7 +33,15 @@ struct SepTcParams {
   State st;
   SepProblem prob[SCT_MAXP];
   int nprob, B;
+#ifdef SCT_TIMELINE
+  long long* tl;          // [8] SM-clock stamps of CTA 0 (tools/ubench/sepconv_tc_timeline.cu)
+#endif
 };
+#ifdef SCT_TIMELINE
+#define STL(slot) do { if (blockIdx.x == 0 && threadIdx.x == 64) p.tl[slot] = clock64(); } while (0)
+#else
+#define STL(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
   pdl_trigger();
@@ -51,6 +59,7 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
     if (i < p.nprob && (int)blockIdx.x >= p.prob[i].tile0) pi = i;
   const SepProblem& q = p.prob[pi];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  STL(0);
   const long long row0 = (long long)(blockIdx.x - q.tile0) * SCT_ROWS;
   const long long nrows = (long long)p.B * q.Fout;
 
@@ -63,6 +72,7 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
   }
   if (warp == 0) tmem_alloc<64>(tmem_slot);
   if (tid < 64) bs[tid] = __ldg(q.bias + tid);
+  STL(1);
 
   // prologue: A[row][c] -> operand images.  Thread = (channel quad g, row r & 7 ...): it keeps the same 4 channels for
   // all of its 8 rows (taps and pathway affine loaded once); the 8 lanes of a channel quad write 8 consecutive rows of
@@ -82,10 +92,10 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
 #pragma unroll
     for (int i = 0; i < SCT_ROWS / 16; ++i) {
       const int r = rsub + 16 * i;
-      const long long row = row0 + r;
+      const int row = (int)row0 + r;                          // < 2^31 rows: 32-bit index math (64-bit division is ~100 instructions)
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < nrows) {
-        const int b = (int)(row / q.Fout), fo = (int)(row % q.Fout);
+      if (row < (int)nrows) {
+        const int b = row / q.Fout, fo = row - b * q.Fout;
         if (q.mode == 0) {
           int fc, j;
           if (q.up > 1) { fc = fo / q.up; j = fo % q.up; } else { fc = fo * q.stride; j = 0; }
@@ -139,11 +149,13 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
       *reinterpret_cast<uint2*>(dst + SCT_IMG) = l;
     }
   }
+  STL(2);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  STL(3);
 
   if (tid == 0) {
     mbar_wait(bars, 0);
@@ -161,6 +173,7 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
   }
   mbar_wait(bars + 1, 0);
   tc_fence_after();
+  STL(4);
 
   // epilogue: thread = (row = TMEM lane, 32-column half); bias + ReLU into the swizzled FP32 staging tile
   {
@@ -181,6 +194,7 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  STL(5);
   for (int it = tid; it < SCT_ROWS * 16; it += SCT_NT) {
     const int r = it >> 4, c4 = it & 15, c = c4 * 4;
     const long long row = row0 + r;
@@ -197,6 +211,7 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
       *reinterpret_cast<float4*>(p.st.c0_ring + (((size_t)slot * ORD + pos % ORD) * NDF + fo) * C + c) = v;
     }
   }
+  STL(6);
   if (warp == 0) tmem_dealloc<64>(tmem);
 }
 
