@@ -218,6 +218,10 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   if (cudaMemcpy(e.weights_dev, payload, payload_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
     return bail(fail(DPDF_ERR_CUDA, "weight upload failed"));
   if (int rc = bind_weights(e)) return bail(rc);
+  {
+    auto it = e.wtable.find("df_dec.df_convp.w");
+    if (it != e.wtable.end()) e.dfp_w_host.assign(payload + it->second.first, payload + it->second.first + it->second.second);
+  }
 
   // band tables
   {
@@ -255,7 +259,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
     add(s.mu, d.fe_feat); add(s.s, NDF); add(s.erb_ring, 3 * d.fe_feat); add(s.df_ring, 3 * 2 * NDF);
     add(s.inter_erb, (size_t)std::max(d.N, 1) * d.fe[3] * C); add(s.inter_df, (size_t)std::max(d.N, 1) * (NDF / 2) * C);
     add(s.h_enc, H); add(s.h_erb, 2 * H); add(s.h_df, 2 * H);
-    add(s.c0_ring, (size_t)ORD * NDF * C); add(s.mask_ring, 3 * d.F * 2); add(s.coef_ring, 3 * NDF * 2 * ORD);
+    add(s.c0_ring, (size_t)ORD * NDF * C); add(s.dfp_acc, (size_t)ORD * NDF * 10); add(s.mask_ring, 3 * d.F * 2); add(s.coef_ring, 3 * NDF * 2 * ORD);
     add(s.dfspec_ring, (size_t)ORD * d.F * 2); add(s.in_hist, d.hop); add(s.ola, d.hop);
     in_scratch = true;
     add(c.e0, (size_t)d.fe[0] * C); add(c.e1, (size_t)d.fe[1] * C); add(c.e2, (size_t)d.fe[2] * C); add(c.e3, (size_t)d.fe[3] * C);
@@ -463,7 +467,9 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     RUN("sepconv", sepconv(e, &q, 1, B, st)); ++n;
   }
   RUN("conv0_out", launch_conv0_out(e, B, st)); ++n;
-  RUN("df_pathway", launch_df_pathway(e, B, st)); ++n;
+  if (e.dfp_ps) { RUN("df_pathway", launch_df_pathway_ps(e, B, st)); }
+  else { RUN("df_pathway", launch_df_pathway(e, B, st)); }
+  ++n;
   RUN("synthesis", launch_synthesis(e, B, st)); ++n;
   e.pdl_now = false;
   e.launches = n;
@@ -899,6 +905,22 @@ extern "C" int dpdf_state_import(dpdf_engine* h, int32_t slot, const float* flat
         for (int f = 0; f < NDF; ++f) buf[((size_t)k * NDF + f) * C + c] = o[((size_t)k * C + c) * NDF + f];
     o += buf.size();
     if ((rc = store(e, e.st.c0_ring, buf.size(), slot, buf))) return rc;
+    // pending sums of the df pathway conv, rebuilt from the five imported frames (pos := 0, logical == physical):
+    // the output m hops ahead already has the taps kt = 0 .. 3 - m of the frames kt + 1 + m
+    std::vector<float> acc((size_t)ORD * NDF * 10, 0.f);
+    if (e.dfp_w_host.size() == (size_t)10 * ORD * 32) {
+      for (int m = 0; m < ORD - 1; ++m)
+        for (int f = 0; f < NDF; ++f)
+          for (int oo = 0; oo < 10; ++oo) {
+            double sum = 0.0;
+            for (int kt = 0; kt + m < ORD - 1; ++kt)
+              for (int ci = 0; ci < 32; ++ci)
+                sum += (double)e.dfp_w_host[((size_t)oo * ORD + kt) * 32 + ci] *
+                       buf[((size_t)(kt + 1 + m) * NDF + f) * C + (oo / 5) * 32 + ci];
+            acc[((size_t)f * ORD + m) * 10 + oo] = (float)sum;
+          }
+    }
+    if ((rc = store(e, e.st.dfp_acc, acc.size(), slot, acc))) return rc;
   }
   if ((rc = plain(e.st.mask_ring, (size_t)3 * d.F * 2))) return rc;
   {
@@ -974,6 +996,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "sep_tc") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "sep_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
     e.sep_tc = value;
+    drop_graphs(e);
+  } else if (strcmp(key, "dfp_ps") == 0) {
+    e.dfp_ps = value ? 1 : 0;                      // switch only on freshly reset streams: the two forms keep different state
     drop_graphs(e);
   } else if (strcmp(key, "pdl") == 0) {
     e.pdl = value ? 1 : 0;

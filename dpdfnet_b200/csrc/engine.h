@@ -34,6 +34,7 @@ struct State {           // all [max_streams][...], float unless noted
   float* h_erb;          // [2][256]
   float* h_df;           // [2][256]
   float* c0_ring;        // [5][96][64]
+  float* dfp_acc;        // [96][5][10] pending sums of the df pathway conv (k_df_pathway_ps); slot (pos + d) % 5 = output d hops ahead
   float* mask_ring;      // [3][F][2]
   float* coef_ring;      // [3][96][10]
   float* dfspec_ring;    // [5][F][2]
@@ -103,6 +104,7 @@ void launch_sepconv(Engine& e, const SepProblem* probs, int nprob, int B, cudaSt
 void launch_sepconv_tc(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st);
 void launch_conv0_out(Engine& e, int B, cudaStream_t st);
 void launch_df_pathway(Engine& e, int B, cudaStream_t st);
+void launch_df_pathway_ps(Engine& e, int B, cudaStream_t st);
 
 void launch_dprnn_intra(Engine& e, int blk, int B, cudaStream_t st);
 void launch_dprnn_post(Engine& e, int blk, int B, cudaStream_t st);
@@ -183,6 +185,10 @@ struct Engine {
   std::map<int, cudaGraphExec_t> lane_graphs; // keyed by B * MAX_LANES + lane: one hop of one lane (free-running lanes of a multi-hop run)
   int launches_per_lane = 0;
   // post kernel overlapped with the intra sweep: per-lane progress counters [lane][2][2][tiles]
+  int dfp_ps = 0;                 // df pathway conv as pending partial sums: 38 KB of accumulator traffic instead of the 120 KB c0 ring
+                                  // read per stream-hop, but measured slower (0.48 vs 0.27 ms at 8192 streams: the 50-value
+                                  // reduce-scatter and the dependent read-modify-writes cost more than the ring read saves)
+  std::vector<float> dfp_w_host;  // [10][5][32] for rebuilding the pending sums at state import
   int pdl = 0;                    // option: chain ALL kernels of a hop with programmatic dependent launches (measured slower: early-resident waiters crowd the running kernel)
   bool pdl_now = false;           // decided per enqueue_step (off while timing with events)
   bool pdl_first = false;         // next launch is the first kernel of a chain: plain launch

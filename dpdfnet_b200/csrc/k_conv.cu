@@ -331,6 +331,114 @@ void launch_df_pathway(Engine& e, int B, cudaStream_t st) {
   launch_k(e, k_df_pathway, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same 5-frame grouped conv as k_df_pathway, as pending partial sums: when the
+// frame of hop t arrives it is multiplied by all five taps at once and added to the outputs of hops t .. t+4
+// (acc slot (pos + d) % 5 <- + W[4 - d] * c0_t); slot pos % 5 is then complete, consumed and cleared.  Per stream
+// and hop this reads the new frame (24 KB, still in L2 from k_sepconv_tc) and 19 KB of accumulators instead of the
+// 120 KB ring.  The raw ring is still written (by the df_conv0 kernel) because the reference-layout state export needs it.
+struct DfPathPsParams {
+  const IoDesc* io;
+  State st;
+  const float *w, *pw, *bias;   // [10][5][32], [10][10], [10]
+  const float* co;              // [B][96][10] tanh(df_out)
+  const float* c0;              // [B][96][64] this hop's frame
+  int B;
+};
+
+__global__ void __launch_bounds__(256) k_df_pathway_ps(DfPathPsParams p) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float ws[2 * ORD * 8 * 5 * 4];        // [g][kt][ci/4][o][4]
+  __shared__ float pws[100], bs[10], tsm[8][4][10];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2 * ORD * 8 * 5 * 4; i += 256) {
+    const int e = i & 3, o = (i >> 2) % 5, c4 = (i / 20) % 8, kt = (i / 160) % ORD, g = i / 800;
+    ws[i] = __ldg(p.w + ((g * 5 + o) * ORD + kt) * 32 + c4 * 4 + e);
+  }
+  if (tid < 100) pws[tid] = __ldg(p.pw + tid);
+  if (tid < 10) bs[tid] = __ldg(p.bias + tid);
+  __syncthreads();
+  const long long witem = ((long long)blockIdx.x * 256 + tid) >> 5;       // (b, group of 4 bins)
+  if (witem >= (long long)p.B * (NDF / 4)) return;
+  const int b = (int)(witem / (NDF / 4)), jb = lane >> 3, f = (int)(witem % (NDF / 4)) * 4 + jb, c8 = lane & 7;
+  const int slot = io_slot(p.io, b);
+  const int pos = p.st.pos[slot];
+  const bool warm = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) != 0;
+  float4 x[2];
+  {
+    const float* src = p.c0 + ((size_t)b * NDF + f) * C + c8 * 4;
+    x[0] = warm ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(src);
+    x[1] = warm ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(src + 32);
+  }
+  // t[d * 10 + g * 5 + o]: this lane's 4-channel share of W[tap 4 - d] * frame for the output d hops ahead
+  float t[56];
+#pragma unroll
+  for (int d = 0; d < ORD; ++d)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const float4* wp = reinterpret_cast<const float4*>(ws) + (g * ORD + (ORD - 1 - d)) * 40 + c8 * 5;
+#pragma unroll
+      for (int o = 0; o < 5; ++o) {
+        const float4 w = wp[o];
+        t[d * 10 + g * 5 + o] = fmaf(w.x, x[g].x, fmaf(w.y, x[g].y, fmaf(w.z, x[g].z, w.w * x[g].w)));
+      }
+    }
+#pragma unroll
+  for (int i = 50; i < 56; ++i) t[i] = 0.f;
+  // reduce-scatter over the 8 channel lanes of a bin (xor 4, 2, 1): lane c8 ends with the seven complete sums
+  // base .. base + 6, base = 28 b2 + 14 b1 + 7 b0
+  const bool b2 = (c8 & 4) != 0, b1 = (c8 & 2) != 0, b0 = (c8 & 1) != 0;
+  float r1[28], r2[14], r3[7];
+#pragma unroll
+  for (int i = 0; i < 28; ++i) {
+    const float keep = b2 ? t[28 + i] : t[i], send = b2 ? t[i] : t[28 + i];
+    r1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 14; ++i) {
+    const float keep = b1 ? r1[14 + i] : r1[i], send = b1 ? r1[i] : r1[14 + i];
+    r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const float keep = b0 ? r2[7 + i] : r2[i], send = b0 ? r2[i] : r2[7 + i];
+    r3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  const int base = (b2 ? 28 : 0) + (b1 ? 14 : 0) + (b0 ? 7 : 0);
+  float* acc = p.st.dfp_acc + (size_t)slot * ORD * NDF * 10;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int idx = base + i;
+    if (idx < 50) {
+      const int d = idx / 10, oo = idx - d * 10;
+      float* a = acc + ((size_t)f * ORD + (pos + d) % ORD) * 10 + oo;      // [96][5][10]: the 50 sums of a bin are contiguous
+      const float v = *a + r3[i];
+      if (d == 0) { tsm[warp][jb][oo] = v; *a = 0.f; }        // complete: consumed below, slot restarts for hop t + 5
+      else *a = v;
+    }
+  }
+  __syncwarp();
+  float* dst = p.st.coef_ring + (((size_t)slot * 3 + pos % 3) * NDF + f) * 10;
+  const float* cop = p.co + ((size_t)b * NDF + f) * 10;
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int oo = c8 + 8 * rep;                      // lanes 0..7 of a bin finish outputs 0..7, lanes 0,1 also 8,9
+    if (oo < 10) {
+      float u = bs[oo];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) u = fmaf(pws[oo * 10 + i], tsm[warp][jb][i], u);
+      dst[oo] = warm ? 0.f : cop[oo] + fmaxf(u, 0.f);
+    }
+  }
+}
+
+void launch_df_pathway_ps(Engine& e, int B, cudaStream_t st) {
+  DfPathPsParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, e.sc.c0, B};
+  const long long threads = (long long)B * (NDF / 4) * 32;
+  launch_k(e, k_df_pathway_ps, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
+}
+
 void init_conv_kernels() {
   cudaFuncSetAttribute(k_sepconv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEP_SMEM);
 }

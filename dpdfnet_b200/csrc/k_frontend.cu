@@ -441,6 +441,7 @@ void launch_reset(Engine& e, const int* slots_dev, int n, cudaStream_t st) {
   add(e.st.h_erb, 2 * H, nullptr);
   add(e.st.h_df, 2 * H, nullptr);
   add(e.st.c0_ring, (long long)ORD * NDF * C, nullptr);
+  add(e.st.dfp_acc, (long long)ORD * NDF * 10, nullptr);
   add(e.st.mask_ring, 3LL * d.F * 2, nullptr);
   add(e.st.coef_ring, 3LL * NDF * 2 * ORD, nullptr);
   add(e.st.dfspec_ring, (long long)ORD * d.F * 2, nullptr);

@@ -84,6 +84,7 @@ def test_stages_vs_oracle(torch_cuda, name, B, intra_tc):
     eng.set_option("intra_tc", intra_tc)
     eng.set_option("sep_tc", intra_tc)          # the separable convs and the GRU(256) cells on the same arm: FFMA2 / tcgen05
     eng.set_option("gru_tc", intra_tc)
+    eng.set_option("dfp_ps", intra_tc)          # df pathway conv: 5-frame ring form (default) / pending-partial-sum form
     ora = _oracle(name, 11, B + 3)
     spec = eng.spec
     rng = np.random.default_rng(2)
@@ -189,8 +190,10 @@ def test_lanes_match_single_chain(torch_cuda, intra_tc):
     assert np.abs(outs[2][0][:4] - ref).max() < WAVE_TOL
 
 
-def test_state_import_export_roundtrip(torch_cuda):
+@pytest.mark.parametrize("dfp_ps", [0, 1])
+def test_state_import_export_roundtrip(torch_cuda, dfp_ps):
     eng = _engine("dpdfnet2", 9, 3)
+    eng.set_option("dfp_ps", dfp_ps)            # partial-sum form: the pending sums are rebuilt from the imported ring
     F = eng.spec.freq_bins
     rng = np.random.default_rng(0)
     X = (rng.standard_normal((7, 3, F, 2)) * 10).astype(np.float32)
@@ -198,6 +201,7 @@ def test_state_import_export_roundtrip(torch_cuda):
         eng.step_spec_host(X[t])
     flat = eng.state_export(2)
     other = _engine("dpdfnet2", 9, 1)
+    other.set_option("dfp_ps", dfp_ps)
     other.state_import(0, flat)
     assert np.array_equal(other.state_export(0), flat)
     a = eng.step_spec_host(X[5])
