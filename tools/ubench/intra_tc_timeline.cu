@@ -23,7 +23,10 @@ int main(int argc, char** argv) {
   cudaMemset(tl, 0, T * 12 * 8);
   IntraTcParams p{};
   p.x[0] = p.x[1] = x; p.hcat[0] = p.hcat[1] = hcat; p.Fp[0] = T; p.Fp[1] = 8;
-  p.wimg[0] = p.wimg[1] = w; p.bias[0] = p.bias[1] = bias; p.B = B; p.tiles = (B + 127) / 128; p.tl = tl;
+  p.wimg[0] = p.wimg[1] = w; p.bias[0] = p.bias[1] = bias; p.B = B; p.tiles = (B + 127) / 128;
+#ifdef ITC_TIMELINE
+  p.tl = tl;
+#endif
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
