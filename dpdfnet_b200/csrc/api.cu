@@ -294,6 +294,9 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   if (cudaStreamCreateWithFlags(&e.own_stream, cudaStreamDefault) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "stream creation failed"));
   for (int l = 0; l < Engine::MAX_LANES; ++l)
     if (cudaStreamCreateWithFlags(&e.lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e.br_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.br_fork[l], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.br_join[l], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.lane_done[l], cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(DPDF_ERR_CUDA, "lane stream creation failed"));
   if (cudaEventCreateWithFlags(&e.lane_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "event creation failed"));
@@ -322,6 +325,9 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
   for (auto& g : e.lane_graphs) cudaGraphExecDestroy(g.second);
   for (int l = 0; l < Engine::MAX_LANES; ++l) {
     if (e.lane_stream[l]) cudaStreamDestroy(e.lane_stream[l]);
+    if (e.br_stream[l]) cudaStreamDestroy(e.br_stream[l]);
+    if (e.br_fork[l]) cudaEventDestroy(e.br_fork[l]);
+    if (e.br_join[l]) cudaEventDestroy(e.br_join[l]);
     if (e.lane_done[l]) cudaEventDestroy(e.lane_done[l]);
   }
   if (e.lane_fork) cudaEventDestroy(e.lane_fork);
@@ -450,12 +456,27 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     pr[1].addend = c.hdf2; pr[1].lda = H;
     RUN("gl", launch_gl(e, pr, 2, B, st)); ++n;
   }
+  // The two decoder tails are independent until the synthesis kernel: the deep-filter coefficients (df_out linear +
+  // pathway conv) run on a forked stream beside the ERB decoder's transposed-conv stack (graph capture turns the events
+  // into dependencies); sequential while timing with events.
+  cudaStream_t sb = st;
+  const bool fork = e.decoder_fork && !e.timing;
+  if (fork) {
+    cudaEventRecord(e.br_fork[e.cur_lane], st);
+    sb = e.br_stream[e.cur_lane];
+    cudaStreamWaitEvent(sb, e.br_fork[e.cur_lane], 0);
+  }
   {
-    GLProblem pr[2];
-    int np = 0;
-    pr[np++] = glp(w.df_out, c.cc, H, c.co, NDF * 2 * ORD, 2);
-    if (d.hr48) pr[np++] = glp(w.erbdec_fc, c.ed, 512, c.ed2, d.fe[3] * C, 1);
-    RUN("gl", launch_gl(e, pr, np, B, st)); ++n;
+    GLProblem q = glp(w.df_out, c.cc, H, c.co, NDF * 2 * ORD, 2);
+    RUN("gl", launch_gl(e, &q, 1, B, sb)); ++n;
+  }
+  if (e.dfp_ps) { RUN("df_pathway", launch_df_pathway_ps(e, B, sb)); }
+  else { RUN("df_pathway", launch_df_pathway(e, B, sb)); }
+  ++n;
+  if (fork) cudaEventRecord(e.br_join[e.cur_lane], sb);
+  if (d.hr48) {
+    GLProblem q = glp(w.erbdec_fc, c.ed, 512, c.ed2, d.fe[3] * C, 1);
+    RUN("gl", launch_gl(e, &q, 1, B, st)); ++n;
   }
   {
     const float* edv = d.hr48 ? c.ed2 : c.ed;
@@ -467,9 +488,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     RUN("sepconv", sepconv(e, &q, 1, B, st)); ++n;
   }
   RUN("conv0_out", launch_conv0_out(e, B, st)); ++n;
-  if (e.dfp_ps) { RUN("df_pathway", launch_df_pathway_ps(e, B, st)); }
-  else { RUN("df_pathway", launch_df_pathway(e, B, st)); }
-  ++n;
+  if (fork) cudaStreamWaitEvent(st, e.br_join[e.cur_lane], 0);
   RUN("synthesis", launch_synthesis(e, B, st)); ++n;
   e.pdl_now = false;
   e.launches = n;
@@ -996,6 +1015,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "sep_tc") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "sep_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
     e.sep_tc = value;
+    drop_graphs(e);
+  } else if (strcmp(key, "decoder_fork") == 0) {
+    e.decoder_fork = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "dfp_ps") == 0) {
     e.dfp_ps = value ? 1 : 0;                      // switch only on freshly reset streams: the two forms keep different state

@@ -185,6 +185,9 @@ struct Engine {
   std::map<int, cudaGraphExec_t> lane_graphs; // keyed by B * MAX_LANES + lane: one hop of one lane (free-running lanes of a multi-hop run)
   int launches_per_lane = 0;
   // post kernel overlapped with the intra sweep: per-lane progress counters [lane][2][2][tiles]
+  int decoder_fork = 1;           // run the deep-filter coefficient tail beside the ERB decoder's conv stack (forked stream)
+  cudaStream_t br_stream[MAX_LANES] = {};
+  cudaEvent_t br_fork[MAX_LANES] = {}, br_join[MAX_LANES] = {};
   int dfp_ps = 0;                 // df pathway conv as pending partial sums: 38 KB of accumulator traffic instead of the 120 KB c0 ring
                                   // read per stream-hop, but measured slower (0.48 vs 0.27 ms at 8192 streams: the 50-value
                                   // reduce-scatter and the dependent read-modify-writes cost more than the ring read saves)
