@@ -84,7 +84,7 @@ PYEOF
       done ;;
     ncuall)
       timeout 1500 ncu --set full --clock-control none --import-source on -s 300 -c 60 \
-        -f -o $OUT/${TAG}_allkernels python bench.py --steps 8 --warmup 8 --no-graph --profile-only \
+        -f -o $OUT/${TAG}_allkernels python bench.py --steps 8 --warmup 8 --no-graph --profile-only --lanes 1 \
         > $OUT/${TAG}_ncu_all.log 2>&1
       echo "ncuall exit $?" ;;
   esac
