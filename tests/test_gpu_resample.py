@@ -21,6 +21,9 @@ def test_batch_resampler_matches_resample_poly(sr_in, sr_out):
     one = rs.resample(xd).cpu().numpy()
     assert one.shape == ref.shape
     assert np.abs(one - ref).max() < 2e-5                               # FP32 taps and accumulation vs float64
+    from oracle.resample_np import resample_direct
+    from dpdfnet_b200.resample import design_taps
+    assert np.abs(one[0] - resample_direct(x[0], rs.up, rs.down, design_taps(rs.up, rs.down))).max() < 2e-5
     # streamed in ragged chunks (including chunks shorter than the filter support) == one shot, bit for bit
     rs.reset()
     parts, pos = [], 0
