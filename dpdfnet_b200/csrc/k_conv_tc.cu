@@ -8,6 +8,8 @@
 // (one bulk copy), and the epilogue is thread = (TMEM lane = row, 32 columns): bias + ReLU -> XOR-swizzled FP32
 // staging (over the dead images) -> coalesced store.  ~50 KB of shared memory and 64 TMEM columns per CTA: three to
 // four CTAs per SM hide the prologue's load latency.
+#include <algorithm>
+
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -17,7 +19,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int SCT_NT = 256;
+// Threads per CTA (template parameter NT): the prologue is a per-thread serial chain (address math, three dependent
+// loads, split) per row, so rows per thread set the kernel's latency (tools/ubench/sepconv_tc_timeline.cu): 512
+// threads x 4 rows when the grid is small (latency bound), 256 threads x 8 rows at 3 CTAs per SM when it is not.
 constexpr int SCT_ROWS = 128;
 constexpr int SCT_IMG = SCT_ROWS * 64 * 2;       // bytes of one FP16 [128][64] image
 constexpr int SCT_OFF_W = 2 * SCT_IMG;           // weight slab: hi | lo, 16 KB
@@ -43,7 +47,9 @@ struct SepTcParams {
 #define STL(slot) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 3) k_sepconv_tc(SepTcParams p) {
+  constexpr int SCT_NT = NT, SCT_RPT = NT / 16;               // row stride of a thread: rows rsub, rsub + SCT_RPT, ...
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -90,8 +96,8 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
       pb = __ldg(reinterpret_cast<const float4*>(q.pb + c));
     }
 #pragma unroll
-    for (int i = 0; i < SCT_ROWS / 16; ++i) {
-      const int r = rsub + 16 * i;
+    for (int i = 0; i < SCT_ROWS / SCT_RPT; ++i) {
+      const int r = rsub + SCT_RPT * i;
       const int row = (int)row0 + r;                          // < 2^31 rows: 32-bit index math (64-bit division is ~100 instructions)
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < (int)nrows) {
@@ -175,17 +181,18 @@ __global__ void __launch_bounds__(SCT_NT, 3) k_sepconv_tc(SepTcParams p) {
   tc_fence_after();
   STL(4);
 
-  // epilogue: thread = (row = TMEM lane, 32-column half); bias + ReLU into the swizzled FP32 staging tile
+  // epilogue: thread = (row = TMEM lane, 16-column group); bias + ReLU into the swizzled FP32 staging tile
   {
     const int qd = warp & 3, ch = warp >> 2, row = qd * 32 + lane;
-    const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + ch * 32;
+    constexpr int CPW = 64 / (NT / 128);                        // accumulator columns per warp: 16 or 32
+    const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + ch * CPW;
 #pragma unroll
-    for (int c16 = 0; c16 < 2; ++c16) {
+    for (int c16 = 0; c16 < CPW / 16; ++c16) {
       float v[16];
       tmem_ld16(ta + c16 * 16, v);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int col = ch * 32 + c16 * 16 + j * 4;
+        const int col = ch * CPW + c16 * 16 + j * 4;
         const float4 o = make_float4(fmaxf(v[j * 4] + bs[col], 0.f), fmaxf(v[j * 4 + 1] + bs[col + 1], 0.f),
                                      fmaxf(v[j * 4 + 2] + bs[col + 2], 0.f), fmaxf(v[j * 4 + 3] + bs[col + 3], 0.f));
         *reinterpret_cast<float4*>(Aimg + row * 256 + ((((col >> 2)) ^ (row & 15)) << 4)) = o;
@@ -227,11 +234,13 @@ void launch_sepconv_tc(Engine& e, const SepProblem* probs, int nprob, int B, cud
     p.prob[i].tile0 = tiles;
     tiles += (int)(((long long)B * probs[i].Fout + SCT_ROWS - 1) / SCT_ROWS);
   }
-  launch_k(e, k_sepconv_tc, dim3(tiles), dim3(SCT_NT), SCT_SMEM, st, p);
+  if (std::max(B, e.total_B) < 4096) launch_k(e, k_sepconv_tc<512>, dim3(tiles), dim3(512), SCT_SMEM, st, p);
+  else launch_k(e, k_sepconv_tc<256>, dim3(tiles), dim3(256), SCT_SMEM, st, p);
 }
 
 void init_conv_tc_kernels() {
-  cudaFuncSetAttribute(k_sepconv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCT_SMEM);
+  cudaFuncSetAttribute(k_sepconv_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCT_SMEM);
+  cudaFuncSetAttribute(k_sepconv_tc<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCT_SMEM);
 }
 
 }  // namespace dpdf

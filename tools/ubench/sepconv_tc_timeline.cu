@@ -21,7 +21,7 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-    k_sepconv_tc<<<tiles, SCT_NT, SCT_SMEM>>>(p);
+    k_sepconv_tc<512><<<tiles, 512, SCT_SMEM>>>(p);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
