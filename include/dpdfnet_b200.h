@@ -122,10 +122,13 @@ int dpdf_state_import(dpdf_engine* e, int32_t slot, const float* flat_host);
 int dpdf_debug_tensor(dpdf_engine* e, const char* name, float* out_host, size_t max_floats,
                       size_t* numel_per_stream);    /* stage output of the last step, [B, numel] */
 int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the last step */
-/* Options (all default to the measured-best choice): "graph" 0/1 one CUDA graph per hop; "lanes" 0 = auto, 1..8
- * kernel-chain lanes per batched step; "free_lanes" 0/1 lanes of a multi-hop run replay their own graphs on their own
- * streams; "intra_tc" / "sep_tc" / "gru_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch size; "post_tc" 0/1; "intra_bt"
- * 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel. */
+/* Options (all default to the measured-best choice): "graph" 0/1 one CUDA graph per hop;
+ * "lanes" 0 = auto, 1..8 kernel-chain lanes per batched step; "free_lanes" 0/1 lanes of a multi-hop run replay their
+ * own graphs on their own streams; "overlap" 0/1 (+ "overlap_max") post kernel overlapped with the intra sweep;
+ * "decoder_fork" 0/1 decoder tails on forked streams; "intra_tc" / "sep_tc" / "gru_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch
+ * size (+ "intra_tc_min"); "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel; "dfp_ps" 0/1
+ * df pathway conv as pending partial sums (switch only on freshly reset streams); "pdl" 0/1 chain every kernel of a
+ * hop with programmatic dependent launches. */
 int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value);
 int dpdf_time_kernels(dpdf_engine* e, int32_t B, int32_t iters, float* ms_out, const char** names_out,
                       int32_t max_entries, int32_t* n_entries); /* per-kernel CUDA-event timing */
