@@ -296,6 +296,13 @@ def run_ours(args):
             torch.cuda.synchronize()
             hl = np.array([evl[i].elapsed_time(evl[i + 1]) for i in range(40)])
             rec["hop_latency_ms"] = {"p50": float(np.percentile(hl, 50)), "p99": float(np.percentile(hl, 99)), "max": float(hl.max())}
+            if rank == 0:       # per-kernel device time at this batch (one chain, CUDA events): the throughput-bound regime
+                ktl = engl.time_kernels(Bl, iters=2)
+                rec["kernel_ms"] = {k: round(v, 4) for k, v in sorted(ktl.items(), key=lambda kv: -kv[1])}
+                macs = (spec.fe[3] + 48) * 2 * 2 * 192 * 64           # intra-GRU MACs per stream per launch
+                if spec.n_blocks and "dprnn_intra" in ktl:
+                    tf = 2.0 * macs * Bl / (ktl["dprnn_intra"] / spec.n_blocks * 1e-3) / 1e12
+                    rec["intra_tensor_tflops"] = {"algorithmic": tf, "issued_fp16_split": 3.0 * tf}
             ladder.append(rec)
             engl.close()
             del engl, xl, yl
@@ -307,7 +314,10 @@ def run_ours(args):
                      "realtime_streams_total": world * best["streams_per_gpu"] if best else None,
                      "ms_per_hop_at_that_batch": best["ms_per_hop"] if best else None,
                      "p99_hop_latency_ms_at_that_batch": best["hop_latency_ms"]["p99"] if best else None,
-                     "criterion": "largest ladder batch whose mean AND p99 lock-step hop latency are below the hop period"}
+                     "criterion": "largest ladder batch whose mean AND p99 lock-step hop latency are below the hop period",
+                     "intra_tensor_tflops_at_that_batch": best.get("intra_tensor_tflops") if best else None,
+                     "note": "ladder[*].intra_tensor_tflops: FP32-equivalent TFLOP/s of k_dprnn_intra_tc (x3 = issued FP16 tensor "
+                             "FLOP/s); against the measured bf16 peak this is the throughput-regime counterpart of roofline_tensor"}
         eng = Engine(spec, ck, max_streams=B, device=local)
 
     if rank != 0:
