@@ -94,8 +94,11 @@ def enhance_batch(clips: Sequence[np.ndarray], sample_rate: int, *, model: str =
     attenuation like the reference (``audio.py:50-76``: ``alpha * noisy + (1 - alpha) * enhanced``, alpha =
     10^(-dB/20)); the offline-exact output is sample-aligned with its input and the STFT pair reconstructs exactly, so
     the blend is done on the waveform.
+
+    Clips of ``hop`` samples or fewer cannot be reflect-padded by the offline model (``torch.stft(center=True)`` raises
+    on them, model/modules.py:360-369); they come back as silence of the input length, with a ``UserWarning``.
     """
-    from .audio import ensure_sample_rate, to_mono
+    from .audio import _validate_attn_limit_db, ensure_sample_rate, to_mono
     from .offline import enhance_offline_exact_ragged
     from .onnx_backend import create_session
     resolved = resolve_model(model=model, onnx_path=onnx_path)
@@ -107,10 +110,12 @@ def enhance_batch(clips: Sequence[np.ndarray], sample_rate: int, *, model: str =
     waves = _batch_resample([to_mono(np.asarray(c, dtype=np.float32)) for c in clips], int(sample_rate), model_sr, engine.device)
     if not exact_offline:
         raise NotImplementedError("only the offline-exact schedule is implemented for batches")
-    if attn_limit_db is not None and attn_limit_db < 0:
-        raise ValueError("attn_limit_db must be >= 0.")                        # audio.py:45-46
+    attn_limit_db = _validate_attn_limit_db(attn_limit_db)                    # NaN / negative: ValueError (audio.py:41-47)
     hop = engine.spec.hop
     short = [i for i, w in enumerate(waves) if w.size <= hop]
+    if short:
+        import warnings
+        warnings.warn(f"{len(short)} clip(s) of <= {hop} samples are too short for the offline model and are returned as silence")
     outs = enhance_offline_exact_ragged(engine, [w for w in waves if w.size > hop])
     it = iter(outs)
     res = []

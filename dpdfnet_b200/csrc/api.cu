@@ -47,9 +47,12 @@ static int parse_blob(Engine& e, const void* blob, size_t nbytes, const float** 
   long long n;
   memcpy(&n, p + 8, 8);
   const size_t rec = NAME_LEN + 16;
+  if (n <= 0 || (unsigned long long)n > (nbytes - 16) / rec)        // before any n * rec product: no wrap-around
+    return fail(DPDF_ERR_WEIGHTS, "truncated weight blob header");
   size_t head = 16 + (size_t)n * rec;
   head += (128 - head % 128) % 128;
-  if (n <= 0 || head > nbytes) return fail(DPDF_ERR_WEIGHTS, "truncated weight blob header");
+  if (head > nbytes) return fail(DPDF_ERR_WEIGHTS, "truncated weight blob header");
+  const size_t avail = (nbytes - head) / sizeof(float);             // payload floats actually present
   size_t maxend = 0;
   for (long long i = 0; i < n; ++i) {
     const char* r = p + 16 + i * rec;
@@ -59,11 +62,12 @@ static int parse_blob(Engine& e, const void* blob, size_t nbytes, const float** 
     long long off, numel;
     memcpy(&off, r + NAME_LEN, 8);
     memcpy(&numel, r + NAME_LEN + 8, 8);
-    if (off < 0 || numel < 0) return fail(DPDF_ERR_WEIGHTS, "corrupt entry %s", name);
+    if (off < 0 || numel < 0 || (size_t)off > avail || (size_t)numel > avail - (size_t)off)   // overflow-safe bounds
+      return fail(DPDF_ERR_WEIGHTS, "corrupt or truncated entry %s", name);
     e.wtable[name] = {(size_t)off, (size_t)numel};
-    if ((size_t)(off + numel) > maxend) maxend = off + numel;
+    if ((size_t)off + (size_t)numel > maxend) maxend = (size_t)off + (size_t)numel;
   }
-  if (head + maxend * sizeof(float) > nbytes) return fail(DPDF_ERR_WEIGHTS, "truncated weight blob payload");
+  if (maxend > avail) return fail(DPDF_ERR_WEIGHTS, "truncated weight blob payload");
   *payload = reinterpret_cast<const float*>(p + head);
   *payload_floats = (nbytes - head) / sizeof(float);
   return 0;
@@ -291,6 +295,10 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   if (cudaMalloc(&e.progress_dev, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int)) != cudaSuccess)
     return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(progress) failed"));
   cudaMemset(e.progress_dev, 0, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int));
+  if (cudaHostAlloc(&e.err_host, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&e.err_dev, e.err_host, 0) != cudaSuccess)
+    return bail(fail(DPDF_ERR_NOMEM, "cudaHostAlloc(error words) failed"));
+  memset(e.err_host, 0, 4 * sizeof(int));
   if (cudaStreamCreateWithFlags(&e.own_stream, cudaStreamDefault) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "stream creation failed"));
   for (int l = 0; l < Engine::MAX_LANES; ++l)
     if (cudaStreamCreateWithFlags(&e.lane_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
@@ -334,6 +342,7 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
   cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_lanes); cudaFree(e.progress_dev);
   cudaFree(e.slots_dev); cudaFree(e.flags_dev); cudaFree(e.stage_in); cudaFree(e.stage_out);
   if (e.pinned) cudaFreeHost(e.pinned);
+  if (e.err_host) cudaFreeHost(e.err_host);
   if (e.own_stream) cudaStreamDestroy(e.own_stream);
   delete h;
   return 0;
@@ -505,6 +514,35 @@ static int check_batch(Engine& e, int B) {
   return 0;
 }
 
+// Errors raised by kernels of earlier hops (Engine::err_host, mapped memory the kernels store to): the overlapped post
+// kernel gave up waiting for its sweep, or an activation left the FP16 operand range.  Either way the recurrent state
+// of the affected streams is no longer the reference's; the words are cleared once reported.  Called after the stream
+// synchronisation of the *_host entry points (errors of THIS hop) and at the start of every device-pointer entry
+// point (errors of hops enqueued earlier and finished since).
+static int check_device_errors(Engine& e) {
+  volatile int* w = e.err_host;
+  if (!w) return 0;
+  const int overlap = w[DPDF_ERRW_OVERLAP], range = w[DPDF_ERRW_RANGE];
+  if (!overlap && !range) return 0;
+  w[DPDF_ERRW_OVERLAP] = 0;
+  w[DPDF_ERRW_RANGE] = 0;
+  if (overlap)
+    return fail(DPDF_ERR_CUDA, "a DPRNN post tile timed out waiting for the intra-frame sweep (GPU preempted or shared?): the "
+                               "hop is invalid, reset the streams of that batch; set option overlap=0 to use full grid dependencies");
+  return fail(DPDF_ERR_CUDA, "an activation exceeded the FP16 operand range (|x| > 65504) or was non-finite in a tensor-core "
+                             "converter: outputs of that hop are invalid; reset the affected streams (option *_tc=0 selects the FP32 kernels)");
+}
+
+extern "C" int dpdf_poll_error(dpdf_engine* h, int32_t synchronize) {
+  if (!h) return fail(DPDF_ERR_INVALID, "NULL engine");
+  Engine& e = h->e;
+  if (synchronize) {
+    CU(cudaSetDevice(e.device));
+    CU(cudaDeviceSynchronize());
+  }
+  return check_device_errors(e);
+}
+
 static void drop_graphs(Engine& e) {
   for (auto& g : e.graphs) cudaGraphExecDestroy(g.second);
   for (auto& g : e.lane_graphs) cudaGraphExecDestroy(g.second);
@@ -657,6 +695,7 @@ static int set_io(Engine& e, const float* in, long long in_stride, float* out, l
     io[l].in_stride = in_stride; io[l].out_stride = out_stride;
     io[l].slot_ids = slot_ids ? slot_ids + r0 : nullptr; io[l].flags = flags ? flags + r0 : nullptr;
     io[l].t_in = 0; io[l].t_out = 0; io[l].mode = mode; io[l].slot_base = r0;
+    io[l].err = e.err_dev;
   }
   CU(cudaMemcpyAsync(e.io_lanes, io, sizeof(IoDesc) * L, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
   return 0;
@@ -668,6 +707,7 @@ extern "C" int dpdf_step_spec(dpdf_engine* h, const float* spec_in, float* spec_
   Engine& e = h->e;
   if (int rc = check_batch(e, B)) return rc;
   CU(cudaSetDevice(e.device));
+  if (int rc = check_device_errors(e)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (int rc = set_io(e, spec_in, 0, spec_out, 0, slot_ids, flags, 1, B, st)) return rc;
   e.last_B = B;
@@ -683,6 +723,7 @@ extern "C" int dpdf_run_pcm(dpdf_engine* h, const float* pcm_in, int64_t in_stri
   if (in_stride < (int64_t)T * e.d.hop || out_stride < (int64_t)T * e.d.hop)
     return fail(DPDF_ERR_INVALID, "row stride smaller than T*hop");
   CU(cudaSetDevice(e.device));
+  if (int rc = check_device_errors(e)) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (int rc = set_io(e, pcm_in, in_stride, pcm_out, out_stride, slot_ids, flags, 0, B, st)) return rc;
   e.last_B = B;
@@ -775,7 +816,7 @@ extern "C" int dpdf_step_spec_host(dpdf_engine* h, const float* spec_in, float* 
   if (int rc = dpdf_step_spec(h, e.stage_in, e.stage_out, s_dev, f_dev, B, st)) return rc;
   CU(cudaMemcpyAsync(spec_out, e.stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  return 0;
+  return check_device_errors(e);
 }
 
 extern "C" int dpdf_run_pcm_host(dpdf_engine* h, const float* pcm_in, float* pcm_out, const int32_t* slot_ids, int32_t B,
@@ -794,7 +835,7 @@ extern "C" int dpdf_run_pcm_host(dpdf_engine* h, const float* pcm_in, float* pcm
   if (int rc = dpdf_run_pcm(h, e.stage_in, (int64_t)T * e.d.hop, e.stage_out, (int64_t)T * e.d.hop, s_dev, nullptr, B, T, st)) return rc;
   CU(cudaMemcpyAsync(pcm_out, e.stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  return 0;
+  return check_device_errors(e);
 }
 
 extern "C" int dpdf_step_pcm_host(dpdf_engine* h, const float* pcm_in, float* pcm_out, const int32_t* slot_ids,
@@ -812,7 +853,7 @@ extern "C" int dpdf_step_pcm_host(dpdf_engine* h, const float* pcm_in, float* pc
   if (int rc = dpdf_run_pcm(h, e.stage_in, e.d.hop, e.stage_out, e.d.hop, s_dev, f_dev, B, 1, st)) return rc;
   CU(cudaMemcpyAsync(pcm_out, e.stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  return 0;
+  return check_device_errors(e);
 }
 
 // ---------------------------------------------------------------------------------------------

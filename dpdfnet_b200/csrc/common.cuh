@@ -31,7 +31,12 @@ struct IoDesc {
   int t_out;              // hop index read by the synthesis kernel
   int mode;               // 0 = pcm, 1 = spec
   int slot_base;          // identity slot mapping: slot = slot_base + b (lanes of one batched step, api.cu:run_step)
+  int* err;               // device-visible error words in mapped host memory (api.cu:check_device_errors):
+                          //   [0] overlapped post kernel gave up waiting for the sweep (tile skipped, hop invalid)
+                          //   [1] an activation left the FP16 range / was non-finite in a tensor-core operand converter
 };
+#define DPDF_ERRW_OVERLAP 0
+#define DPDF_ERRW_RANGE 1
 
 __device__ __forceinline__ int io_slot(const IoDesc* io, int b) {
   return io->slot_ids ? __ldg(io->slot_ids + b) : io->slot_base + b;

@@ -201,6 +201,10 @@ struct Engine {
   int cur_lane = 0;
   int* progress_dev = nullptr;
   int progress_tiles = 0;
+  // Device-raised error words (IoDesc::err) in mapped pinned host memory: the kernels store, the host polls without
+  // a copy (api.cu:check_device_errors).  [0] overlap wait timed out, [1] FP16 operand range exceeded / non-finite.
+  int* err_host = nullptr;
+  int* err_dev = nullptr;
   int free_lanes = 1;             // multi-hop runs: every lane replays its own graph on its own stream, joined once at the end
   std::vector<std::pair<std::string, float>> ktimes;
   bool timing = false;

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 3) k_sepconv_tc(SepTcParam
   if (warp == 0) tmem_alloc<64>(tmem_slot);
   if (tid < 64) bs[tid] = __ldg(q.bias + tid);
   STL(1);
+  uint32_t ovf = 0;                                        // FP16 range guard of the operand converter (tc_common.cuh)
 
   // prologue: A[row][c] -> operand images.  Thread = (channel quad g, row r & 7 ...): it keeps the same 4 channels for
   // all of its 8 rows (taps and pathway affine loaded once); the 8 lanes of a channel quad write 8 consecutive rows of
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 3) k_sepconv_tc(SepTcParam
       uint2 h, l;
       split2_f16(acc.x, acc.y, h.x, l.x);
       split2_f16(acc.z, acc.w, h.y, l.y);
+      ovf |= f16_nonfinite(h.x) | f16_nonfinite(h.y);
       unsigned char* dst = Aimg + (r >> 3) * 1024 + (g >> 1) * 128 + (r & 7) * 16 + (g & 1) * 8;
       *reinterpret_cast<uint2*>(dst) = h;
       *reinterpret_cast<uint2*>(dst + SCT_IMG) = l;
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 3) k_sepconv_tc(SepTcParam
     }
   }
   STL(6);
+  if (ovf) p.io->err[DPDF_ERRW_RANGE] = 1;
   if (warp == 0) tmem_dealloc<64>(tmem);
 }
 

@@ -89,6 +89,7 @@ struct IntraTcParams {
   int tiles;              // ceil(B / 128)
   int B;
   int* progress;          // [2 branches][2 dirs][tiles] completed steps of each CTA, or nullptr (overlapped post kernel)
+  int* err;               // engine error words (IoDesc::err), may be nullptr
 #ifdef ITC_TIMELINE
   long long* tl;          // [steps][12] SM-clock stamps of CTA 0 (tools/ubench/intra_tc_timeline.cu)
 #endif
@@ -173,6 +174,8 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   auto store_x1 = [&](int buf, const float (&v)[2][8], int i) {
     uint4 hi, lo;
     split8_f16(v[i], hi, lo);
+    // FP16 range guard (tc_common.cuh:f16_nonfinite); stored at once: a flag word would be a live register of the gate warps
+    if ((f16_nonfinite(hi.x) | f16_nonfinite(hi.y) | f16_nonfinite(hi.z) | f16_nonfinite(hi.w)) && p.err) p.err[DPDF_ERRW_RANGE] = 1;
     unsigned char* dst = Xsm + buf * 2 * A_IMG + img16_off(xr_[i], xkc);
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
@@ -458,6 +461,7 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.B = B;
   p.tiles = (B + 127) / 128;
   p.progress = e.overlap_now ? e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles : nullptr;
+  p.err = e.err_dev;
   launch_k(e, k_dprnn_intra_tc, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
 }
 

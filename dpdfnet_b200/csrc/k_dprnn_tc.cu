@@ -96,6 +96,9 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
   int bi, valid, fpos = 0;
   long long rbase, rstride;
+  uint32_t ovf = 0;                                        // FP16 range guard of the y converter (tc_common.cuh:f16_nonfinite)
+  __shared__ int s_abort;
+  if (tid == 0) s_abort = 0;
   if (p.progress) {
     const int tiles_e = p.br[1].Fp * p.stiles;
     bi = (int)blockIdx.x < tiles_e ? 1 : 0;
@@ -109,8 +112,16 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
       const volatile int* fw = p.progress + (bi * 2 + 0) * p.stiles + stile;   // branch index as in the intra kernel: 0 = df, 1 = erb
       const volatile int* bw = p.progress + (bi * 2 + 1) * p.stiles + stile;
       // the forward CTA has finished position f after f + 1 steps, the backward one after T - f; bounded wait (~2 s):
-      // a broken producer must show up as a failed parity test, not as a hung GPU
-      for (long long spin = 0; (*fw < fpos + 1 || *bw < T - fpos) && spin < (1ll << 23); ++spin) __nanosleep(256);
+      // a broken or preempted producer must show up as an error, not as a hung GPU - and never as stale data: on
+      // time-out the tile is SKIPPED (nothing read, nothing written) and the engine's error word is raised, which
+      // the host turns into DPDF_ERR_CUDA for this hop (api.cu:check_device_errors)
+      long long spin = 0;
+      for (; (*fw < fpos + 1 || *bw < T - fpos) && spin < (1ll << 23); ++spin) __nanosleep(256);
+      if (*fw < fpos + 1 || *bw < T - fpos) {
+        s_abort = 1;
+        p.io->err[DPDF_ERRW_OVERLAP] = 1;
+        __threadfence_system();
+      }
       __threadfence();                                     // acquire: the rows those counts cover are visible (loads below bypass L1)
     }
   } else {
@@ -146,6 +157,11 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   __syncthreads();                                       // barriers initialised, s_hoff visible
+  if (s_abort) {                                         // the sweep never delivered this tile's rows: skip it (see above)
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc<256>(*tmem_slot);
+    return;
+  }
 
   // ---- weight slab ring (thread 0 only) --------------------------------------------------------------------
   auto slab_src = [&](int i) -> const unsigned char* {
@@ -273,6 +289,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
       y[4] = v[c * 8 + 4] + xv[2 * c + 1].x; y[5] = v[c * 8 + 5] + xv[2 * c + 1].y; y[6] = v[c * 8 + 6] + xv[2 * c + 1].z; y[7] = v[c * 8 + 7] + xv[2 * c + 1].w;
       uint4 h, l;
       split8_f16(y, h, l);
+      ovf |= f16_nonfinite(h.x) | f16_nonfinite(h.y) | f16_nonfinite(h.z) | f16_nonfinite(h.w);
       const int off = img16_off(row, cg * 2 + c);
       *reinterpret_cast<uint4*>(y_hi + off) = h;
       *reinterpret_cast<uint4*>(y_hi + IMG + off) = l;
@@ -392,6 +409,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
       *reinterpret_cast<float4*>(q.xout + (rbase + r * rstride) * C + ch * 4) = *reinterpret_cast<const float4*>(RA + r * 256 + ((ch ^ (r & 15)) << 4));
   }
   PTL(7);
+  if (ovf) p.io->err[DPDF_ERRW_RANGE] = 1;
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 

@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(1024) k_synthesis(SynParams p) {
       else p.st.ola[(size_t)s_slot[bb] * hop + (n - hop)] = fr;
     }
   }
-  if (tid < nb) p.st.pos[s_slot[tid]] = s_pos[tid] + 1;
+  if (tid < nb) p.st.pos[s_slot[tid]] = (s_pos[tid] + 1) % 15;      // only pos % 3 and pos % 5 are ever used: no int32 wrap after 248 days
 }
 
 __global__ void k_prime(State st, int hop, const float* pcm, long long stride, const int* slot_ids, int B) {

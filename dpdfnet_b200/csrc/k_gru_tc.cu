@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
     // so a warp's 8-byte stores fill two whole 128-byte core matrices
     const int g = (tid >> 3) & 15;
     const int rsub = (tid & 7) | ((tid >> 7) << 3);
+    uint32_t ovf = 0;                                         // FP16 range guard (tc_common.cuh:f16_nonfinite)
     for (int s = 0; s < 8; ++s) {
       const int buf = s & 1, k0 = (s & 3) * 64 + g * 4;
       const bool hpart = s >= 4;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
         uint2 h, l;
         split2_f16(v[i].x, v[i].y, h.x, l.x);
         split2_f16(v[i].z, v[i].w, h.y, l.y);
+        ovf |= f16_nonfinite(h.x) | f16_nonfinite(h.y);
         unsigned char* dst = img + (r >> 3) * 1024 + (g >> 1) * 128 + (r & 7) * 16 + (g & 1) * 8;
         *reinterpret_cast<uint2*>(dst) = h;
         *reinterpret_cast<uint2*>(dst + GT_AIMG) = l;
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
       if (buf == 0) asm volatile("bar.arrive 1, %0;" ::"n"(GT_NT) : "memory");
       else asm volatile("bar.arrive 2, %0;" ::"n"(GT_NT) : "memory");
     }
+    if (ovf) p.io->err[DPDF_ERRW_RANGE] = 1;
     // ---- epilogue: thread = (stream row = TMEM lane, 32 units) ----------------------------------------------------
     mbar_wait(done + 7, 0);
     tc_fence_after();

@@ -143,6 +143,10 @@ __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint3
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// Non-zero when either half of a packed FP16 pair has an all-ones exponent (inf / NaN): the FP32 value was beyond
+// +-65504 or already non-finite.  The converters OR this into a per-thread word and raise IoDesc::err[1] at the end of
+// the kernel, so an out-of-range activation surfaces as DPDF_ERR_CUDA instead of silently poisoning a stream's state.
+__device__ __forceinline__ uint32_t f16_nonfinite(uint32_t packed) { return ((packed & 0x7fff7fffu) + 0x04000400u) & 0x80008000u; }
 // eight consecutive K elements of one row = one 16-byte core-matrix row
 __device__ __forceinline__ void split8_f16(const float (&v)[8], uint4& hi, uint4& lo) {
   split2_f16(v[0], v[1], hi.x, lo.x);

@@ -65,6 +65,7 @@ C_API = {
     "dpdf_resampler_process": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
                                               ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64),
                                               ctypes.c_void_p]),
+    "dpdf_poll_error": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32]),
     "dpdf_last_error": (ctypes.c_char_p, []),
     "dpdf_version": (ctypes.c_char_p, []),
 }
@@ -166,10 +167,10 @@ class Engine:
         if rc != 0:
             _raise(self._lib, rc)
 
-    @staticmethod
-    def _stream() -> int:
+    def _stream(self) -> int:
+        """torch's current stream ON THE ENGINE'S DEVICE (not on whatever device is current)."""
         import torch
-        return int(torch.cuda.current_stream().cuda_stream)
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _dev_int(self, a, B):
         """slot ids / flags given as None, torch cuda int32 tensor, or host sequence."""
@@ -186,13 +187,16 @@ class Engine:
 
     # ----- device-tensor entry points (torch tensors are containers only) --
     def reset(self, slots: Optional[Sequence[int]] = None):
+        """``None`` resets every slot; a (possibly empty) list resets exactly those slots."""
         if slots is None:
             self._check(self._lib.dpdf_reset(self._handle, None, 0, self._stream()))
-        else:
-            arr = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
-            self._check(self._lib.dpdf_reset(self._handle, arr.ctypes.data, arr.size, self._stream()))
-            import torch
-            torch.cuda.current_stream().synchronize()       # host slot list must outlive the async copy
+            return
+        arr = np.ascontiguousarray(np.asarray(slots, dtype=np.int32).reshape(-1))
+        if arr.size == 0:                # the C ABI reads n <= 0 as "all slots": an empty list must reset nothing
+            return
+        self._check(self._lib.dpdf_reset(self._handle, arr.ctypes.data, arr.size, self._stream()))
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()       # host slot list must outlive the async copy
 
     def step_spec(self, spec_in, slot_ids=None, flags=None, out=None):
         import torch
@@ -280,7 +284,7 @@ class Engine:
         import torch
         x = torch.as_tensor(np.ascontiguousarray(pcm, dtype=np.float32), device=f"cuda:{self.device}")
         self.prime_pcm(x, slot_ids)
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
 
     # ----- state ----------------------------------------------------------
     @property
@@ -305,6 +309,10 @@ class Engine:
         out = np.empty((B, n.value), np.float32)
         self._check(self._lib.dpdf_debug_tensor(self._handle, name.encode(), out.ctypes.data, out.size, ctypes.byref(n)))
         return out
+
+    def poll_error(self, synchronize: bool = True):
+        """Raise ``RuntimeError`` if a kernel of an earlier hop flagged an invalid hop (see dpdf_poll_error)."""
+        self._check(self._lib.dpdf_poll_error(self._handle, int(bool(synchronize))))
 
     @property
     def kernel_launches(self) -> int:

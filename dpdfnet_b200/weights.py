@@ -451,10 +451,16 @@ def pack_checkpoint(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> bytes:
 
 def load_checkpoint_file(path) -> Dict[str, np.ndarray]:
     """Load a reference ``.pth`` (plain ``state_dict`` or ``{'state_dict': ...}``) as numpy."""
+    import os
     import torch
     try:
         obj = torch.load(path, map_location="cpu", weights_only=True)
-    except Exception:
+    except Exception as exc:
+        # The reference's inference package never unpickles; only its export script falls back to a full pickle load
+        # (export_dpdfnet_to_onnx.py:103-106).  Arbitrary-code pickles are therefore an explicit opt-in here.
+        if os.environ.get("DPDFNET_B200_ALLOW_PICKLE") != "1":
+            raise ValueError(f"{path} is not a plain tensor state_dict (safe load failed: {exc}); set "
+                             "DPDFNET_B200_ALLOW_PICKLE=1 to unpickle a trusted checkpoint") from exc
         obj = torch.load(path, map_location="cpu", weights_only=False)
     if isinstance(obj, dict) and "state_dict" in obj and not any(k.startswith("enc.") for k in obj):
         obj = obj["state_dict"]

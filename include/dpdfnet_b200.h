@@ -148,6 +148,15 @@ int64_t dpdf_resampler_pending(const dpdf_resampler* r, int32_t n_new, int32_t f
 int dpdf_resampler_process(dpdf_resampler* r, const float* in_dev, int64_t in_stride, int32_t n_new, float* out_dev,
                            int64_t out_stride, int32_t B, int32_t flush, int64_t* n_out, void* cuda_stream);
 
+/* Errors raised ON THE DEVICE by earlier hops: a DPRNN post tile that timed out waiting for the overlapped sweep, or an
+ * activation outside the FP16 operand range / non-finite in a tensor-core converter (the FP16 hi/lo split of
+ * DESIGN.md section 3 is exact only inside +-65504).  Returns 0 or DPDF_ERR_CUDA with the message in dpdf_last_error()
+ * and clears the condition.  `synchronize` != 0 waits for the device first.  The *_host entry points call it after
+ * their own synchronisation (so they report errors of the hop they ran); the device-pointer entry points call it on
+ * entry (so they report errors of hops that finished since the previous call).  The reference raises nothing
+ * comparable: ONNX Runtime computes in FP32 throughout. */
+int dpdf_poll_error(dpdf_engine* e, int32_t synchronize);
+
 const char* dpdf_last_error(void);
 const char* dpdf_version(void);
 
