@@ -357,6 +357,7 @@ class StreamGroup:
             return y
         n = y.shape[1]
         if n == 0:
+            torch.cuda.current_stream(self._dev).synchronize()      # the pinned input block is reused by the next call
             return np.zeros((self.streams, 0), np.float32)
         if self._pin_out is None or self._pin_out.shape[1] < n:
             self._pin_out = torch.empty((self.streams, n), dtype=torch.float32).pin_memory()

@@ -16,7 +16,7 @@ for w in $WHAT; do
       DPDF_OPTIONS=intra_tc=1 timeout 600 python tools/gpu_debug.py dpdfnet2 > $OUT/${TAG}_debug_tc.log 2>&1; tail -25 $OUT/${TAG}_debug_tc.log ;;
     quick)   # kernel-time table at two batch sizes, no ladder
       for b in 1024 8192; do
-        timeout 600 python bench.py --steps 50 --warmup 10 --no-ladder --batch $b --cpu-hops 2 --cpu-batch 16 2>&1 | python -c "
+        timeout 600 python bench.py --steps 50 --warmup 10 --no-ladder --no-extras --latency-hops 50 --batch $b --cpu-hops 2 --cpu-batch 16 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
@@ -32,7 +32,7 @@ for l in sys.stdin:
     configs)   # BASELINE.json configs[2..4]: other model sizes / 48 kHz (device-resident throughput + kernel table)
       for cfg in "dpdfnet8 4096" "dpdfnet2_48khz_hr 2048" "dpdfnet8_48khz_hr 2048" "dpdfnet2 1024"; do
         set -- $cfg
-        timeout 600 python bench.py --steps 40 --warmup 10 --no-ladder --model $1 --batch $2 --cpu-hops 2 --cpu-batch 16 2>&1 | python -c "
+        timeout 600 python bench.py --steps 40 --warmup 10 --no-ladder --no-extras --latency-hops 50 --model $1 --batch $2 --cpu-hops 2 --cpu-batch 16 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
@@ -81,6 +81,13 @@ PYEOF
           -f -o $OUT/${TAG}_$k python bench.py --steps 4 --warmup 4 --no-graph --profile-only --lanes 1 ${BENCH_ARGS:-} \
           > $OUT/${TAG}_ncu_$k.log 2>&1
         echo "ncu $k exit $?"
+      done ;;
+    ncubig)   # throughput regime: full captures of the dominant kernels at NCU_BATCH streams (one chain) for NCU_MODEL
+      for k in ${NCU_KERNELS:-k_dprnn_post_tc k_sepconv_tc k_dprnn_intra_tc}; do
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 2 \
+          -f -o $OUT/${TAG}_${NCU_MODEL:-dpdfnet4}_B${NCU_BATCH:-16384}_$k python bench.py --steps 3 --warmup 3 --no-graph --profile-only --lanes 1 \
+          --model ${NCU_MODEL:-dpdfnet4} --batch ${NCU_BATCH:-16384} > $OUT/${TAG}_ncubig_$k.log 2>&1
+        echo "ncubig $k exit $?"
       done ;;
     ncuall)
       timeout 1500 ncu --set full --clock-control none --import-source on -s 300 -c 60 \

@@ -71,8 +71,40 @@ def full(paths):
         print()
 
 
+def traffic(args):
+    """traffic <model> <batch> <rep...>: merge DRAM bytes per launch of every profiled kernel into profiles/ncu_traffic.json
+    (read by bench.py for roofline.traffic).  Kernel names are mapped to the bench's kernel_ms keys."""
+    import json
+    import os
+    model, batch, reps = args[0], int(args[1]), args[2:]
+    names = {"k_dprnn_intra_tc": "dprnn_intra", "k_dprnn_intra": "dprnn_intra", "k_dprnn_post_tc": "dprnn_post", "k_dprnn_post": "dprnn_post",
+             "k_sepconv_tc": "sepconv", "k_sepconv": "sepconv", "k_gru_tc": "gru", "k_gl": "gl", "k_analysis": "analysis",
+             "k_synthesis": "synthesis", "k_df_pathway": "df_pathway"}
+    out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "ncu_traffic.json")
+    recs = json.load(open(out_path)) if os.path.exists(out_path) else []
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in reps:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units = rows[0], rows[1]
+        ri, wi, ki = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        by = collections.defaultdict(list)
+        for r in rows[2:]:
+            kn = r[ki].split("(")[0].split("<")[0].replace("void ", "").split("::")[-1]
+            by[kn].append(float(r[ri].replace(",", "")) * unit[units[ri]] + float(r[wi].replace(",", "")) * unit[units[wi]])
+        for kn, vals in by.items():
+            key = names.get(kn, kn)
+            recs = [x for x in recs if not (x["kernel"] == key and x["model"] == model and x["batch"] == batch)]
+            recs.append({"kernel": key, "model": model, "batch": batch, "dram_bytes_per_launch": int(sum(vals) / len(vals)),
+                         "source": f"{os.path.basename(path)} ({kn}, {len(vals)} launch(es), ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"})
+    json.dump(recs, open(out_path, "w"), indent=1)
+    print(f"{out_path}: {len(recs)} records")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
     else:
         full(sys.argv[2:])
