@@ -337,6 +337,7 @@ class OracleEngine:
             self.h_df[sl, l] = np.where(commit[:, None], x, self.h_df[sl, l])
         c = (x + grouped_linear(emb, w["df_dec.df_skip.w"], w["df_dec.df_skip.b"])).astype(f32)
         co = np.tanh(grouped_linear(c, w["df_dec.df_out.w"], w["df_dec.df_out.b"]), dtype=f32).reshape(B, NB_DF, 2 * DF_ORDER)
+        dbg["co"] = co
         return m, co, c0
 
     def _df_pathway(self, c0_log):

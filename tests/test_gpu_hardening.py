@@ -1,0 +1,206 @@
+"""Parity where the FP16 hi/lo split of the tensor-core arm could break: reference
+goldens for every model and the 10 s BASELINE configs[0] clip, level extremes (clipped full scale, digital silence,
+60 dB level steps, -120 dBFS), weights with a 100x wider dynamic range, a 3000-hop drift run (BASELINE configs[1] is
+30 s of audio) and more intermediate stages.  All through the C ABI; tolerance 1e-4 on waveforms (north_star)."""
+import numpy as np
+import pytest
+
+from dpdfnet_b200.spec import get_spec
+from dpdfnet_b200.weights import pack_tensors, random_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+SPEC_TOL = 2e-4
+WAVE_TOL = 1e-4
+STATE_TOL = 1e-4
+TC_OPTS = ("intra_tc", "post_tc", "sep_tc", "gru_tc")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+    return torch
+
+
+def _engine(name, seed, B, tc=None, ck=None):
+    from dpdfnet_b200.engine import Engine
+    spec = get_spec(name)
+    eng = Engine(spec, ck if ck is not None else random_checkpoint(spec, seed), max_streams=B)
+    if tc is not None:
+        for o in TC_OPTS:
+            eng.set_option(o, tc)
+    return eng
+
+
+def _oracle(name, seed, B, ck=None):
+    from oracle.oracle_np import OracleEngine
+    spec = get_spec(name)
+    return OracleEngine(spec, pack_tensors(spec, ck if ck is not None else random_checkpoint(spec, seed)), B)
+
+
+# ---- reference goldens added in round 2 ------------------------------------------------------------------------
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("name", ["baseline", "dpdfnet8", "dpdfnet8_48khz_hr"])
+def test_stream_and_offline_goldens_of_the_remaining_models(torch_cuda, golden_dir, name, tc):
+    from dpdfnet_b200.offline import enhance_offline_exact
+    g = np.load(golden_dir / f"stream_{name}.npz")
+    eng = _engine(name, int(g["seed"]), 2, tc)
+    for t in range(g["spec_in"].shape[0]):
+        y = eng.step_spec_host(g["spec_in"][t][None], slot_ids=[1])
+        assert np.abs(y[0] - g["spec_out"][t]).max() < SPEC_TOL, t
+    assert np.abs(eng.state_export(1)[::int(g["state_stride"])] - g["state"]).max() < STATE_TOL
+    eng.reset()
+    o = np.load(golden_dir / f"offline_{name}.npz")
+    out = enhance_offline_exact(eng, o["wave_in"])
+    assert out.shape == o["wave_out"].shape and np.abs(out - o["wave_out"]).max() < WAVE_TOL
+    eng.poll_error()
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+def test_cfg0_ten_second_clip_against_the_offline_reference(torch_cuda, golden_dir, tc):
+    """BASELINE.json configs[0]: dpdfnet2 16 kHz, a single 10 s noisy clip, model/dpdfnet.py output, 1e-4 max-abs."""
+    from dpdfnet_b200.offline import enhance_offline_exact
+    from oracle.make_golden import test_signal
+    g = np.load(golden_dir / "offline_cfg0_dpdfnet2_10s.npz")
+    spec = get_spec("dpdfnet2")
+    wave = test_signal(np.random.default_rng(int(g["signal_seed"])), spec.sample_rate, int(g["seconds"]) * spec.sample_rate, 1)
+    eng = _engine("dpdfnet2", int(g["seed"]), 1, tc)
+    out = enhance_offline_exact(eng, wave)
+    assert out.shape == (1, 160000)
+    err = np.abs(out - g["wave_out"])
+    assert err.max() < WAVE_TOL
+    assert err[:, -16000:].max() < WAVE_TOL          # no drift: the last second is as good as the first
+    eng.poll_error()
+
+
+@pytest.mark.parametrize("tag", ["fullscale", "quiet"])
+def test_level_extreme_goldens_on_the_tensor_core_arm(torch_cuda, golden_dir, tag):
+    from dpdfnet_b200.offline import enhance_offline_exact
+    from oracle.make_golden import test_signal
+    g = np.load(golden_dir / f"offline_dpdfnet2_{tag}.npz")
+    spec = get_spec("dpdfnet2")
+    wave = np.clip(test_signal(np.random.default_rng(int(g["signal_seed"])), spec.sample_rate, spec.sample_rate, 1) * float(g["gain"]), -1, 1).astype(np.float32)
+    eng = _engine("dpdfnet2", int(g["seed"]), 1, 1)
+    out = enhance_offline_exact(eng, wave)
+    assert np.abs(out - g["wave_out"]).max() < WAVE_TOL
+    eng.poll_error()
+
+
+# ---- level extremes in a batched streaming run --------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["dpdfnet4", "dpdfnet2_48khz_hr"])
+def test_level_extremes_streaming_tc(torch_cuda, name):
+    """Rows of one batch: clipped full-scale noise, digital silence, +60 dB and -60 dB level steps, -120 dBFS noise,
+    a full-scale square wave.  tcgen05 arm against the oracle, no device-raised range error."""
+    spec = get_spec(name)
+    hop, T = spec.hop, 40
+    rng = np.random.default_rng(31)
+    n = T * hop
+    rows = [np.clip(rng.standard_normal(n) * 0.7, -1, 1),
+            np.zeros(n),
+            np.concatenate([rng.standard_normal(n // 2) * 1e-3, np.clip(rng.standard_normal(n - n // 2), -1, 1)]),
+            np.concatenate([np.clip(rng.standard_normal(n // 2), -1, 1), rng.standard_normal(n - n // 2) * 1e-3]),
+            rng.standard_normal(n) * 1e-6,
+            np.sign(np.sin(2 * np.pi * 440.0 * np.arange(n) / spec.sample_rate))]
+    pcm = np.stack(rows).astype(np.float32)
+    B = pcm.shape[0]
+    ora = _oracle(name, 0, B)
+    ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    big = np.tile(pcm, (22, 1))                               # 132 streams: two 128-stream MMA tiles, rows repeat
+    eng = _engine(name, 0, big.shape[0], 1)
+    out = eng.run_pcm_host(big)
+    eng.poll_error()
+    assert np.isfinite(out).all()
+    err = np.abs(out[:B] - ref).max(1)
+    assert err.max() < WAVE_TOL, err
+    assert np.array_equal(out[B:2 * B], out[:B])
+    assert not out[1].any() or np.abs(out[1]).max() < 1e-6   # silence in, (numerically) silence out
+    for b in range(B):
+        assert np.abs(eng.state_export(b) - ora.export_state(b)).max() < STATE_TOL, b
+
+
+def _wide_checkpoint(spec, seed):
+    """The seeded stand-in checkpoint with every weight matrix rescaled element-wise by 10^U(-1, 1): a 100x wider
+    dynamic range inside each tensor than the fan-in initialisation gives (BN statistics, LayerNorm and biases kept)."""
+    ck = random_checkpoint(spec, seed)
+    rng = np.random.default_rng(seed + 1000)
+    out = {}
+    for k, v in ck.items():
+        if v.ndim >= 2 and "running" not in k:
+            scale = 10.0 ** rng.uniform(-1.0, 1.0, v.shape)
+            scale /= np.sqrt((scale ** 2).mean())              # keep the layer gain, widen the spread
+            out[k] = (v * scale).astype(np.float32)
+        else:
+            out[k] = v
+    return out
+
+
+@pytest.mark.parametrize("name", ["dpdfnet2", "dpdfnet2_48khz_hr"])
+def test_wide_dynamic_range_weights_tc(torch_cuda, name):
+    spec = get_spec(name)
+    ck = _wide_checkpoint(spec, 5)
+    hop, T, B = spec.hop, 12, 4
+    rng = np.random.default_rng(32)
+    pcm = np.clip(rng.standard_normal((B, T * hop)) * np.array([[0.7], [0.1], [0.01], [1e-4]]), -1, 1).astype(np.float32)
+    ora = _oracle(name, 0, B, ck)
+    ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    for tc in (0, 1):
+        eng = _engine(name, 0, B, tc, ck)
+        out = eng.run_pcm_host(pcm)
+        eng.poll_error()
+        assert np.abs(out - ref).max() < WAVE_TOL, tc
+
+
+# ---- long run ---------------------------------------------------------------------------------------------------
+def test_three_thousand_hops_do_not_drift(torch_cuda):
+    """BASELINE configs[1] is 30 s of audio = 3000 hops.  256 streams on the tensor-core arm (graph replay, lanes as the
+    engine picks them); the oracle follows 4 of them on the CPU."""
+    name, B, T, R = "dpdfnet4", 256, 3000, 4
+    spec = get_spec(name)
+    hop = spec.hop
+    rng = np.random.default_rng(33)
+    pcm = np.clip(rng.standard_normal((B, T * hop), dtype=np.float32) * np.float32(0.1), -1, 1)
+    t = np.arange(T * hop) / spec.sample_rate
+    pcm[1] += (0.3 * np.sin(2 * np.pi * 220 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 0.7 * t))).astype(np.float32)
+    pcm[2] *= np.float32(5.0)
+    pcm[2] = np.clip(pcm[2], -1, 1)
+    pcm[3, T * hop // 2:] = 0
+    eng = _engine(name, 0, B, 1)
+    out = eng.run_pcm_host(pcm)
+    eng.poll_error()
+    ora = _oracle(name, 0, R)
+    worst = 0.0
+    for k in range(T):
+        r = ora.step_pcm(pcm[:R, k * hop:(k + 1) * hop])
+        worst = max(worst, float(np.abs(r - out[:R, k * hop:(k + 1) * hop]).max()))
+    assert worst < WAVE_TOL, worst
+    for b in range(R):
+        assert np.abs(eng.state_export(b) - ora.export_state(b)).max() < STATE_TOL
+
+
+# ---- more stages ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("name", ["dpdfnet4", "dpdfnet2_48khz_hr"])
+def test_more_stages_vs_oracle(torch_cuda, name, tc):
+    """xe (erb-branch DPRNN output), the intra-GRU outputs hcat of the last block, the decoder activations d3..d1 and
+    the deep-filter coefficients before the pathway add, which round 1 only checked indirectly."""
+    B = 3
+    eng = _engine(name, 13, B, tc)
+    eng.set_option("graph", 0)
+    ora = _oracle(name, 13, B)
+    spec = eng.spec
+    N = spec.n_blocks
+    rng = np.random.default_rng(3)
+    for t in range(4):
+        X = (rng.standard_normal((B, spec.freq_bins, 2)) * 20).astype(np.float32)
+        eng.step_spec_host(X)
+        ora.step_spec(X)
+        want = {"xe": ora.dbg[f"xe{N - 1}"], "hcat_e": ora.dbg[f"erb_hcat{N - 1}"], "hcat_d": ora.dbg[f"df_hcat{N - 1}"]}
+        for k in ("d3", "d2", "d1", "co"):
+            if k in ora.dbg:
+                want[k] = ora.dbg[k]
+        for stage, ref in want.items():
+            got = eng.debug_tensor(stage, B)
+            assert np.abs(got - np.asarray(ref, np.float32).reshape(B, -1)).max() < 2e-4, (stage, t)
+    assert {"d3", "d2", "d1", "co"} <= set(ora.dbg)

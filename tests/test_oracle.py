@@ -16,19 +16,44 @@ def _engine(name, seed, B):
     return OracleEngine(spec, pack_tensors(spec, random_checkpoint(spec, seed)), B)
 
 
-@pytest.mark.parametrize("name", ["dpdfnet2", "dpdfnet4", "dpdfnet2_48khz_hr"])
+ALL_MODELS = ["baseline", "dpdfnet2", "dpdfnet4", "dpdfnet8", "dpdfnet2_48khz_hr", "dpdfnet8_48khz_hr"]
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
 def test_stream_golden(golden_dir, name):
     g = np.load(golden_dir / f"stream_{name}.npz")
     eng = _engine(name, int(g["seed"]), 1)
     for t in range(g["spec_in"].shape[0]):
         y = eng.step_spec(g["spec_in"][t][None])
         assert np.abs(y[0] - g["spec_out"][t]).max() < STREAM_TOL, t
-    st = eng.export_state(0)
+    st = eng.export_state(0)[::int(g["state_stride"]) if "state_stride" in g else 1]
     assert st.shape == g["state"].shape
     assert np.abs(st - g["state"]).max() < 5e-5
 
 
-@pytest.mark.parametrize("name", ["dpdfnet2", "dpdfnet4", "dpdfnet2_48khz_hr"])
+def test_offline_golden_cfg0_10s_clip(golden_dir):
+    """BASELINE.json configs[0]: dpdfnet2 16 kHz, one 10 s noisy clip against model/dpdfnet.py (1e-4 on the waveform)."""
+    from oracle.make_golden import test_signal
+    g = np.load(golden_dir / "offline_cfg0_dpdfnet2_10s.npz")
+    spec = get_spec("dpdfnet2")
+    wave = test_signal(np.random.default_rng(int(g["signal_seed"])), spec.sample_rate, int(g["seconds"]) * spec.sample_rate, 1)
+    out = offline_exact(_engine("dpdfnet2", int(g["seed"]), 1), wave)
+    assert out.shape == g["wave_out"].shape == (1, 160000)
+    assert np.abs(out - g["wave_out"]).max() < WAVE_TOL
+
+
+@pytest.mark.parametrize("tag", ["fullscale", "quiet"])
+def test_offline_golden_level_extremes(golden_dir, tag):
+    """Clipped full-scale input (RMS 0.48) and a -100 dBFS input through the offline reference."""
+    from oracle.make_golden import test_signal
+    g = np.load(golden_dir / f"offline_dpdfnet2_{tag}.npz")
+    spec = get_spec("dpdfnet2")
+    wave = np.clip(test_signal(np.random.default_rng(int(g["signal_seed"])), spec.sample_rate, spec.sample_rate, 1) * float(g["gain"]), -1, 1).astype(np.float32)
+    out = offline_exact(_engine("dpdfnet2", int(g["seed"]), 1), wave)
+    assert np.abs(out - g["wave_out"]).max() < WAVE_TOL
+
+
+@pytest.mark.parametrize("name", ALL_MODELS)
 def test_offline_golden(golden_dir, name):
     g = np.load(golden_dir / f"offline_{name}.npz")
     eng = _engine(name, int(g["seed"]), g["wave_in"].shape[0])
