@@ -253,7 +253,14 @@ def build_runtime_model(onnx_path: Union[str, Path]) -> RuntimeModel:
     ``StreamEnhancer`` / ``enhance`` callers cost one engine, not one each."""
     session = create_session(onnx_path, device=int(os.environ.get("DPDFNET_B200_DEVICE", "0")))
     ins, outs = session.get_inputs(), session.get_outputs()
-    return RuntimeModel(session=session, init_state=initial_state(session.engine.spec), in_spec_name=ins[0].name,
+    if Path(onnx_path).suffix == ".onnx":          # the shipped artefact: state init from its metadata, like the reference (:52-78)
+        from .onnx_ingest import initial_state_from_metadata, read_onnx
+        init = initial_state_from_metadata(read_onnx(onnx_path))
+        if init.size != session.engine.spec.state_size:
+            raise ValueError(f"ONNX metadata state_size {init.size} does not match the engine's {session.engine.spec.state_size}")
+    else:
+        init = initial_state(session.engine.spec)
+    return RuntimeModel(session=session, init_state=init, in_spec_name=ins[0].name,
                         in_state_name=ins[1].name, out_spec_name=outs[0].name, out_state_name=outs[1].name)
 
 

@@ -220,10 +220,13 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
     """Reference checkpoint -> named float32 tensors in engine layout."""
     C = CONV_CH
     sd = {k: np.asarray(v) for k, v in sd.items()}
-    missing = [k for k in ref_param_shapes(spec) if k not in sd]
+    # enc.lsnr_fc is computed by the reference but never leaves the ONNX graph (SURVEY 8a): the engine does not use it and
+    # an .onnx export does not contain it, so it is optional here
+    want = {k: shp for k, shp in ref_param_shapes(spec).items() if ".lsnr_fc." not in k or k in sd}
+    missing = [k for k in want if k not in sd]
     if missing:
         raise KeyError(f"checkpoint is missing {len(missing)} tensors, e.g. {missing[:3]}")
-    for k, shp in ref_param_shapes(spec).items():
+    for k, shp in want.items():
         if tuple(sd[k].shape) != tuple(shp):
             raise ValueError(f"{k}: expected shape {shp}, got {tuple(sd[k].shape)}")
     t: "OrderedDict[str, np.ndarray]" = OrderedDict()

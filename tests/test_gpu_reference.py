@@ -40,3 +40,28 @@ def test_engine_stream_matches_reference_stream_enhancer(name, arm):
     # flat state in the reference layout against the reference session's state vector
     assert np.abs(eng.state_export(0) - se._state).max() < 5e-5
     eng.close()
+
+
+def test_stream_enhancer_runs_a_real_onnx_export(tmp_path):
+    """f3 end to end: reference graph -> torch ONNX exporter -> .onnx file -> StreamEnhancer(onnx_path=...) on the engine
+    (weights from the initialisers, initial state from the metadata) == the reference StreamEnhancer on the same weights."""
+    import dpdfnet_b200
+    from dpdfnet_b200.onnx_backend import EnginePool
+    from oracle import ref_import
+    from oracle.onnx_export import export_reference_onnx
+    spec = get_spec("dpdfnet2")
+    ck = random_checkpoint(spec, 4)
+    path = export_reference_onnx(spec, ck, tmp_path / "dpdfnet2.onnx")
+    x = np.clip(np.random.default_rng(8).standard_normal(21 * spec.hop) * 0.1, -1, 1).astype(np.float32)
+    ref = ref_import.reference_stream_enhancer(spec, ck).process(x)
+    e = dpdfnet_b200.StreamEnhancer(model="dpdfnet2", onnx_path=path)
+    assert e._fused
+    got = e.process(x, 16000)
+    assert got.shape == ref.shape and np.abs(got - ref).max() < WAVE_TOL
+    # the ONNX-shaped seam with the metadata-built initial state
+    rt = e._runtime
+    y, st = rt.session.run([rt.out_spec_name, rt.out_state_name],
+                           {rt.in_spec_name: np.zeros((1, 1, 161, 2), np.float32), rt.in_state_name: rt.init_state.copy()})
+    assert st.shape == (spec.state_size,) and np.isfinite(y).all()
+    e.close()
+    EnginePool.shutdown()
