@@ -315,6 +315,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   init_dprnn_tc_kernels();
   init_dprnn_intra_tc_kernels();
   init_conv_tc_kernels();
+  init_conv_tma_kernels();
   init_gru_tc_kernels();
   launch_reset(e, nullptr, max_streams, e.own_stream);
   if (cudaStreamSynchronize(e.own_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
@@ -377,7 +378,8 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   e.pdl_first = true;                                      // the analysis kernel follows a copy / an event, not a kernel
   const bool use_sep_tc = e.sep_tc == 1 || (e.sep_tc == 2 && std::max(B, e.total_B) >= e.sep_tc_min);
   auto sepconv = [&](Engine& en, const SepProblem* probs, int nprob, int Bn, cudaStream_t s_) {
-    if (use_sep_tc) launch_sepconv_tc(en, probs, nprob, Bn, s_);
+    if (use_sep_tc && en.sep_tma && sepconv_tma_available()) launch_sepconv_tma(en, probs, nprob, Bn, s_);
+    else if (use_sep_tc) launch_sepconv_tc(en, probs, nprob, Bn, s_);
     else launch_sepconv(en, probs, nprob, Bn, s_);
   };
   const bool use_gru_tc = e.gru_tc == 1 || (e.gru_tc == 2 && std::max(B, e.total_B) >= e.gru_tc_min);
@@ -1057,6 +1059,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "sep_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
     e.sep_tc = value;
     drop_graphs(e);
+  } else if (strcmp(key, "sep_tma") == 0) {
+    e.sep_tma = value ? 1 : 0;
+    drop_graphs(e);
   } else if (strcmp(key, "decoder_fork") == 0) {
     e.decoder_fork = value ? 1 : 0;
     drop_graphs(e);
@@ -1075,6 +1080,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "lanes") == 0) {
     if (value < 0 || value > Engine::MAX_LANES) return fail(DPDF_ERR_INVALID, "lanes must be 0 (auto) .. %d", Engine::MAX_LANES);
     e.lanes = value;
+    drop_graphs(e);
+  } else if (strcmp(key, "post_pf") == 0) {
+    if (value < 0 || value > 16) return fail(DPDF_ERR_INVALID, "post_pf must be 0 (off) .. 16");
+    e.post_pf = value;
     drop_graphs(e);
   } else if (strcmp(key, "post_tc") == 0) {
     e.post_tc = value ? 1 : 0;

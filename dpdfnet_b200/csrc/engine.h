@@ -102,6 +102,8 @@ struct SepProblem {
 };
 void launch_sepconv(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st);
 void launch_sepconv_tc(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st);
+void launch_sepconv_tma(Engine& e, const SepProblem* probs, int nprob, int B, cudaStream_t st);   // persistent, TMA-fed (k_conv_tma.cu)
+bool sepconv_tma_available();
 void launch_conv0_out(Engine& e, int B, cudaStream_t st);
 void launch_df_pathway(Engine& e, int B, cudaStream_t st);
 void launch_df_pathway_ps(Engine& e, int B, cudaStream_t st);
@@ -180,6 +182,8 @@ struct Engine {
   int gru_tc_min = 256;
   int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min
   int sep_tc_min = 256;
+  int sep_tma = 1;                // tensor-core separable convs as the persistent TMA-fed kernel (k_conv_tma.cu) instead of k_sepconv_tc
+  int post_pf = 1;                // k_dprnn_post_tc: L2 prefetch distance in units of the SM count (2 CTAs per SM -> 2), 0 = off
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
   std::map<int, cudaGraphExec_t> graphs;     // keyed by B: one hop of all lanes (forked chains, joined)
   std::map<int, cudaGraphExec_t> lane_graphs; // keyed by B * MAX_LANES + lane: one hop of one lane (free-running lanes of a multi-hop run)
@@ -237,6 +241,7 @@ void init_dense_kernels();
 void init_dprnn_tc_kernels();
 void init_dprnn_intra_tc_kernels();
 void init_conv_tc_kernels();
+void init_conv_tma_kernels();
 void init_gru_tc_kernels();
 void enqueue_step(Engine& e, int B, cudaStream_t st);    // all kernels of one hop, in order
 

@@ -55,6 +55,8 @@ struct PostTcParams {
   // order in which both sweep directions complete them); the CTA waits for the two intra CTAs it depends on
   const int* progress;    // [2 branches][2 dirs][stiles] completed steps, nullptr = row-major tiles of a finished sweep
   int stiles;             // ceil(B / 128)
+  int pf_dist;            // row-major mode: warm L2 with the inputs of tile blockIdx.x + pf_dist (0 = off); CTAs are dispatched in
+                          // index order, so with pf_dist = resident CTAs that tile starts about when this one ends
 #ifdef PT_TIMELINE
   long long* tl;          // [16] SM-clock stamps of CTA 0 (tools/ubench/post_tc_timeline.cu)
 #endif
@@ -131,6 +133,31 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     valid = (int)min((long long)128, (long long)p.B * p.br[bi].Fp - rbase);
   }
   const PostTcBranch& q = p.br[bi];
+
+  // Warm L2 for the CTA that will take this CTA's place: its hcat tile (64 KB) and block input (32 KB) are contiguous,
+  // its 128 inter-GRU state rows are scattered over the slot arena.  At throughput batch sizes none of them is L2
+  // resident any more (hcat alone is 0.4 GB at 16 384 streams) and the tile's dependent phases would each eat a DRAM
+  // round trip: ncu showed 38 % long-scoreboard stalls, hcat staging 9 k and the first epilogue 12 k of 44 k cycles.
+  if (p.pf_dist > 0 && !p.progress) {
+    const long long nt = (long long)blockIdx.x + p.pf_dist;
+    const int tiles1 = (int)(((long long)p.B * p.br[1].Fp + 127) / 128);
+    if (nt < (long long)p.tiles0 + tiles1) {
+      const int nb = nt >= p.tiles0 ? 1 : 0;
+      const PostTcBranch& nq = p.br[nb];
+      const long long nbase = (nt - (nb ? p.tiles0 : 0)) * 128;
+      const int nvalid = (int)min((long long)128, (long long)p.B * nq.Fp - nbase);
+      if (tid == 0) {
+        bulk_prefetch_l2(nq.hcat + nbase * 2 * C, (uint32_t)nvalid * 2 * C * 4);
+        bulk_prefetch_l2(nq.xin + nbase * C, (uint32_t)nvalid * C * 4);
+      } else if (tid >= 128 && tid < 128 + nvalid) {
+        const long long r = nbase + (tid - 128);
+        const int b = (int)(r / nq.Fp), f = (int)(r % nq.Fp);
+        const float* hp = nq.hstate + (long long)io_slot(p.io, b) * nq.per_slot + (long long)f * C;
+        prefetch_l2(hp);
+        prefetch_l2(hp + 32);
+      }
+    }
+  }
 
   if (tid < 128) {
     long long off = 0;
@@ -430,6 +457,7 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.tiles0 = (int)(((long long)B * (NDF / 2) + 127) / 128);
   const int tiles1 = (int)(((long long)B * e.d.fe[3] + 127) / 128);
   if (!e.overlap_now) {
+    p.pf_dist = e.post_pf * e.num_sms;
     launch_k(e, k_dprnn_post_tc, dim3(p.tiles0 + tiles1), dim3(TC_NT), POST_TC_SMEM, st, p);
     return;
   }

@@ -180,14 +180,15 @@ def test_three_thousand_hops_do_not_drift(torch_cuda):
 
 
 # ---- more stages ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("tc", [0, 1, 2])
 @pytest.mark.parametrize("name", ["dpdfnet4", "dpdfnet2_48khz_hr"])
 def test_more_stages_vs_oracle(torch_cuda, name, tc):
     """xe (erb-branch DPRNN output), the intra-GRU outputs hcat of the last block, the decoder activations d3..d1 and
     the deep-filter coefficients before the pathway add, which round 1 only checked indirectly."""
     B = 3
-    eng = _engine(name, 13, B, tc)
+    eng = _engine(name, 13, B, min(tc, 1))
     eng.set_option("graph", 0)
+    eng.set_option("sep_tma", 0 if tc == 2 else 1)          # tc=1: persistent TMA-fed separable convs, tc=2: the per-tile kernel
     ora = _oracle(name, 13, B)
     spec = eng.spec
     N = spec.n_blocks
@@ -196,7 +197,9 @@ def test_more_stages_vs_oracle(torch_cuda, name, tc):
         X = (rng.standard_normal((B, spec.freq_bins, 2)) * 20).astype(np.float32)
         eng.step_spec_host(X)
         ora.step_spec(X)
-        want = {"xe": ora.dbg[f"xe{N - 1}"], "hcat_e": ora.dbg[f"erb_hcat{N - 1}"], "hcat_d": ora.dbg[f"df_hcat{N - 1}"]}
+        want = {"xe": ora.dbg[f"xe{N - 1}"], "hcat_e": ora.dbg[f"erb_hcat{N - 1}"], "hcat_d": ora.dbg[f"df_hcat{N - 1}"],
+                "e1": ora.dbg["e1"], "e2": ora.dbg["e2"], "e3": ora.dbg["e3"], "c0": ora.dbg["c0"], "xd0": None}
+        want.pop("xd0")
         for k in ("d3", "d2", "d1", "co"):
             if k in ora.dbg:
                 want[k] = ora.dbg[k]
