@@ -1081,6 +1081,12 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     if (value < 0 || value > Engine::MAX_LANES) return fail(DPDF_ERR_INVALID, "lanes must be 0 (auto) .. %d", Engine::MAX_LANES);
     e.lanes = value;
     drop_graphs(e);
+  } else if (strcmp(key, "ana_force") == 0 || strcmp(key, "syn_force") == 0) {
+    (key[0] == 'a' ? e.ana_force : e.syn_force) = value;
+    drop_graphs(e);
+  } else if (strcmp(key, "ana_nb") == 0 || strcmp(key, "syn_sb") == 0) {
+    (key[0] == 'a' ? e.ana_nb : e.syn_sb) = value;
+    drop_graphs(e);
   } else if (strcmp(key, "post_pf") == 0) {
     if (value < 0 || value > 16) return fail(DPDF_ERR_INVALID, "post_pf must be 0 (off) .. 16");
     e.post_pf = value;

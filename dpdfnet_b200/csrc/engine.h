@@ -183,6 +183,8 @@ struct Engine {
   int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min
   int sep_tc_min = 256;
   int sep_tma = 1;                // tensor-core separable convs as the persistent TMA-fed kernel (k_conv_tma.cu) instead of k_sepconv_tc
+  int ana_force = 0, syn_force = 0;   // experiments: force that many streams per CTA regardless of the grid size (0 = auto)
+  int ana_nb = 32, syn_sb = 16;   // caps on the streams per CTA of the analysis / synthesis kernels (8|16|32, 4|8|16)
   int post_pf = 1;                // k_dprnn_post_tc: L2 prefetch distance in units of the SM count (2 CTAs per SM -> 2), 0 = off
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
   std::map<int, cudaGraphExec_t> graphs;     // keyed by B: one hop of all lanes (forked chains, joined)
