@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cuda_fp16.h>
+
 #include "engine.h"
 
 using namespace dpdf;
@@ -913,6 +915,12 @@ extern "C" int dpdf_state_export(dpdf_engine* h, int32_t slot, float* flat) {
   if ((rc = plain(e.st.h_df, 2 * H))) return rc;
   {   // c0 ring: engine [5][96][64] -> reference [5][64][96]
     if ((rc = fetch(e, e.st.c0_ring, (size_t)ORD * NDF * C, slot, buf))) return rc;
+    if (e.st.c0_fp16) {                            // compact FP16 frames at the start of the region -> FP32 (via a copy)
+      std::vector<float> wide(buf.size());
+      const __half* hsrc = reinterpret_cast<const __half*>(buf.data());
+      for (size_t i = 0; i < wide.size(); ++i) wide[i] = __half2float(hsrc[i]);
+      buf.swap(wide);
+    }
     for (int k = 0; k < ORD; ++k) {
       const float* src = buf.data() + (size_t)((pos + k) % ORD) * NDF * C;
       for (int c = 0; c < C; ++c)
@@ -966,7 +974,12 @@ extern "C" int dpdf_state_import(dpdf_engine* h, int32_t slot, const float* flat
       for (int c = 0; c < C; ++c)
         for (int f = 0; f < NDF; ++f) buf[((size_t)k * NDF + f) * C + c] = o[((size_t)k * C + c) * NDF + f];
     o += buf.size();
-    if ((rc = store(e, e.st.c0_ring, buf.size(), slot, buf))) return rc;
+    if (e.st.c0_fp16) {                            // the pending sums below use the FP32 values; the device ring gets the rounded frames
+      std::vector<float> packed(buf.size(), 0.f);
+      __half* hdst = reinterpret_cast<__half*>(packed.data());
+      for (size_t i = 0; i < buf.size(); ++i) hdst[i] = __float2half_rn(buf[i]);
+      if ((rc = store(e, e.st.c0_ring, packed.size(), slot, packed))) return rc;
+    } else if ((rc = store(e, e.st.c0_ring, buf.size(), slot, buf))) return rc;
     // pending sums of the df pathway conv, rebuilt from the five imported frames (pos := 0, logical == physical):
     // the output m hops ahead already has the taps kt = 0 .. 3 - m of the frames kt + 1 + m
     std::vector<float> acc((size_t)ORD * NDF * 10, 0.f);
@@ -1064,6 +1077,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     drop_graphs(e);
   } else if (strcmp(key, "decoder_fork") == 0) {
     e.decoder_fork = value ? 1 : 0;
+    drop_graphs(e);
+  } else if (strcmp(key, "c0_fp16") == 0) {
+    e.st.c0_fp16 = value ? 1 : 0;                  // switch only on freshly reset streams: the ring changes its storage format
     drop_graphs(e);
   } else if (strcmp(key, "dfp_ps") == 0) {
     e.dfp_ps = value ? 1 : 0;                      // switch only on freshly reset streams: the two forms keep different state

@@ -1,5 +1,6 @@
 // Shared device helpers for the DPDFNet-B200 kernels (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,6 +42,20 @@ struct IoDesc {
 __device__ __forceinline__ int io_slot(const IoDesc* io, int b) {
   return io->slot_ids ? __ldg(io->slot_ids + b) : io->slot_base + b;
 }
+// ---- c0 ring in half precision (option "c0_fp16") ------------------------------------------
+// 58 % of a stream's state is the five-frame c0 ring that only the df pathway conv reads (30 720 floats, 120 KB per stream
+// and hop).  Stored as FP16 it costs half the HBM bytes on both sides; the conv then sees its inputs rounded to 11
+// significant bits (2^-12 relative), which moves the deep-filter coefficients by ~1e-5 and the waveform by < 1e-5
+// (tests/test_gpu_hardening.py::test_c0_ring_fp16).  Frames are compact [96][64] halves at the start of the slot's region.
+__device__ __forceinline__ uint2 pack4_f16(const float4& v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ float4 unpack4_f16(const uint2& u) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
 __device__ __forceinline__ int io_flags(const IoDesc* io, int b) {
   return io->flags ? __ldg(io->flags + b) : 0;
 }

@@ -41,6 +41,7 @@ struct State {           // all [max_streams][...], float unless noted
   float* in_hist;        // [hop]
   float* ola;            // [hop]
   int* pos;              // frames pushed so far
+  int c0_fp16;           // c0_ring holds FP16 frames [5][96][64] halves at the start of each slot's (FP32-sized) region (option "c0_fp16")
 };
 
 struct Scratch {         // all [max_streams][...]

@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(256, 2) k_sepconv(SepParams p) {
       const int pos = p.st.pos[slot];
       *reinterpret_cast<float4*>(q.out + (size_t)row * C + c) = v;      // c0 for df_conv1 (this hop)
       if (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) v = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(p.st.c0_ring + (((size_t)slot * ORD + pos % ORD) * NDF + fo) * C + c) = v;
+      if (p.st.c0_fp16)
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.st.c0_ring + (size_t)slot * ORD * NDF * C) + ((size_t)(pos % ORD) * NDF + fo) * C + c) = pack4_f16(v);
+      else
+        *reinterpret_cast<float4*>(p.st.c0_ring + (((size_t)slot * ORD + pos % ORD) * NDF + fo) * C + c) = v;
     }
   }
 }
@@ -286,11 +289,21 @@ __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
 #pragma unroll
   for (int o = 0; o < 10; ++o) t[o] = 0.f;
   float4 x[ORD][2];
+  if (p.st.c0_fp16) {                                  // half the bytes: this kernel is bound by the 120 KB ring read per stream
+    const __half* ringh = reinterpret_cast<const __half*>(ring);
 #pragma unroll
-  for (int kt = 0; kt < ORD; ++kt) {
-    const float* src = ring + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
-    x[kt][0] = *reinterpret_cast<const float4*>(src);
-    x[kt][1] = *reinterpret_cast<const float4*>(src + 32);
+    for (int kt = 0; kt < ORD; ++kt) {
+      const __half* src = ringh + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
+      x[kt][0] = unpack4_f16(*reinterpret_cast<const uint2*>(src));
+      x[kt][1] = unpack4_f16(*reinterpret_cast<const uint2*>(src + 32));
+    }
+  } else {
+#pragma unroll
+    for (int kt = 0; kt < ORD; ++kt) {
+      const float* src = ring + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
+      x[kt][0] = *reinterpret_cast<const float4*>(src);
+      x[kt][1] = *reinterpret_cast<const float4*>(src + 32);
+    }
   }
 #pragma unroll
   for (int kt = 0; kt < ORD; ++kt)

@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 3) k_sepconv_tc(SepTcParam
       const int pos = p.st.pos[slot];
       *reinterpret_cast<float4*>(q.out + (size_t)row * C + c) = v;      // c0 for df_conv1 (this hop)
       if (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) v = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(p.st.c0_ring + (((size_t)slot * ORD + pos % ORD) * NDF + fo) * C + c) = v;
+      if (p.st.c0_fp16)
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.st.c0_ring + (size_t)slot * ORD * NDF * C) + ((size_t)(pos % ORD) * NDF + fo) * C + c) = pack4_f16(v);
+      else
+        *reinterpret_cast<float4*>(p.st.c0_ring + (((size_t)slot * ORD + pos % ORD) * NDF + fo) * C + c) = v;
     }
   }
   STL(6);

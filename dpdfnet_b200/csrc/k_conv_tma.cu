@@ -41,6 +41,7 @@ constexpr int ST_TILE = 128;                      // output rows per MMA tile
 constexpr int ST_IMG = ST_TILE * 64 * 2;          // one FP16 [128][64] operand image (16 KB)
 constexpr int ST_RING = 57344;                    // bytes of the input ring: cut into as many stages as the problem's unit size allows
 constexpr int ST_MAXSTAGE = 8;
+constexpr int ST_RING16 = 24576;                  // df_conv0 uses 8 x 3 KB of the ring: the FP16 c0-ring staging tile (16 KB) sits behind them
 constexpr int ST_OFF_A = 0;                       // hi | lo images (32 KB); later the swizzled FP32 output staging
 constexpr int ST_OFF_W = ST_OFF_A + 2 * ST_IMG;   // weight slab hi | lo (16 KB)
 constexpr int ST_OFF_STAGE = ST_OFF_W + 2 * 64 * 64 * 2;
@@ -309,6 +310,10 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
             const float4 o = make_float4(fmaxf(v[jq * 4] + bs[col], 0.f), fmaxf(v[jq * 4 + 1] + bs[col + 1], 0.f),
                                          fmaxf(v[jq * 4 + 2] + bs[col + 2], 0.f), fmaxf(v[jq * 4 + 3] + bs[col + 3], 0.f));
             *reinterpret_cast<float4*>(hb + (((c16 * 4 + jq) ^ (row & 7)) << 4)) = o;
+            if (q.mode == 1 && p.st.c0_fp16) {                   // FP16 copy of the tile for the c0 ring: [128 rows][64 halves], 128B swizzle
+              const int hc = ch * 4 + c16 * 2 + (jq >> 1);         // 16-byte chunk of the 128-byte row
+              *reinterpret_cast<uint2*>(stage + ST_RING16 + row * 128 + ((hc ^ (row & 7)) << 4) + (jq & 1) * 8) = pack4_f16(o);
+            }
           }
         }
       }
@@ -327,6 +332,10 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
             const int slot = io_slot(p.io, b);
             const int rrow = (slot * ORD + p.st.pos[slot] % ORD) * NDF + fo;
             const bool warm = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) != 0;
+            if (p.st.c0_fp16) {                                  // ring rows are 128 B (64 halves): two per FP32-sized row of the region
+              tma_store_2d(&q.ring, 0, (slot * 2 * ORD + p.st.pos[slot] % ORD) * NDF + fo, warm ? zeros : stage + ST_RING16 + k * 4096);
+              continue;
+            }
             tma_store_2d(&q.ring, 0, rrow, warm ? zeros : Aimg + k * 4096);
             tma_store_2d(&q.ring, 32, rrow, warm ? zeros : Aimg + ST_TILE * 128 + k * 4096);
           }
@@ -355,6 +364,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 
 // [rows][64] FP32 row-major view, box {32 floats, box_rows}, 128-byte swizzle, zero fill outside
+bool make_map_f16(CUtensorMap* m, const void* base, long long rows, int box_rows) {     // [rows][64] FP16, box {64, box_rows}
+  const cuuint64_t dims[2] = {64, (cuuint64_t)std::max<long long>(rows, 1)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool make_map(CUtensorMap* m, const void* base, long long rows, int box_rows) {
   const cuuint64_t dims[2] = {64, (cuuint64_t)std::max<long long>(rows, 1)};
   const cuuint64_t strides[1] = {256};
@@ -397,7 +415,9 @@ void launch_sepconv_tma(Engine& e, const SepProblem* probs, int nprob, int B, cu
     } else {
       q.stage_bytes = 3072;                      // 3 x 2 x 96 floats of ring, rounded up
       q.n_stage = ST_MAXSTAGE;
-      ok = ok && s.Fout == NDF && make_map(&q.ring, e.st.c0_ring, (long long)e.max_streams * ORD * NDF, 32);
+      ok = ok && s.Fout == NDF &&
+           (e.st.c0_fp16 ? make_map_f16(&q.ring, e.st.c0_ring, (long long)e.max_streams * 2 * ORD * NDF, 32)
+                         : make_map(&q.ring, e.st.c0_ring, (long long)e.max_streams * ORD * NDF, 32));
     }
   }
   if (!ok) {                                     // geometry this kernel does not cover: the per-tile kernel handles everything

@@ -126,7 +126,8 @@ int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the la
  * "lanes" 0 = auto, 1..8 kernel-chain lanes per batched step; "free_lanes" 0/1 lanes of a multi-hop run replay their
  * own graphs on their own streams; "overlap" 0/1 (+ "overlap_max") post kernel overlapped with the intra sweep;
  * "decoder_fork" 0/1 decoder tails on forked streams; "intra_tc" / "sep_tc" / "gru_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch
- * size (+ "intra_tc_min"); "sep_tma" 0/1 tensor-core separable convs as the persistent TMA-fed kernel; "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel; "dfp_ps" 0/1
+ * size (+ "intra_tc_min"); "sep_tma" 0/1 tensor-core separable convs as the persistent TMA-fed kernel; "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel; "c0_fp16" 0/1 c0 ring stored in half precision (switch only on freshly reset streams); "ana_nb" / "syn_sb" caps on the
+ * streams per CTA of the analysis / synthesis kernels; "post_pf" L2 prefetch distance of the post kernel; "dfp_ps" 0/1
  * df pathway conv as pending partial sums (switch only on freshly reset streams); "pdl" 0/1 chain every kernel of a
  * hop with programmatic dependent launches. */
 int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value);
