@@ -266,6 +266,7 @@ struct DfPathParams {
 // One warp = four consecutive bins of a stream; lane = (bin, 4-channel chunk).  Every load of the 5-frame c0 ring
 // is a fully used 128-byte line per bin, weights are broadcast float4 from shared memory, the 8 chunk-lanes of a
 // bin are reduced with xor shuffles.  HBM-bound on the ring (120 KB per stream-frame).
+template <bool RING16>       // c0 ring stored in half precision (option c0_fp16); a template so that the FP32 path costs nothing
 __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
   pdl_trigger();
   pdl_wait();
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
 #pragma unroll
   for (int o = 0; o < 10; ++o) t[o] = 0.f;
   float4 x[ORD][2];
-  if (p.st.c0_fp16) {                                  // half the bytes: this kernel is bound by the 120 KB ring read per stream
+  if (RING16) {                                        // half the bytes of the 120 KB ring read per stream (measured: not faster)
     const __half* ringh = reinterpret_cast<const __half*>(ring);
 #pragma unroll
     for (int kt = 0; kt < ORD; ++kt) {
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
 void launch_df_pathway(Engine& e, int B, cudaStream_t st) {
   DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B};
   const long long threads = (long long)B * (NDF / 4) * 32;
-  launch_k(e, k_df_pathway, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
+  if (e.st.c0_fp16) launch_k(e, k_df_pathway<true>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
+  else launch_k(e, k_df_pathway<false>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -60,7 +60,8 @@ struct alignas(64) TmaProblem {
   int src1_off;                      // byte offset of the pathway source inside a stage
   int stage_bytes, n_stage;          // the ring of this problem: n_stage stages of stage_bytes
   int tile0;                         // first tile of this problem in the launch
-  long long nrows;                   // B * Fout
+  int nrows;                         // B * Fout (< 2^31: checked by the launcher)
+  unsigned magic_fout, magic_up;     // ceil(2^32 / d): x / d == __umulhi(x, magic) for the small x used here (x < 2^16, d < 2^10)
 };
 
 struct SepTmaParams {
@@ -141,13 +142,13 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
 
     // ---- producer (thread 0): the inputs of unit `lu` of this segment into stage lu % NS -------------------------------
     auto issue = [&](int lu) {
-      const long long r0 = (long long)(s_begin - q.tile0 + lu / 4) * ST_TILE + (long long)(lu & 3) * ST_UNIT;
+      const int r0 = (s_begin - q.tile0 + lu / 4) * ST_TILE + (lu & 3) * ST_UNIT;
       const int sidx = lu % NS;
       unsigned char* dst = stage + sidx * q.stage_bytes;
       uint64_t* bar = full + sidx;
       if (q.mode == 0) {
         // output rows [r0, r0 + 32) read input rows [first, first + n_in): centre of row R is R * stride (up == 1) or R / up
-        const int first = (q.up > 1 ? (int)(r0 / q.up) : (int)(r0 * q.stride)) - 1;
+        const int first = (q.up > 1 ? r0 / q.up : r0 * q.stride) - 1;
         mbar_expect_tx(bar, (uint32_t)q.n_in * 256u * (q.has_in2 ? 2u : 1u));
         tma_load_2d(dst, &q.in1, 0, first, bar);
         tma_load_2d(dst + q.half_off, &q.in1, 32, first, bar);
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
       } else {
         // df_conv0: the three-frame feature ring of the unit's stream (a unit never straddles streams: 96 % 32 == 0);
         // past the end any valid source will do, those rows are zeroed below
-        const int b = r0 < q.nrows ? (int)(r0 / NDF) : 0;
+        const int b = r0 < q.nrows ? r0 / NDF : 0;
         const int slot = io_slot(p.io, b);
         *reinterpret_cast<int*>(dst + 3 * 2 * NDF * 4) = p.st.pos[slot];     // ring head for the consumers (released by the arrive below)
         mbar_expect_tx(bar, 3 * 2 * NDF * 4);
@@ -195,24 +196,29 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
 
     for (int lu = 0; lu < n_units; ++lu) {
       const int tile = s_begin + lu / 4, uu = lu & 3;
-      const long long r0 = (long long)(tile - q.tile0) * ST_TILE + (long long)uu * ST_UNIT;
+      const int r0 = (tile - q.tile0) * ST_TILE + uu * ST_UNIT;
       const int sidx = lu % NS;
       const unsigned char* src = stage + sidx * q.stage_bytes;
+      // per-unit index arithmetic (one 32-bit division each; the per-row part below is multiply-high only)
+      const unsigned fo0 = (unsigned)r0 % (unsigned)q.Fout;      // frequency position of the unit's first row
+      const unsigned a0 = q.up > 1 ? (unsigned)r0 / (unsigned)q.up : 0u;
+      const unsigned rem0 = (unsigned)r0 - a0 * (unsigned)q.up;  // r0 % up
       mbar_wait(full + sidx, (lu / NS) & 1);
 
       // ---- depthwise / grouped stage of two rows per thread, out of shared memory -------------------------------------
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int j = rs + 16 * k;                               // row inside the unit
-        const long long R = r0 + j;
+        const int R = r0 + j;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         if (R < q.nrows) {
           if (q.mode == 0) {
-            const int fo = (int)(R % q.Fout);
+            const unsigned x = fo0 + (unsigned)j;
+            const int fo = (int)(x - (unsigned)q.Fout * __umulhi(x, q.magic_fout));   // (fo0 + j) % Fout
             int fc, jj, lr;                                      // input position of the centre tap, sub-pixel phase, its row in the box
             if (q.up > 1) {
-              fc = fo / q.up; jj = fo - fc * q.up;
-              lr = (int)(R / q.up) - (int)(r0 / q.up) + 1;
+              fc = (int)__umulhi((unsigned)fo, q.magic_up); jj = fo - fc * q.up;
+              lr = (int)__umulhi(rem0 + (unsigned)j, q.magic_up) + 1;                 // R / up - r0 / up + 1
             } else {
               fc = fo * q.stride; jj = 0;
               lr = j * q.stride + 1;
@@ -238,13 +244,15 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
               acc.w = fmaf(w.w, v.w, acc.w);
             }
           } else {
-            const int b = (int)(r0 / NDF), fo = (int)(R - (long long)b * NDF);
+            const int fo = (int)fo0 + j;                         // a unit never straddles streams (96 % 32 == 0)
             const float* ring = reinterpret_cast<const float*>(src);
             const int pos = *reinterpret_cast<const int*>(src + 3 * 2 * NDF * 4);
             const int plane = c >= 32 ? 1 : 0;
 #pragma unroll
             for (int kt = 0; kt < 3; ++kt) {
-              const float* rowp = ring + (((pos + 1 + kt) % 3) * 2 + plane) * NDF;
+              int ph = pos + 1 + kt;                             // (pos + 1 + kt) % 3 with pos in [0, 15)
+              ph -= 3 * ((ph * 11) >> 5);
+              const float* rowp = ring + (ph * 2 + plane) * NDF;
 #pragma unroll
               for (int kf = 0; kf < 3; ++kf) {
                 const int fi = fo + kf - 1;
@@ -321,14 +329,14 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
       tc_fence_before();
       CSYNC();
       if (tid == 0) {
-        const long long row0 = (long long)(tile - q.tile0) * ST_TILE;
-        tma_store_2d(&q.out, 0, (int)row0, Aimg);
-        tma_store_2d(&q.out, 32, (int)row0, Aimg + ST_TILE * 128);
+        const int row0 = (tile - q.tile0) * ST_TILE;
+        tma_store_2d(&q.out, 0, row0, Aimg);
+        tma_store_2d(&q.out, 32, row0, Aimg + ST_TILE * 128);
         if (q.mode == 1) {                                       // the same rows into the c0 ring slot of their stream, 32-row blocks
           for (int k = 0; k < 4; ++k) {
-            const long long R = row0 + 32 * k;
+            const int R = row0 + 32 * k;
             if (R >= q.nrows) break;
-            const int b = (int)(R / NDF), fo = (int)(R - (long long)b * NDF);
+            const int b = R / NDF, fo = R - b * NDF;
             const int slot = io_slot(p.io, b);
             const int rrow = (slot * ORD + p.st.pos[slot] % ORD) * NDF + fo;
             const bool warm = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) != 0;
@@ -399,9 +407,12 @@ void launch_sepconv_tma(Engine& e, const SepProblem* probs, int nprob, int B, cu
     TmaProblem& q = p.prob[i];
     q.pa = s.pa; q.pb = s.pb; q.dw = s.dw; q.tc_pw = s.tc_pw; q.bias = s.bias;
     q.mode = s.mode; q.Fin = s.Fin; q.Fout = s.Fout; q.stride = s.stride; q.up = s.up; q.has_in2 = s.in2 ? 1 : 0;
-    q.nrows = (long long)B * s.Fout;
+    ok = ok && (long long)B * std::max(s.Fout, s.Fin) < (1ll << 31) - 4 * ST_TILE;
+    q.nrows = (int)((long long)B * s.Fout);
+    q.magic_fout = (unsigned)(((1ull << 32) + s.Fout - 1) / s.Fout);
+    q.magic_up = (unsigned)(((1ull << 32) + s.up - 1) / std::max(s.up, 1));
     q.tile0 = tiles;
-    tiles += (int)((q.nrows + ST_TILE - 1) / ST_TILE);
+    tiles += (q.nrows + ST_TILE - 1) / ST_TILE;
     ok = ok && make_map(&q.out, s.out, q.nrows, ST_TILE);
     if (s.mode == 0) {
       q.n_in = s.up > 1 ? (ST_UNIT - 1) / s.up + 4 : (ST_UNIT - 1) * s.stride + 3;
