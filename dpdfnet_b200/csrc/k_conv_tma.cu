@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
         }
         umma_commit(bars + 1);
       }
-      mbar_wait(bars + 1, mma_phase & 1);
+      if (warp == 0) mbar_wait(bars + 1, mma_phase & 1);         // one warp polls, the others park on the named barrier
+      CSYNC();
       ++mma_phase;
       tc_fence_after();
 

@@ -280,7 +280,10 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     const int r = rg * 8 + rr;
     hv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  mbar_wait(bars + 4, 0);
+  // one warp polls the mbarrier, the other fifteen park on the hardware barrier: 512 spinning threads cost a quarter of
+  // the kernel's issued instructions (ncu, r2c: SYNCS + BRA + YIELD = 25 %) and stole issue slots from the co-resident CTA
+  if (warp == 0) mbar_wait(bars + 4, 0);
+  __syncthreads();
   tc_fence_after();
   PTL(2);
 
@@ -353,7 +356,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     umma_commit(bars + 4);
     load_slab(8);
   }
-  mbar_wait(bars + 4, 1);
+  if (warp == 0) mbar_wait(bars + 4, 1);
+  __syncthreads();
   tc_fence_after();
   PTL(4);
 #pragma unroll
@@ -412,7 +416,8 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) yv[c * 8 + e] = t8[e];
   }
-  mbar_wait(bars + 4, 0);
+  if (warp == 0) mbar_wait(bars + 4, 0);
+  __syncthreads();
   tc_fence_after();
   PTL(6);
   {
