@@ -461,8 +461,6 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     RUN("gru", gru_cells(e, g, 2, B, st)); ++n;
     GRUProblem g2[2] = {{c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
     RUN("gru", gru_cells(e, g2, 2, B, st)); ++n;
-    GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc}, g[0], g[1], g2[0], g2[1]};
-    RUN("gru_commit", launch_gru_commit(e, all, 5, B, st)); ++n;
   }
   {
     GLProblem pr[2] = {glp(w.erbdec_out, c.herb2, H, c.ed, 512, 1), glp(w.df_skip, c.emb, 512, c.cc, H, 0)};
@@ -480,6 +478,12 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     cudaStreamWaitEvent(sb, e.br_fork[e.cur_lane], 0);
   }
   {
+    // the new GRU states are committed to the slot arena on the forked chain as well: nothing reads them before the next
+    // hop, and the coefficient tail is the shorter of the two (13 us off the critical path of a 1024-stream hop)
+    GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc},
+                         {c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1},
+                         {c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
+    RUN("gru_commit", launch_gru_commit(e, all, 5, B, sb)); ++n;
     GLProblem q = glp(w.df_out, c.cc, H, c.co, NDF * 2 * ORD, 2);
     RUN("gl", launch_gl(e, &q, 1, B, sb)); ++n;
   }
