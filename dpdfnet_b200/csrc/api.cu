@@ -344,6 +344,14 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
   if (e.lane_fork) cudaEventDestroy(e.lane_fork);
   cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_lanes); cudaFree(e.progress_dev);
   cudaFree(e.slots_dev); cudaFree(e.flags_dev); cudaFree(e.stage_in); cudaFree(e.stage_out);
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(e.pipe.in[k]); cudaFree(e.pipe.out[k]); cudaFree(e.pipe.slots[k]); cudaFree(e.pipe.flags[k]);
+    if (e.pipe.h2d_done[k]) cudaEventDestroy(e.pipe.h2d_done[k]);
+    if (e.pipe.step_done[k]) cudaEventDestroy(e.pipe.step_done[k]);
+    if (e.pipe.d2h_done[k]) cudaEventDestroy(e.pipe.d2h_done[k]);
+  }
+  if (e.pipe.in_stream) cudaStreamDestroy(e.pipe.in_stream);
+  if (e.pipe.out_stream) cudaStreamDestroy(e.pipe.out_stream);
   if (e.pinned) cudaFreeHost(e.pinned);
   if (e.err_host) cudaFreeHost(e.err_host);
   if (e.own_stream) cudaStreamDestroy(e.own_stream);
@@ -861,6 +869,82 @@ extern "C" int dpdf_step_pcm_host(dpdf_engine* h, const float* pcm_in, float* pc
   if (int rc = dpdf_run_pcm(h, e.stage_in, e.d.hop, e.stage_out, e.d.hop, s_dev, f_dev, B, 1, st)) return rc;
   CU(cudaMemcpyAsync(pcm_out, e.stage_out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  return check_device_errors(e);
+}
+
+// ---- pipelined host entry ----------------------------------------------------------------------------------------------
+// dpdf_step_pcm_host is synchronous: copy in, hop, copy out, wait - what a caller with one hop of audio in hand does.  A
+// server that always has the next hop ready submits it before collecting the previous one: ticket t's host->device copy
+// (in_stream) and ticket t-1's device->host copy (out_stream) then overlap ticket t-1's / t's kernels (own_stream), and
+// the host never idles in a stream synchronisation between hops.  Two staging sets, so at most two tickets are in flight;
+// submit blocks until ticket t-2 has been delivered.  Host buffers must stay valid (and should be pinned) until dpdf_wait.
+static int ensure_pipe(Engine& e, size_t floats, int B) {
+  Engine::HostPipe& hp = e.pipe;
+  if (!hp.in_stream) {
+    if (cudaStreamCreateWithFlags(&hp.in_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&hp.out_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return fail(DPDF_ERR_CUDA, "pipeline stream creation failed");
+    for (int k = 0; k < 2; ++k)
+      if (cudaEventCreateWithFlags(&hp.h2d_done[k], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&hp.step_done[k], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&hp.d2h_done[k], cudaEventDisableTiming) != cudaSuccess)
+        return fail(DPDF_ERR_CUDA, "pipeline event creation failed");
+  }
+  if (floats > hp.cap || B > hp.cap_ids) {
+    CU(cudaDeviceSynchronize());
+    for (int k = 0; k < 2; ++k) {
+      cudaFree(hp.in[k]); cudaFree(hp.out[k]); cudaFree(hp.slots[k]); cudaFree(hp.flags[k]);
+      hp.in[k] = hp.out[k] = nullptr; hp.slots[k] = hp.flags[k] = nullptr;
+      if (cudaMalloc(&hp.in[k], floats * sizeof(float)) != cudaSuccess || cudaMalloc(&hp.out[k], floats * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&hp.slots[k], B * sizeof(int)) != cudaSuccess || cudaMalloc(&hp.flags[k], B * sizeof(int)) != cudaSuccess)
+        return fail(DPDF_ERR_NOMEM, "pipeline staging alloc failed");
+    }
+    hp.cap = floats;
+    hp.cap_ids = B;
+  }
+  return 0;
+}
+
+extern "C" int dpdf_submit_pcm_host(dpdf_engine* h, const float* pcm_in, float* pcm_out, const int32_t* slot_ids,
+                                    const int32_t* flags, int32_t B, int64_t* ticket) {
+  if (!h || !pcm_in || !pcm_out || !ticket) return fail(DPDF_ERR_INVALID, "NULL argument");
+  Engine& e = h->e;
+  if (int rc = check_batch(e, B)) return rc;
+  CU(cudaSetDevice(e.device));
+  const size_t n = (size_t)B * e.d.hop;
+  if (int rc = ensure_pipe(e, n, B)) return rc;
+  Engine::HostPipe& hp = e.pipe;
+  const long long t = hp.submitted;
+  const int k = (int)(t & 1);
+  if (t >= 2) CU(cudaEventSynchronize(hp.d2h_done[k]));            // ticket t-2 delivered: staging set k is free
+  if (slot_ids)
+    for (int i = 0; i < B; ++i)
+      if (slot_ids[i] < 0 || slot_ids[i] >= e.max_streams) return fail(DPDF_ERR_INVALID, "slot %d out of range", slot_ids[i]);
+  CU(cudaMemcpyAsync(hp.in[k], pcm_in, n * sizeof(float), cudaMemcpyHostToDevice, hp.in_stream));
+  if (slot_ids) CU(cudaMemcpyAsync(hp.slots[k], slot_ids, B * sizeof(int), cudaMemcpyHostToDevice, hp.in_stream));
+  if (flags) CU(cudaMemcpyAsync(hp.flags[k], flags, B * sizeof(int), cudaMemcpyHostToDevice, hp.in_stream));
+  CU(cudaEventRecord(hp.h2d_done[k], hp.in_stream));
+  CU(cudaStreamWaitEvent(e.own_stream, hp.h2d_done[k], 0));
+  if (int rc = dpdf_run_pcm(h, hp.in[k], e.d.hop, hp.out[k], e.d.hop, slot_ids ? hp.slots[k] : nullptr, flags ? hp.flags[k] : nullptr, B, 1,
+                            e.own_stream))
+    return rc;
+  CU(cudaEventRecord(hp.step_done[k], e.own_stream));
+  CU(cudaStreamWaitEvent(hp.out_stream, hp.step_done[k], 0));
+  CU(cudaMemcpyAsync(pcm_out, hp.out[k], n * sizeof(float), cudaMemcpyDeviceToHost, hp.out_stream));
+  CU(cudaEventRecord(hp.d2h_done[k], hp.out_stream));
+  *ticket = t;
+  ++hp.submitted;
+  return 0;
+}
+
+extern "C" int dpdf_wait(dpdf_engine* h, int64_t ticket) {
+  if (!h) return fail(DPDF_ERR_INVALID, "NULL engine");
+  Engine& e = h->e;
+  Engine::HostPipe& hp = e.pipe;
+  if (ticket < 0 || ticket >= hp.submitted) return fail(DPDF_ERR_INVALID, "unknown ticket %lld", (long long)ticket);
+  if (ticket + 2 < hp.submitted) return check_device_errors(e);     // already overwritten by a later ticket: delivered long ago
+  CU(cudaSetDevice(e.device));
+  CU(cudaEventSynchronize(hp.d2h_done[ticket & 1]));
   return check_device_errors(e);
 }
 

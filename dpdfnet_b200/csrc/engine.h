@@ -160,6 +160,16 @@ struct Engine {
   float* stage_in = nullptr;      // device staging for *_host entry points
   float* stage_out = nullptr;
   size_t stage_in_floats = 0, stage_out_floats = 0;
+  // 2-deep host pipeline (dpdf_submit_pcm_host / dpdf_wait): H2D, hop and D2H of consecutive tickets on three streams
+  struct HostPipe {
+    float *in[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};
+    int *slots[2] = {nullptr, nullptr}, *flags[2] = {nullptr, nullptr};
+    size_t cap = 0;               // floats per staging buffer
+    int cap_ids = 0;
+    cudaEvent_t h2d_done[2] = {}, step_done[2] = {}, d2h_done[2] = {};
+    cudaStream_t in_stream = nullptr, out_stream = nullptr;
+    long long submitted = 0;
+  } pipe;
   float* pinned = nullptr;        // pinned host staging
   size_t pinned_floats = 0;
   cudaStream_t own_stream = nullptr;

@@ -48,6 +48,8 @@ C_API = {
     "dpdf_step_spec_host": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32]),
     "dpdf_step_pcm_host": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32]),
     "dpdf_run_pcm_host": (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int32, ctypes.c_int32]),
+    "dpdf_submit_pcm_host": (ctypes.c_int, [ctypes.c_void_p] * 5 + [ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]),
+    "dpdf_wait": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "dpdf_state_size": (ctypes.c_int, [ctypes.c_void_p]),
     "dpdf_state_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
     "dpdf_state_import": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]),
@@ -268,6 +270,22 @@ class Engine:
         s, f = self._host_int(slot_ids, B), self._host_int(flags, B)
         self._check(self._lib.dpdf_step_pcm_host(self._handle, _ptr(x), _ptr(out), _ptr(s), _ptr(f), B))
         return out
+
+    def submit_pcm_host(self, pcm: np.ndarray, out: np.ndarray, slot_ids=None, flags=None) -> int:
+        """Pipelined form of ``step_pcm_host``: returns a ticket at once; ``wait(ticket)`` delivers ``out``.  ``pcm`` and
+        ``out`` must be C-contiguous float32 [B, hop] arrays that stay alive (ideally pinned) until the wait."""
+        if pcm.dtype != np.float32 or not pcm.flags.c_contiguous or pcm.ndim != 2 or pcm.shape[1] != self.spec.hop:
+            raise ValueError(f"pcm must be a C-contiguous float32 [B, {self.spec.hop}] array")
+        if out.shape != pcm.shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array shaped like pcm")
+        B = pcm.shape[0]
+        s, f = self._host_int(slot_ids, B), self._host_int(flags, B)
+        t = ctypes.c_int64()
+        self._check(self._lib.dpdf_submit_pcm_host(self._handle, _ptr(pcm), _ptr(out), _ptr(s), _ptr(f), B, ctypes.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket: int) -> None:
+        self._check(self._lib.dpdf_wait(self._handle, int(ticket)))
 
     def run_pcm_host(self, pcm: np.ndarray, slot_ids=None) -> np.ndarray:
         x = np.ascontiguousarray(pcm, dtype=np.float32)

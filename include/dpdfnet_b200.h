@@ -111,6 +111,16 @@ int dpdf_step_pcm_host(dpdf_engine* e, const float* pcm_in, float* pcm_out, cons
 int dpdf_run_pcm_host(dpdf_engine* e, const float* pcm_in, float* pcm_out, const int32_t* slot_ids,
                       int32_t B, int32_t T);
 
+/* Pipelined host entry for callers that always have the next hop in hand (a server feeding fixed 10 ms packets): submit
+ * returns at once with a ticket; the host->device copy of ticket t and the device->host copy of ticket t-1 overlap the
+ * kernels of the neighbouring ticket on separate CUDA streams.  At most two tickets are in flight (submit blocks until
+ * ticket t-2 has been delivered); pcm_in / pcm_out must stay valid until dpdf_wait(ticket) returns and should be pinned
+ * (pageable memory makes the copies synchronous).  Same arithmetic as dpdf_step_pcm_host, hop for hop.  Do not mix with the
+ * synchronous *_host calls while tickets are outstanding. */
+int dpdf_submit_pcm_host(dpdf_engine* e, const float* pcm_in, float* pcm_out, const int32_t* slot_ids,
+                         const int32_t* flags, int32_t B, int64_t* ticket);
+int dpdf_wait(dpdf_engine* e, int64_t ticket);
+
 /* Flat state vector of one slot in the reference layout (onnx_model/dpdfnet.py:737-746):
  * drop-in for StreamEnhancer._state / the `state_in`,`state_out` tensors.  HOST buffers of
  * dpdf_state_size() floats; synchronous. */

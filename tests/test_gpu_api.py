@@ -137,3 +137,36 @@ def test_enhance_batch_resamples_on_the_device(random_weights):
         ref = ensure_sample_rate(m, 16000, 48000)
         n = min(ref.size, c.size)
         assert np.abs(g[:n] - ref[:n]).max() < 1e-4
+
+
+def test_pipelined_host_entry_equals_the_synchronous_one(random_weights):
+    """dpdf_submit_pcm_host / dpdf_wait (two hops in flight, copies on their own streams) == dpdf_step_pcm_host hop for hop,
+    with slot indirection and per-row flags."""
+    import torch
+    from dpdfnet_b200.engine import Engine
+    B, T = 300, 9
+    eng_a, eng_b = Engine("dpdfnet2", None, max_streams=B + 4), Engine("dpdfnet2", None, max_streams=B + 4)
+    hop = eng_a.spec.hop
+    rng = np.random.default_rng(2)
+    slots = rng.permutation(B + 4)[:B].astype(np.int32)
+    pin_in = torch.from_numpy((rng.standard_normal((T, B, hop)) * 0.1).astype(np.float32)).pin_memory().numpy()
+    pin_out = torch.empty(2, B, hop).pin_memory().numpy()
+    flags = np.zeros(B, np.int32)
+    flags[::7] = 1                                                # WARMUP rows on the first two hops
+    ref = [eng_a.step_pcm_host(pin_in[t], slot_ids=slots, flags=flags if t < 2 else None).copy() for t in range(T)]
+    got, prev = [], None
+    for t in range(T):
+        tk = eng_b.submit_pcm_host(pin_in[t], pin_out[t & 1], slot_ids=slots, flags=flags if t < 2 else None)
+        if prev is not None:
+            eng_b.wait(prev)
+            got.append(pin_out[(t - 1) & 1].copy())
+        prev = tk
+    eng_b.wait(prev)
+    got.append(pin_out[(T - 1) & 1].copy())
+    for t in range(T):
+        assert np.array_equal(got[t], ref[t]), t
+    assert np.array_equal(eng_a.state_export(int(slots[5])), eng_b.state_export(int(slots[5])))
+    with pytest.raises(ValueError):
+        eng_b.wait(10 ** 6)
+    eng_a.close()
+    eng_b.close()
