@@ -434,6 +434,10 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     ++n;
   }
   const float* xe_final = d.N > 0 ? c.xe : c.e3;
+  const bool pdl_saved = e.pdl_now;
+  const bool tail_chain = e.tail_pdl && !e.timing && !e.pdl_now;
+  if (tail_chain) { e.pdl_now = true; e.pdl_first = true; }    // dense tail as a PDL chain (Engine::tail_pdl); its first kernel is a plain
+                                                               // launch: it must see the whole DPRNN stack (overlapped post kernels included)
   auto glp = [&](const GLW& gw, const float* in0, int ld0, float* out, int ldo, int act) {
     GLProblem q{};
     q.in0 = in0; q.ld0 = ld0; q.in1 = nullptr; q.ld1 = 0; q.split = 1 << 30; q.w = gw; q.out = out; q.ldo = ldo; q.col0 = 0;
@@ -446,6 +450,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     pr[np++] = glp(w.df_fc_emb, c.c1, (NDF / 2) * C, c.cemb, 512, 1);
     if (d.hr48) pr[np++] = glp(w.erb_fc_emb, xe_final, d.fe[3] * C, c.emb_e, 512, 1);
     RUN("gl", launch_gl(e, pr, np, B, st)); ++n;
+    if (tail_chain) e.pdl_first = false;
   }
   {
     GLProblem q = glp(w.enc_in, d.hr48 ? c.emb_e : xe_final, 512, c.g0, H, 1);
@@ -475,6 +480,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     pr[1].addend = c.hdf2; pr[1].lda = H;
     RUN("gl", launch_gl(e, pr, 2, B, st)); ++n;
   }
+  e.pdl_now = pdl_saved;
   // The two decoder tails are independent until the synthesis kernel: the deep-filter coefficients (df_out linear +
   // pathway conv) run on a forked stream beside the ERB decoder's transposed-conv stack (graph capture turns the events
   // into dependencies); sequential while timing with events.
@@ -1171,6 +1177,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     drop_graphs(e);
   } else if (strcmp(key, "dfp_ps") == 0) {
     e.dfp_ps = value ? 1 : 0;                      // switch only on freshly reset streams: the two forms keep different state
+    drop_graphs(e);
+  } else if (strcmp(key, "tail_pdl") == 0) {
+    e.tail_pdl = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "pdl") == 0) {
     e.pdl = value ? 1 : 0;

@@ -209,6 +209,9 @@ struct Engine {
                                   // read per stream-hop, but measured slower (0.48 vs 0.27 ms at 8192 streams: the 50-value
                                   // reduce-scatter and the dependent read-modify-writes cost more than the ring read saves)
   std::vector<float> dfp_w_host;  // [10][5][32] for rebuilding the pending sums at state import
+  int tail_pdl = 1;               // option (measured -0.6 % hop time at 1024 and 16 384 streams, profiles/r2s_sweep.log): programmatic dependent launches for the dense per-stream tail only (grouped linears + GRU
+                                  // cells between the last DPRNN block and the decoder fork): eight tiny dependent kernels whose
+                                  // prologues and weight prefetches can run under their predecessor
   int pdl = 0;                    // option: chain ALL kernels of a hop with programmatic dependent launches (measured slower: early-resident waiters crowd the running kernel)
   bool pdl_now = false;           // decided per enqueue_step (off while timing with events)
   bool pdl_first = false;         // next launch is the first kernel of a chain: plain launch

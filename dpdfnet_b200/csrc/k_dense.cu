@@ -17,8 +17,7 @@ struct GLParams {
 
 template <int NJ>
 __global__ void __launch_bounds__(256) k_gl(GLParams p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_trigger();        // griddepcontrol.wait sits between the weight loads and the activation loads
   extern __shared__ __align__(16) float smem[];
   int pi = 0;
 #pragma unroll
@@ -39,15 +38,16 @@ __global__ void __launch_bounds__(256) k_gl(GLParams p) {
   int ld;
   if (q.in1 == nullptr || incol < q.split) { src = q.in0 + incol; ld = q.ld0; }
   else { src = q.in1 + (incol - q.split); ld = q.ld1; }
-  for (int i = tid; i < 64 * kch; i += 256) {
-    const int r = i / kch, c = (i % kch) * 4;
-    if (r < valid) cp_async16(As + r * LD + c, src + (size_t)(b0 + r) * ld + c);
-    else *reinterpret_cast<float4*>(As + r * LD + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   const float* wg = q.w.w + (size_t)g * Ng * Kg;
   for (int i = tid; i < Ng * kch; i += 256) {
     const int r = i / kch, c = (i % kch) * 4;
     cp_async16(Ws + r * LD + c, wg + (size_t)r * Kg + c);
+  }
+  pdl_wait();                                                 // the activations are the previous kernel's output
+  for (int i = tid; i < 64 * kch; i += 256) {
+    const int r = i / kch, c = (i % kch) * 4;
+    if (r < valid) cp_async16(As + r * LD + c, src + (size_t)(b0 + r) * ld + c);
+    else *reinterpret_cast<float4*>(As + r * LD + c) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   cp_async_commit();
   cp_async_wait<0>();

@@ -35,8 +35,7 @@ struct GRUTcParams {
 };
 
 __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_trigger();        // griddepcontrol.wait comes after the prologue and the first weight slabs: neither depends on the previous kernel
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* Asm = smem_raw;
   unsigned char* Wsm = smem_raw + GT_OFF_W;
@@ -71,6 +70,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
       bulk_g2s(Wsm + (s % 3) * GT_WSLAB, wsrc + (size_t)s * GT_WSLAB, GT_WSLAB, full_w + s % 3);
     };
     if (lane == 0) { load_w(0); load_w(1); load_w(2); }
+    pdl_wait();
     for (int s = 0; s < 8; ++s) {
       const int buf = s & 1;
       if (buf == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT_NT) : "memory");      // A images of stage s written
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
     // so a warp's 8-byte stores fill two whole 128-byte core matrices
     const int g = (tid >> 3) & 15;
     const int rsub = (tid & 7) | ((tid >> 7) << 3);
+    pdl_wait();                                               // x and h_prev come from the kernels before this one
     uint32_t ovf = 0;                                         // FP16 range guard (tc_common.cuh:f16_nonfinite)
     for (int s = 0; s < 8; ++s) {
       const int buf = s & 1, k0 = (s & 3) * 64 + g * 4;
