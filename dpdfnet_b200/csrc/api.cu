@@ -384,6 +384,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   const Weights& w = e.w;
   Scratch& c = e.sc;
   int n = 0;
+  const bool seg_pdl = e.pdl == 2 && !e.timing;            // PDL chains everywhere but across the DPRNN stack
   e.pdl_now = e.pdl && !e.timing;
   e.pdl_first = true;                                      // the analysis kernel follows a copy / an event, not a kernel
   const bool use_sep_tc = e.sep_tc == 1 || (e.sep_tc == 2 && std::max(B, e.total_B) >= e.sep_tc_min);
@@ -425,6 +426,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   }
   const bool intra_on_tc = e.intra_tc == 1 || (e.intra_tc == 2 && std::max(B, e.total_B) >= e.intra_tc_min);
   e.overlap_now = e.overlap_now && intra_on_tc && !e.timing;        // requested by the caller (enqueue_lanes / run_hops_free)
+  if (seg_pdl) e.pdl_now = false;
   for (int i = 0; i < d.N; ++i) {
     if (intra_on_tc) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
     else { RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); }
@@ -435,7 +437,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   }
   const float* xe_final = d.N > 0 ? c.xe : c.e3;
   const bool pdl_saved = e.pdl_now;
-  const bool tail_chain = e.tail_pdl && !e.timing && !e.pdl_now;
+  const bool tail_chain = (e.tail_pdl || seg_pdl) && !e.timing && !e.pdl_now;
   if (tail_chain) { e.pdl_now = true; e.pdl_first = true; }    // dense tail as a PDL chain (Engine::tail_pdl); its first kernel is a plain
                                                                // launch: it must see the whole DPRNN stack (overlapped post kernels included)
   auto glp = [&](const GLW& gw, const float* in0, int ld0, float* out, int ldo, int act) {
@@ -480,7 +482,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     pr[1].addend = c.hdf2; pr[1].lda = H;
     RUN("gl", launch_gl(e, pr, 2, B, st)); ++n;
   }
-  e.pdl_now = pdl_saved;
+  e.pdl_now = pdl_saved || seg_pdl;
   // The two decoder tails are independent until the synthesis kernel: the deep-filter coefficients (df_out linear +
   // pathway conv) run on a forked stream beside the ERB decoder's transposed-conv stack (graph capture turns the events
   // into dependencies); sequential while timing with events.
@@ -497,7 +499,9 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc},
                          {c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1},
                          {c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
+    if (fork) e.pdl_first = true;                            // first kernel of the forked chain: its predecessor is an event, not a kernel
     RUN("gru_commit", launch_gru_commit(e, all, 5, B, sb)); ++n;
+    e.pdl_first = false;
     GLProblem q = glp(w.df_out, c.cc, H, c.co, NDF * 2 * ORD, 2);
     RUN("gl", launch_gl(e, &q, 1, B, sb)); ++n;
   }
@@ -1182,7 +1186,8 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     e.tail_pdl = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "pdl") == 0) {
-    e.pdl = value ? 1 : 0;
+    if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "pdl must be 0 (off), 1 (whole hop) or 2 (all segments but the DPRNN stack)");
+    e.pdl = value;
     drop_graphs(e);
   } else if (strcmp(key, "overlap") == 0 || strcmp(key, "overlap_max") == 0) {
     if (key[7] == 0) e.overlap = value ? 1 : 0;
