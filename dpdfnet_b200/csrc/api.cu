@@ -293,7 +293,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
       cudaMalloc(&e.flags_dev, max_streams * sizeof(int)) != cudaSuccess)
     return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(io) failed"));
   e.io_dev = e.io_lanes;
-  e.progress_tiles = (max_streams + 127) / 128 + 1;
+  e.progress_tiles = (max_streams + 31) / 32 + 1;            // sweep tiles are 128 / D streams, D <= 4
   if (cudaMalloc(&e.progress_dev, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int)) != cudaSuccess)
     return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(progress) failed"));
   cudaMemset(e.progress_dev, 0, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int));
@@ -1161,6 +1161,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     } else {
       e.intra_tc_min = value;
     }
+    drop_graphs(e);
+  } else if (strcmp(key, "intra_dup") == 0) {
+    if (value != 0 && value != 1 && value != 2 && value != 4) return fail(DPDF_ERR_INVALID, "intra_dup must be 0 (auto), 1, 2 or 4");
+    e.intra_dup = value;
     drop_graphs(e);
   } else if (strcmp(key, "gru_tc") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "gru_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");

@@ -113,6 +113,7 @@ void launch_dprnn_intra(Engine& e, int blk, int B, cudaStream_t st);
 void launch_dprnn_post(Engine& e, int blk, int B, cudaStream_t st);
 void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st);
 void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st);
+int intra_tc_dup(const Engine& e, int B);   // stream tiles of the sweep are 128 / D streams
 
 struct GLProblem {
   const float* in0; int ld0;     // input columns [0, split)
@@ -189,6 +190,7 @@ struct Engine {
   int intra_bt = 0;               // 0 = auto
   int intra_tc = 2;               // intra-frame GRU on tcgen05 (FP16 split): 0 never, 1 always, 2 = when B >= intra_tc_min
   int intra_tc_min = 1024;
+  int intra_dup = 0;              // k_dprnn_intra_tc row duplication D (128 / D streams per CTA): 0 = auto (largest D whose sweep fits one wave), 1, 2, 4
   int gru_tc = 2;                 // GRUCell(256) gate GEMMs on tcgen05: 0 never, 1 always, 2 = when B >= gru_tc_min
   int gru_tc_min = 256;
   int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min

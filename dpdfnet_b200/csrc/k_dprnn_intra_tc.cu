@@ -19,6 +19,16 @@
 //                  the next step and as FP32 to hcat[b][f][dir*64 + u]; convert the prefetched x_{t+2} tile.
 // The x-part MMAs and the global loads of x are hidden behind the gate math of the previous step, and the recurrent
 // MMAs of step t+1 are issued per K slice (16 units) as soon as the gate warps have produced that slice of h_t.
+//
+// Row duplication (template parameter D = 1, 2, 4).  A step of the sweep is bound by the gate math of its 128 x 64
+// (stream, unit) pairs, not by the tensor core, and at latency batch sizes most SMs are idle (32 CTAs per 1024
+// streams).  With D > 1 a CTA owns only 128 / D streams and every stream occupies D rows of the M = 128 tile: the
+// MMAs are unchanged (an M = 64 instruction would cost the same tensor time, B300_MICROARCH "tcgen05 floor"), rows
+// (s, 0..D-1) carry identical operands and therefore identical accumulators, and the thread of row (s, part) does the
+// gate math of only 4 / D of the cg-group's units per K slice.  The D rows of a stream sit in the same warp (lanes
+// l + part * 32 / D), so the partners exchange their h units with shuffles before every thread writes the complete
+// operand columns of its own row with tcgen05.st.  Per-step gate work per CTA drops by D and the sweep spreads over
+// D times as many SMs (128 CTAs at 1024 streams with D = 4).
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -86,7 +96,7 @@ struct IntraTcParams {
   int Fp[2];
   const float* wimg[2];   // [2 dirs][W_ih hi | W_ih lo | W_hh hi | W_hh lo] FP16 operand images
   const float* bias[2];   // [2][4][64], exponent scales folded in (weights.py: tc.intra_bias)
-  int tiles;              // ceil(B / 128)
+  int tiles;              // ceil(B / (128 / D)): stream tiles of the sweep
   int B;
   int* progress;          // [2 branches][2 dirs][tiles] completed steps of each CTA, or nullptr (overlapped post kernel)
   int* err;               // engine error words (IoDesc::err), may be nullptr
@@ -105,11 +115,17 @@ struct IntraTcParams {
 #define TL(slot) do { } while (0)
 #endif
 
+template <int D>
 #ifdef ITC_MAXNREG
 __global__ void __maxnreg__(ITC_MAXNREG) k_dprnn_intra_tc(IntraTcParams p) {
 #else
 __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
 #endif
+  static_assert(D == 1 || D == 2 || D == 4, "row duplication factor");
+  constexpr int SPC = 128 / D;        // streams per CTA
+  constexpr int LPQ = 32 / D;         // lanes of a warp (TMEM lane quadrant) that hold distinct streams
+  constexpr int UPS = 4 / D;          // units per gate thread and K slice
+  constexpr int NX = D == 1 ? 2 : 1;  // x staging items per thread
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* Wsm = smem_raw;
   unsigned char* Xsm = smem_raw + OFF_X;
@@ -119,13 +135,15 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
+  const int qd = warp & 3, cg = warp >> 2;
+  const int part = lane / LPQ;                               // which of the D rows of its stream this thread is
+  const int srow = qd * LPQ + (lane % LPQ);                  // the stream's row in the CTA's staging tiles
   const int item = blockIdx.x;
   const int br = item / (2 * p.tiles);
   const int dir = (item % (2 * p.tiles)) / p.tiles;
   const int tile = item % p.tiles;
   const int T = br ? p.Fp[1] : p.Fp[0];
-  const int b0 = tile * 128;
+  const int b0 = tile * SPC;
   const float* __restrict__ xg = br ? p.x[1] : p.x[0];
   float* __restrict__ hg = br ? p.hcat[1] : p.hcat[0];
 
@@ -151,18 +169,20 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
     for (int i = 0; i < 4; ++i) bulk_g2s(Wsm + i * W_IMG, src + (size_t)i * W_IMG, W_IMG, bars);
   }
 
-  // ---- x tile staging: 128 rows x 8 chunks of 8 floats, two (row, chunk) items per thread ------------------
-  // warp item j = warp + 16 i covers row group j >> 1, K half j & 1: lanes = 8 rows x 4 chunks, so the 16-byte
-  // operand rows a warp writes are four contiguous 128-byte core matrices (conflict-free)
+  // ---- x tile staging: SPC streams x 8 chunks of 8 floats, NX (stream, chunk) items per thread ---------------
+  // warp item j = warp + 16 i covers stream group j >> 1, K half j & 1: lanes = 8 streams x 4 chunks, so the 16-byte
+  // operand rows a warp writes are four contiguous 128-byte core matrices (conflict-free); every item is stored to
+  // the D operand rows of its stream (D = 4: 256 items, the upper eight warps have none)
+  const bool x_active = D < 4 || warp < 8;
   const int xr_[2] = {((warp) >> 1) * 8 + (lane & 7), ((warp + 16) >> 1) * 8 + (lane & 7)};
   const int xkc = (warp & 1) * 4 + (lane >> 3);
-  auto load_x = [&](int t, float (&v)[2][8]) {
+  auto load_x = [&](int t, float (&v)[NX][8]) {
     const int f = dir ? T - 1 - t : t;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NX; ++i) {
       const int bb = b0 + xr_[i];
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-      if (bb < p.B) {
+      if (bb < p.B && x_active) {
         const float4* src = reinterpret_cast<const float4*>(xg + ((size_t)bb * T + f) * C + xkc * 8);
         a = __ldg(src);
         c = __ldg(src + 1);
@@ -171,18 +191,23 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
       v[i][4] = c.x; v[i][5] = c.y; v[i][6] = c.z; v[i][7] = c.w;
     }
   };
-  auto store_x1 = [&](int buf, const float (&v)[2][8], int i) {
+  auto store_x1 = [&](int buf, const float (&v)[NX][8], int i) {
+    if (!x_active) return;
     uint4 hi, lo;
     split8_f16(v[i], hi, lo);
     // FP16 range guard (tc_common.cuh:f16_nonfinite); stored at once: a flag word would be a live register of the gate warps
     if ((f16_nonfinite(hi.x) | f16_nonfinite(hi.y) | f16_nonfinite(hi.z) | f16_nonfinite(hi.w)) && p.err) p.err[DPDF_ERRW_RANGE] = 1;
-    unsigned char* dst = Xsm + buf * 2 * A_IMG + img16_off(xr_[i], xkc);
-    *reinterpret_cast<uint4*>(dst) = hi;
-    *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
+#pragma unroll
+    for (int pt = 0; pt < D; ++pt) {                         // operand row of (stream, part): quadrant, part block, lane
+      const int r = (xr_[i] / LPQ) * 32 + pt * LPQ + (xr_[i] % LPQ);
+      unsigned char* dst = Xsm + buf * 2 * A_IMG + img16_off(r, xkc);
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
+    }
   };
-  auto store_x = [&](int buf, const float (&v)[2][8]) {
-    store_x1(buf, v, 0);
-    store_x1(buf, v, 1);
+  auto store_x = [&](int buf, const float (&v)[NX][8]) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) store_x1(buf, v, i);
   };
   // Everything above (barriers, TMEM, the 96 KB of weight images) overlaps with the tail of the previous kernel.
   pdl_wait();
@@ -192,7 +217,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   }
   __syncthreads();
   pdl_trigger();                                             // every CTA of this grid is resident (or done): dependents may launch
-  float xv[2][8];
+  float xv[NX][8];
   if (warp < 16) {
     load_x(0, xv);
     store_x(0, xv);
@@ -299,23 +324,31 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
     // inside step s + 1, under the MUFU-bound gate math: passing the accumulator barrier of step s + 1 proves that every
     // warp has finished writing staging[s & 1], and the buffer is not rewritten before step s + 2, which no warp can
     // reach before all warps have handed over the last slice of step s + 1 (after this copy).
-    const int nvalid = min(128, p.B - b0);
+    const int nvalid = min(SPC, p.B - b0);
     auto write_out = [&](int s_) {
       const int f = dir ? T - 1 - s_ : s_;
       const unsigned char* sbuf = Ssm + (s_ & 1) * ST_BUF;
       float* gdst = hg + ((size_t)b0 * T + f) * 2 * C + dir * C + (tid & 15) * 4;
-      float4 v[4];
+      float4 v[UPS];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < UPS; ++i) {
         const int r = (tid >> 4) + 32 * i;
         v[i] = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < UPS; ++i) {
         const int r = (tid >> 4) + 32 * i;
         if (r < nvalid) *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = v[i];
       }
     };
+    // the thread's own UPS units out of the four columns of its cg group (a tcgen05.ld address is warp-uniform, so the
+    // D parts of a warp load the same four columns and select)
+    auto own = [&](const uint32_t (&g)[4], int j) -> float {
+      if constexpr (D == 1) return __uint_as_float(g[j]);
+      else if constexpr (D == 2) return __uint_as_float(part ? g[2 + j] : g[j]);
+      else return __uint_as_float((part & 2) ? ((part & 1) ? g[3] : g[2]) : ((part & 1) ? g[1] : g[0]));
+    };
+    const int uoff = UPS * part;                             // first own unit inside the cg group's four
     for (int t = 0; t < T; ++t) {
       TL(0);
       if (t + 2 < T) load_x(t + 2, xv);                      // in flight during the wait
@@ -337,59 +370,83 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
       tmem_ld4_nowait(pa + 128, gi);
       tmem_ld_wait();
       TL(2);
-      unsigned char* srow = Ssm + (t & 1) * ST_BUF + row * 256;
-      const unsigned char* prow = Ssm + ((t + 1) & 1) * ST_BUF + row * 256;      // h_{t-1} of this thread's units (FP32)
+      unsigned char* srow_w = Ssm + (t & 1) * ST_BUF + srow * 256 + uoff * 4;
+      const unsigned char* prow = Ssm + ((t + 1) & 1) * ST_BUF + srow * 256 + uoff * 4;      // h_{t-1} of this thread's units (FP32)
       const float2 one = make_float2(1.0f, 1.0f);
       // sigmoid stage: r = 1 / (1 + 2^a_r), z = 1 / (1 + 2^a_z) with one shared reciprocal.  The operand images and
       // biases carry the exponent scales (weights.py: r, z rows x -log2(e); n rows x 2 log2(e)).
-      auto stage_a = [&](int ks, const uint32_t (&g_r)[4], const uint32_t (&g_z)[4], float2 (&r)[2], float2 (&z)[2]) {
-        const int u0 = 16 * ks + 4 * cg;
+      auto stage_a = [&](int ks, const uint32_t (&g_r)[4], const uint32_t (&g_z)[4], float (&r)[UPS], float (&z)[UPS]) {
+        const int u0 = 16 * ks + 4 * cg + uoff;
+        if constexpr (UPS >= 2) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float2 b_r = *reinterpret_cast<const float2*>(sb + u0 + 2 * e);
-          const float2 b_z = *reinterpret_cast<const float2*>(sb + C + u0 + 2 * e);
-          const float2 ar = __fadd2_rn(make_float2(__uint_as_float(g_r[2 * e]), __uint_as_float(g_r[2 * e + 1])), b_r);
-          const float2 az = __fadd2_rn(make_float2(__uint_as_float(g_z[2 * e]), __uint_as_float(g_z[2 * e + 1])), b_z);
+          for (int e = 0; e < UPS / 2; ++e) {
+            const float2 b_r = *reinterpret_cast<const float2*>(sb + u0 + 2 * e);
+            const float2 b_z = *reinterpret_cast<const float2*>(sb + C + u0 + 2 * e);
+            const float2 ar = __fadd2_rn(make_float2(own(g_r, 2 * e), own(g_r, 2 * e + 1)), b_r);
+            const float2 az = __fadd2_rn(make_float2(own(g_z, 2 * e), own(g_z, 2 * e + 1)), b_z);
 #if ITC_POLY
-          const float2 pr = __fadd2_rn(ex2_poly2(make_float2(clampf(ar.x, -125.f, 60.f), clampf(ar.y, -125.f, 60.f))), one);
-          const float2 pz = __fadd2_rn(ex2_poly2(make_float2(clampf(az.x, -125.f, 60.f), clampf(az.y, -125.f, 60.f))), one);
+            const float2 pr = __fadd2_rn(ex2_poly2(make_float2(clampf(ar.x, -125.f, 60.f), clampf(ar.y, -125.f, 60.f))), one);
+            const float2 pz = __fadd2_rn(ex2_poly2(make_float2(clampf(az.x, -125.f, 60.f), clampf(az.y, -125.f, 60.f))), one);
 #else
-          // 2^60 * 2^60 stays finite in the shared reciprocal; sigmoid(-41) = 1e-18 is already 0 in FP32 terms
-          const float2 pr = __fadd2_rn(make_float2(ex2_ftz(fminf(ar.x, 60.f)), ex2_ftz(fminf(ar.y, 60.f))), one);
-          const float2 pz = __fadd2_rn(make_float2(ex2_ftz(fminf(az.x, 60.f)), ex2_ftz(fminf(az.y, 60.f))), one);
+            // 2^60 * 2^60 stays finite in the shared reciprocal; sigmoid(-41) = 1e-18 is already 0 in FP32 terms
+            const float2 pr = __fadd2_rn(make_float2(ex2_ftz(fminf(ar.x, 60.f)), ex2_ftz(fminf(ar.y, 60.f))), one);
+            const float2 pz = __fadd2_rn(make_float2(ex2_ftz(fminf(az.x, 60.f)), ex2_ftz(fminf(az.y, 60.f))), one);
 #endif
-          const float2 pp = __fmul2_rn(pr, pz);
-          const float2 ip = make_float2(rcp_ftz(pp.x), rcp_ftz(pp.y));
-          r[e] = __fmul2_rn(ip, pz);
-          z[e] = __fmul2_rn(ip, pr);
+            const float2 pp = __fmul2_rn(pr, pz);
+            const float2 ip = make_float2(rcp_ftz(pp.x), rcp_ftz(pp.y));
+            const float2 rr = __fmul2_rn(ip, pz), zz = __fmul2_rn(ip, pr);
+            r[2 * e] = rr.x; r[2 * e + 1] = rr.y;
+            z[2 * e] = zz.x; z[2 * e + 1] = zz.y;
+          }
+        } else {                                             // one unit: r and z share the packed lanes instead
+          const float2 a = __fadd2_rn(make_float2(own(g_r, 0), own(g_z, 0)), make_float2(sb[u0], sb[C + u0]));
+          const float2 pq = __fadd2_rn(make_float2(ex2_ftz(fminf(a.x, 60.f)), ex2_ftz(fminf(a.y, 60.f))), one);
+          const float ip = rcp_ftz(pq.x * pq.y);
+          r[0] = ip * pq.y;
+          z[0] = ip * pq.x;
         }
       };
-      float2 rc[2], zc[2];
+      float rc[UPS], zc[UPS];
       stage_a(0, grz[0][0], grz[0][1], rc, zc);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        const int u0 = 16 * ks + 4 * cg;
-        float2 rn[2], zn[2];
+        const int u0 = 16 * ks + 4 * cg + uoff;
+        float rn[UPS], zn[UPS];
         if (ks < 3) stage_a(ks + 1, grz[(ks + 1) & 1][0], grz[(ks + 1) & 1][1], rn, zn);
         // tanh stage: n = tanh(c) = 1 - 2 / (1 + 2^c'),  h' = (1 - z) n + z h
-        const float4 hp4 = *reinterpret_cast<const float4*>(prow + (((4 * ks + cg) ^ (row & 15)) << 4));
-        float hn[4];
+        const int hchunk = ((4 * ks + cg) ^ (srow & 15)) << 4;
+        float hp[UPS], hn[UPS];
+        if constexpr (UPS == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(prow + hchunk);
+          hp[0] = q.x; hp[1] = q.y; hp[2] = q.z; hp[3] = q.w;
+        } else if constexpr (UPS == 2) {
+          const float2 q = *reinterpret_cast<const float2*>(prow + hchunk);
+          hp[0] = q.x; hp[1] = q.y;
+        } else {
+          hp[0] = *reinterpret_cast<const float*>(prow + hchunk);
+        }
 #ifdef ITC_NO_MATH
-        hn[0] = rc[0].x * 1e-30f + hp4.x; hn[1] = zc[0].y * 1e-30f + hp4.y; hn[2] = __uint_as_float(gi[2] ^ ghn[ks][2]) * 1e-30f + hp4.z; hn[3] = hp4.w;
-#else
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float2 b_i = *reinterpret_cast<const float2*>(sb + 2 * C + u0 + 2 * e);
-          const float2 b_h = *reinterpret_cast<const float2*>(sb + 3 * C + u0 + 2 * e);
-          const float2 vhn = __fadd2_rn(make_float2(__uint_as_float(ghn[ks][2 * e]), __uint_as_float(ghn[ks][2 * e + 1])), b_h);
-          const float2 vin = __fadd2_rn(make_float2(__uint_as_float(gi[2 * e]), __uint_as_float(gi[2 * e + 1])), b_i);
-          const float2 c = __ffma2_rn(rc[e], vhn, vin);
-          const float2 pc = __fadd2_rn(make_float2(ex2_ftz(c.x), ex2_ftz(c.y)), one);
-          const float2 q = make_float2(rcp_ftz(pc.x), rcp_ftz(pc.y));
-          const float2 n = __ffma2_rn(make_float2(-2.0f, -2.0f), q, one);
-          const float2 hp = e ? make_float2(hp4.z, hp4.w) : make_float2(hp4.x, hp4.y);
-          const float2 hv = __ffma2_rn(zc[e], __fadd2_rn(hp, make_float2(-n.x, -n.y)), n);
-          hn[2 * e] = hv.x; hn[2 * e + 1] = hv.y;
+        for (int j = 0; j < UPS; ++j) hn[j] = (rc[j] + zc[j] + own(gi, j) + own(ghn[ks], j)) * 1e-30f + hp[j];
+#else
+        if constexpr (UPS >= 2) {
+#pragma unroll
+          for (int e = 0; e < UPS / 2; ++e) {
+            const float2 b_i = *reinterpret_cast<const float2*>(sb + 2 * C + u0 + 2 * e);
+            const float2 b_h = *reinterpret_cast<const float2*>(sb + 3 * C + u0 + 2 * e);
+            const float2 vhn = __fadd2_rn(make_float2(own(ghn[ks], 2 * e), own(ghn[ks], 2 * e + 1)), b_h);
+            const float2 vin = __fadd2_rn(make_float2(own(gi, 2 * e), own(gi, 2 * e + 1)), b_i);
+            const float2 c = __ffma2_rn(make_float2(rc[2 * e], rc[2 * e + 1]), vhn, vin);
+            const float2 pc = __fadd2_rn(make_float2(ex2_ftz(c.x), ex2_ftz(c.y)), one);
+            const float2 q = make_float2(rcp_ftz(pc.x), rcp_ftz(pc.y));
+            const float2 n = __ffma2_rn(make_float2(-2.0f, -2.0f), q, one);
+            const float2 hv = __ffma2_rn(make_float2(zc[2 * e], zc[2 * e + 1]), __fadd2_rn(make_float2(hp[2 * e], hp[2 * e + 1]), make_float2(-n.x, -n.y)), n);
+            hn[2 * e] = hv.x; hn[2 * e + 1] = hv.y;
+          }
+        } else {
+          const float c = fmaf(rc[0], own(ghn[ks], 0) + sb[3 * C + u0], own(gi, 0) + sb[2 * C + u0]);
+          const float n = fmaf(-2.0f, rcp_ftz(ex2_ftz(c) + 1.0f), 1.0f);
+          hn[0] = fmaf(zc[0], hp[0] - n, n);
         }
 #endif
         if (ks < 3) {                                        // pre-activations of the coming slices: in flight under the stores below
@@ -398,14 +455,34 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
             tmem_ld4_nowait(pa + 16 * (ks + 2), grz[ks & 1][0]);
             tmem_ld4_nowait(pa + 64 + 16 * (ks + 2), grz[ks & 1][1]);
           }
-          rc[0] = rn[0]; rc[1] = rn[1]; zc[0] = zn[0]; zc[1] = zn[1];
+#pragma unroll
+          for (int j = 0; j < UPS; ++j) { rc[j] = rn[j]; zc[j] = zn[j]; }
         }
+        // the cg group's four units of this slice as two packed FP16 columns (units 2c, 2c+1 -> column c), hi and lo:
+        // every thread writes the complete pair of columns of its own row, the partner rows' units arrive by shuffle
         uint32_t hi0, lo0, hi1, lo1;
-        split2_f16(hn[0], hn[1], hi0, lo0);
-        split2_f16(hn[2], hn[3], hi1, lo1);
-        tmem_st2(lane_base + TM_HHI + 8 * ks + 2 * cg, hi0, hi1);          // units 2c, 2c+1 -> column c of the A operand
+        if constexpr (D == 1) {
+          split2_f16(hn[0], hn[1], hi0, lo0);
+          split2_f16(hn[2], hn[3], hi1, lo1);
+          *reinterpret_cast<float4*>(srow_w + hchunk) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        } else if constexpr (D == 2) {
+          uint32_t hi, lo;
+          split2_f16(hn[0], hn[1], hi, lo);
+          const uint32_t ohi = __shfl_xor_sync(0xffffffffu, hi, 16), olo = __shfl_xor_sync(0xffffffffu, lo, 16);
+          hi0 = part ? ohi : hi; hi1 = part ? hi : ohi;
+          lo0 = part ? olo : lo; lo1 = part ? lo : olo;
+          *reinterpret_cast<float2*>(srow_w + hchunk) = make_float2(hn[0], hn[1]);
+        } else {
+          const float o = __shfl_xor_sync(0xffffffffu, hn[0], 8);                  // the other unit of this thread's column
+          uint32_t hi, lo;
+          split2_f16((part & 1) ? o : hn[0], (part & 1) ? hn[0] : o, hi, lo);
+          const uint32_t ohi = __shfl_xor_sync(0xffffffffu, hi, 16), olo = __shfl_xor_sync(0xffffffffu, lo, 16);
+          hi0 = (part & 2) ? ohi : hi; hi1 = (part & 2) ? hi : ohi;
+          lo0 = (part & 2) ? olo : lo; lo1 = (part & 2) ? lo : olo;
+          *reinterpret_cast<float*>(srow_w + hchunk) = hn[0];
+        }
+        tmem_st2(lane_base + TM_HHI + 8 * ks + 2 * cg, hi0, hi1);
         tmem_st2(lane_base + TM_HLO + 8 * ks + 2 * cg, lo0, lo1);
-        *reinterpret_cast<float4*>(srow + (((4 * ks + cg) ^ (row & 15)) << 4)) = make_float4(hn[0], hn[1], hn[2], hn[3]);
         if (ks == 1 && t > 0) write_out(t - 1);
         if (ks == 2 && t + 2 < T) store_x(t & 1, xv);        // x_mma(t) (reader of this buffer) completed with the commit
         if (ks == 3) {
@@ -431,10 +508,10 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   if (warp < 16) {                                           // write-out of the last step (all staging rows visible after the barrier)
     const int s_ = T - 1, f = dir ? 0 : T - 1;
     const unsigned char* sbuf = Ssm + (s_ & 1) * ST_BUF;
-    const int nvalid = min(128, p.B - b0);
+    const int nvalid = min(SPC, p.B - b0);
     float* gdst = hg + ((size_t)b0 * T + f) * 2 * C + dir * C + (tid & 15) * 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < UPS; ++i) {
       const int r = (tid >> 4) + 32 * i;
       if (r < nvalid)
         *reinterpret_cast<float4*>(gdst + (size_t)r * T * 2 * C) = *reinterpret_cast<const float4*>(sbuf + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
@@ -448,6 +525,19 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// Row duplication factor of the sweep for a step of B streams (Engine::intra_dup = 0: auto).  Measured on dpdfnet4
+// (profiles/r2u_sweep.log, r2u_intra_timeline.txt): one sweep launch 168 / 113 / 99 us for D = 1 / 2 / 4 at 1024 streams,
+// but the 225 KB CTAs of a D = 4 sweep then hold 128 SMs and squeeze the overlapped post kernel (hop 1.082 / 0.911 /
+// 0.920 ms), and a sweep that needs more than one wave loses outright (2048 streams: 1.330 / 1.258 / 1.451 ms).  So:
+// D = 4 while the sweep takes at most half of the SMs, D = 2 while it fits one wave, else D = 1.
+int intra_tc_dup(const Engine& e, int B) {
+  if (e.intra_dup == 1 || e.intra_dup == 2 || e.intra_dup == 4) return e.intra_dup;
+  const int Bt = std::max(B, e.total_B);                     // lanes run their sweeps side by side
+  if (4 * ((Bt + 31) / 32) <= e.num_sms / 2) return 4;
+  if (4 * ((Bt + 63) / 64) <= e.num_sms) return 2;
+  return 1;
+}
+
 void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   IntraTcParams p{};
   p.x[0] = e.sc.c1;
@@ -459,14 +549,19 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.wimg[0] = e.w.dprnn_df[blk].tc_intra;  p.bias[0] = e.w.dprnn_df[blk].tc_intra_bias;
   p.wimg[1] = e.w.dprnn_erb[blk].tc_intra; p.bias[1] = e.w.dprnn_erb[blk].tc_intra_bias;
   p.B = B;
-  p.tiles = (B + 127) / 128;
+  const int D = intra_tc_dup(e, B);
+  p.tiles = (B * D + 127) / 128;
   p.progress = e.overlap_now ? e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles : nullptr;
   p.err = e.err_dev;
-  launch_k(e, k_dprnn_intra_tc, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  if (D == 4) launch_k(e, k_dprnn_intra_tc<4>, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else if (D == 2) launch_k(e, k_dprnn_intra_tc<2>, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else launch_k(e, k_dprnn_intra_tc<1>, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
 }
 
 void init_dprnn_intra_tc_kernels() {
-  cudaFuncSetAttribute(k_dprnn_intra_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
 }
 
 }  // namespace dpdf

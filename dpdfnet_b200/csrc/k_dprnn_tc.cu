@@ -53,8 +53,9 @@ struct PostTcParams {
   int tiles0, B;
   // overlapped mode: tile = (position f, 128-stream tile), erb tiles first, positions middle-out (the
   // order in which both sweep directions complete them); the CTA waits for the two intra CTAs it depends on
-  const int* progress;    // [2 branches][2 dirs][stiles] completed steps, nullptr = row-major tiles of a finished sweep
+  const int* progress;    // [2 branches][2 dirs][ptiles] completed steps, nullptr = row-major tiles of a finished sweep
   int stiles;             // ceil(B / 128)
+  int dup, ptiles;        // the sweep's CTAs own 128 / dup streams each: ptiles = ceil(B * dup / 128) counters per (branch, direction)
   int pf_dist;            // row-major mode: warm L2 with the inputs of tile blockIdx.x + pf_dist (0 = off); CTAs are dispatched in
                           // index order, so with pf_dist = resident CTAs that tile starts about when this one ends
 #ifdef PT_TIMELINE
@@ -111,15 +112,22 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     rstride = T;
     valid = min(128, p.B - stile * 128);
     if (tid == 0) {
-      const volatile int* fw = p.progress + (bi * 2 + 0) * p.stiles + stile;   // branch index as in the intra kernel: 0 = df, 1 = erb
-      const volatile int* bw = p.progress + (bi * 2 + 1) * p.stiles + stile;
-      // the forward CTA has finished position f after f + 1 steps, the backward one after T - f; bounded wait (~2 s):
+      // the sweep CTAs this tile's 128 streams come from: dup per direction (branch index as in the intra kernel: 0 = df, 1 = erb)
+      const volatile int* fw = p.progress + (bi * 2 + 0) * p.ptiles + stile * p.dup;
+      const volatile int* bw = p.progress + (bi * 2 + 1) * p.ptiles + stile * p.dup;
+      const int nsrc = min(p.dup, p.ptiles - stile * p.dup);
+      // a forward CTA has finished position f after f + 1 steps, a backward one after T - f; bounded wait (~2 s):
       // a broken or preempted producer must show up as an error, not as a hung GPU - and never as stale data: on
       // time-out the tile is SKIPPED (nothing read, nothing written) and the engine's error word is raised, which
       // the host turns into DPDF_ERR_CUDA for this hop (api.cu:check_device_errors)
+      auto ready = [&]() {
+        bool ok = true;
+        for (int k = 0; k < nsrc; ++k) ok = ok && fw[k] >= fpos + 1 && bw[k] >= T - fpos;
+        return ok;
+      };
       long long spin = 0;
-      for (; (*fw < fpos + 1 || *bw < T - fpos) && spin < (1ll << 23); ++spin) __nanosleep(256);
-      if (*fw < fpos + 1 || *bw < T - fpos) {
+      for (; !ready() && spin < (1ll << 23); ++spin) __nanosleep(256);
+      if (!ready()) {
         s_abort = 1;
         p.io->err[DPDF_ERRW_OVERLAP] = 1;
         __threadfence_system();
@@ -471,6 +479,8 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   // synchronised with it through the per-CTA progress counters only.
   p.progress = e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles;
   p.stiles = (B + 127) / 128;
+  p.dup = intra_tc_dup(e, B);
+  p.ptiles = (B * p.dup + 127) / 128;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(p.stiles * (NDF / 2 + e.d.fe[3])));
   cfg.blockDim = dim3(TC_NT);

@@ -156,6 +156,38 @@ def test_intra_tc_multi_tile(torch_cuda, name, B):
     assert np.abs(ffma.run_pcm_host(pcm) - out).max() < 1e-5
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 200), ("dpdfnet4", 330)])
+def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
+    """tcgen05 intra-GRU kernel with 128 / D streams per CTA (D rows of the MMA tile per stream, the gate math split
+    over the D partner threads): D = 1, 2, 4 run the same arithmetic, so they must agree bit for bit, on ragged last
+    tiles and both with the post kernel overlapped with the sweep (per-CTA progress counters, D per 128-stream post
+    tile) and after it; the auto choice is one of them; all against the oracle."""
+    T = 4
+    hop = get_spec(name).hop
+    rng = np.random.default_rng(31)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    outs = {}
+    for D in (1, 2, 4, 0):
+        eng = _engine(name, 4, B)
+        eng.set_option("intra_tc", 1)
+        eng.set_option("overlap", overlap)
+        eng.set_option("lanes", 1)
+        eng.set_option("intra_dup", D)
+        outs[D] = (eng.run_pcm_host(pcm), eng.debug_tensor("xd", B), eng.state_export(B - 1))
+        eng.close()
+    for D in (2, 4, 0):
+        for a, b in zip(outs[D], outs[1]):
+            assert np.array_equal(a, b), D
+    ora = _oracle(name, 4, B)
+    ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    assert np.abs(outs[4][0] - ref).max() < WAVE_TOL
+    N = get_spec(name).n_blocks
+    assert np.abs(outs[4][1] - np.asarray(ora.dbg[f"xd{N - 1}"]).reshape(B, -1)).max() < 2e-4
+    with pytest.raises(ValueError):
+        _engine(name, 4, 2).set_option("intra_dup", 3)
+
+
 @pytest.mark.parametrize("intra_tc", [0, 1])
 def test_lanes_match_single_chain(torch_cuda, intra_tc):
     """A batched step split into lanes (row ranges running as forked kernel chains inside one CUDA graph) must give
