@@ -428,8 +428,16 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   e.overlap_now = e.overlap_now && intra_on_tc && !e.timing;        // requested by the caller (enqueue_lanes / run_hops_free)
   if (seg_pdl) e.pdl_now = false;
   for (int i = 0; i < d.N; ++i) {
-    if (intra_on_tc) { RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st)); }
-    else { RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); }
+    if (intra_on_tc) {
+      // Sweep of block i >= 1 as a programmatic dependent of the post kernel of block i - 1 (Engine::intra_pdl): its CTAs
+      // take the SMs the post kernel's tail leaves idle, set up barriers and tensor memory and pull their 96 KB of weight
+      // images, then wait (griddepcontrol.wait) for the post grid to complete and flush.  They cannot crowd the post
+      // kernel: dependents launch only once every post CTA has started.
+      const bool chain = e.intra_pdl && i > 0 && e.post_tc && !e.timing && !e.pdl_now;
+      if (chain) { e.pdl_now = true; e.pdl_first = false; }
+      RUN("dprnn_intra", launch_dprnn_intra_tc(e, i, B, st));
+      if (chain) e.pdl_now = false;
+    } else { RUN("dprnn_intra", launch_dprnn_intra(e, i, B, st)); }
     ++n;
     if (e.post_tc) { RUN("dprnn_post", launch_dprnn_post_tc(e, i, B, st)); }
     else { RUN("dprnn_post", launch_dprnn_post(e, i, B, st)); }
@@ -1161,6 +1169,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     } else {
       e.intra_tc_min = value;
     }
+    drop_graphs(e);
+  } else if (strcmp(key, "intra_pdl") == 0) {
+    e.intra_pdl = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "intra_dup") == 0) {
     if (value != 0 && value != 1 && value != 2 && value != 4) return fail(DPDF_ERR_INVALID, "intra_dup must be 0 (auto), 1, 2 or 4");
