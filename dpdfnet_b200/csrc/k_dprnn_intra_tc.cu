@@ -96,9 +96,9 @@ struct IntraTcParams {
   int Fp[2];
   const float* wimg[2];   // [2 dirs][W_ih hi | W_ih lo | W_hh hi | W_hh lo] FP16 operand images
   const float* bias[2];   // [2][4][64], exponent scales folded in (weights.py: tc.intra_bias)
-  int tiles;              // ceil(B / (128 / D)): stream tiles of the sweep
+  int tiles[2];           // stream tiles of the sweep per branch: ceil(B / (128 / D)) with the branch's row duplication D
   int B;
-  int* progress;          // [2 branches][2 dirs][tiles] completed steps of each CTA, or nullptr (overlapped post kernel)
+  int* progress;          // [df: 2 dirs x tiles[0] | erb: 2 dirs x tiles[1]] completed steps of each CTA, or nullptr (overlapped post kernel)
   int* err;               // engine error words (IoDesc::err), may be nullptr
 #ifdef ITC_TIMELINE
   long long* tl;          // [steps][12] SM-clock stamps of CTA 0 (tools/ubench/intra_tc_timeline.cu)
@@ -115,12 +115,9 @@ struct IntraTcParams {
 #define TL(slot) do { } while (0)
 #endif
 
+// The sweep of one CTA: branch br, direction dir, stream tile `tile` of 128 / D streams.
 template <int D>
-#ifdef ITC_MAXNREG
-__global__ void __maxnreg__(ITC_MAXNREG) k_dprnn_intra_tc(IntraTcParams p) {
-#else
-__global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
-#endif
+__device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br, const int dir, const int tile) {
   static_assert(D == 1 || D == 2 || D == 4, "row duplication factor");
   constexpr int SPC = 128 / D;        // streams per CTA
   constexpr int LPQ = 32 / D;         // lanes of a warp (TMEM lane quadrant) that hold distinct streams
@@ -138,10 +135,6 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   const int qd = warp & 3, cg = warp >> 2;
   const int part = lane / LPQ;                               // which of the D rows of its stream this thread is
   const int srow = qd * LPQ + (lane % LPQ);                  // the stream's row in the CTA's staging tiles
-  const int item = blockIdx.x;
-  const int br = item / (2 * p.tiles);
-  const int dir = (item % (2 * p.tiles)) / p.tiles;
-  const int tile = item % p.tiles;
   const int T = br ? p.Fp[1] : p.Fp[0];
   const int b0 = tile * SPC;
   const float* __restrict__ xg = br ? p.x[1] : p.x[0];
@@ -159,7 +152,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
 #ifdef ITC_NO_PROGRESS
   auto progress_ptr = [&]() -> int* { return nullptr; };
 #else
-  auto progress_ptr = [&]() -> int* { return p.progress ? p.progress + (br * 2 + dir) * p.tiles + tile : nullptr; };
+  auto progress_ptr = [&]() -> int* { return p.progress ? p.progress + (br ? 2 * p.tiles[0] + dir * p.tiles[1] : dir * p.tiles[0]) + tile : nullptr; };
 #endif
   __syncthreads();                                           // barriers initialised
   if (tid == 0) {
@@ -525,16 +518,33 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(IntraTcParams p) {
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// Row duplication factor of the sweep for a step of B streams (Engine::intra_dup = 0: auto).  Measured on dpdfnet4
-// (profiles/r2u_sweep.log, r2u_intra_timeline.txt): one sweep launch 168 / 113 / 99 us for D = 1 / 2 / 4 at 1024 streams,
-// but the 225 KB CTAs of a D = 4 sweep then hold 128 SMs and squeeze the overlapped post kernel (hop 1.082 / 0.911 /
-// 0.920 ms), and a sweep that needs more than one wave loses outright (2048 streams: 1.330 / 1.258 / 1.451 ms).  So:
-// D = 4 while the sweep takes at most half of the SMs, D = 2 while it fits one wave, else D = 1.
+// Grid = df CTAs (2 directions x tiles[0]) followed by erb CTAs.  The erb sweep has F'e = 8 positions against the df
+// sweep's 48, so it is never the critical path: it keeps full 128-stream tiles (DERB = 1) while the df branch is
+// split DDF ways, which leaves more SMs to the overlapped post kernel than duplicating both branches.
+template <int DDF, int DERB>
+#ifdef ITC_MAXNREG
+__global__ void __maxnreg__(ITC_MAXNREG) k_dprnn_intra_tc(const __grid_constant__ IntraTcParams p) {
+#else
+__global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(const __grid_constant__ IntraTcParams p) {
+#endif
+  const int item = blockIdx.x, ndf = 2 * p.tiles[0];
+  // two inlined copies of the sweep even for DDF == DERB: the branch index is then a compile-time constant in each
+  // (one generic copy costs the gate warps live registers: 56 instead of 16 bytes of spills)
+  if (item < ndf) intra_sweep<DDF>(p, 0, item / p.tiles[0], item % p.tiles[0]);
+  else intra_sweep<DERB>(p, 1, (item - ndf) / p.tiles[1], (item - ndf) % p.tiles[1]);
+}
+
+// Row duplication factor of the df-branch sweep for a step of B streams (Engine::intra_dup = 0: auto); the erb branch
+// always runs D = 1.  Measured on dpdfnet4 (profiles/r2u_sweep_intra_dup.log, r2u_intra_timeline.txt): one sweep launch
+// 168 / 113 / 99 us for D = 1 / 2 / 4 at 1024 streams; a sweep that needs more than one wave of its 225 KB CTAs loses
+// outright, and one that holds most SMs squeezes the overlapped post kernel.  So: D = 4 while the sweep's CTAs take at
+// most two thirds of the SMs, D = 2 while they fit one wave, else D = 1.
 int intra_tc_dup(const Engine& e, int B) {
   if (e.intra_dup == 1 || e.intra_dup == 2 || e.intra_dup == 4) return e.intra_dup;
   const int Bt = std::max(B, e.total_B);                     // lanes run their sweeps side by side
-  if (4 * ((Bt + 31) / 32) <= e.num_sms / 2) return 4;
-  if (4 * ((Bt + 63) / 64) <= e.num_sms) return 2;
+  auto ctas = [&](int D) { return 2 * ((Bt * D + 127) / 128) + 2 * ((Bt + 127) / 128); };
+  if (ctas(4) <= e.num_sms * 2 / 3) return 4;
+  if (ctas(2) <= e.num_sms) return 2;
   return 1;
 }
 
@@ -550,18 +560,20 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.wimg[1] = e.w.dprnn_erb[blk].tc_intra; p.bias[1] = e.w.dprnn_erb[blk].tc_intra_bias;
   p.B = B;
   const int D = intra_tc_dup(e, B);
-  p.tiles = (B * D + 127) / 128;
+  p.tiles[0] = (B * D + 127) / 128;
+  p.tiles[1] = (B + 127) / 128;
   p.progress = e.overlap_now ? e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles : nullptr;
   p.err = e.err_dev;
-  if (D == 4) launch_k(e, k_dprnn_intra_tc<4>, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
-  else if (D == 2) launch_k(e, k_dprnn_intra_tc<2>, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
-  else launch_k(e, k_dprnn_intra_tc<1>, dim3(4 * p.tiles), dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  const dim3 grid(2 * (p.tiles[0] + p.tiles[1]));
+  if (D == 4) launch_k(e, k_dprnn_intra_tc<4, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else if (D == 2) launch_k(e, k_dprnn_intra_tc<2, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else launch_k(e, k_dprnn_intra_tc<1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
 }
 
 void init_dprnn_intra_tc_kernels() {
-  cudaFuncSetAttribute(k_dprnn_intra_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
-  cudaFuncSetAttribute(k_dprnn_intra_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
-  cudaFuncSetAttribute(k_dprnn_intra_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
 }
 
 }  // namespace dpdf

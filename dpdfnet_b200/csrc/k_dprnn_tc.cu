@@ -53,9 +53,9 @@ struct PostTcParams {
   int tiles0, B;
   // overlapped mode: tile = (position f, 128-stream tile), erb tiles first, positions middle-out (the
   // order in which both sweep directions complete them); the CTA waits for the two intra CTAs it depends on
-  const int* progress;    // [2 branches][2 dirs][ptiles] completed steps, nullptr = row-major tiles of a finished sweep
+  const int* progress;    // sweep counters [df: 2 dirs x ptiles | erb: 2 dirs x stiles], nullptr = row-major tiles of a finished sweep
   int stiles;             // ceil(B / 128)
-  int dup, ptiles;        // the sweep's CTAs own 128 / dup streams each: ptiles = ceil(B * dup / 128) counters per (branch, direction)
+  int dup, ptiles;        // the df sweep's CTAs own 128 / dup streams each: ptiles = ceil(B * dup / 128) counters per direction (erb: dup = 1)
   int pf_dist;            // row-major mode: warm L2 with the inputs of tile blockIdx.x + pf_dist (0 = off); CTAs are dispatched in
                           // index order, so with pf_dist = resident CTAs that tile starts about when this one ends
 #ifdef PT_TIMELINE
@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     valid = min(128, p.B - stile * 128);
     if (tid == 0) {
       // the sweep CTAs this tile's 128 streams come from: dup per direction (branch index as in the intra kernel: 0 = df, 1 = erb)
-      const volatile int* fw = p.progress + (bi * 2 + 0) * p.ptiles + stile * p.dup;
-      const volatile int* bw = p.progress + (bi * 2 + 1) * p.ptiles + stile * p.dup;
-      const int nsrc = min(p.dup, p.ptiles - stile * p.dup);
+      const int dup = bi ? 1 : p.dup, pt = bi ? p.stiles : p.ptiles;
+      const volatile int* fw = p.progress + (bi ? 2 * p.ptiles : 0) + stile * dup;
+      const volatile int* bw = fw + pt;
+      const int nsrc = min(dup, pt - stile * dup);
       // a forward CTA has finished position f after f + 1 steps, a backward one after T - f; bounded wait (~2 s):
       // a broken or preempted producer must show up as an error, not as a hung GPU - and never as stale data: on
       // time-out the tile is SKIPPED (nothing read, nothing written) and the engine's error word is raised, which
@@ -297,19 +298,21 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
 
   unsigned char* y_hi = RA;                                // images 0, 1: y = block input of the inter-frame half
   unsigned char* h_hi = RA + 2 * IMG;                      // images 2, 3: h_prev, then h_new
-  // row statistics over 64 columns held by the four column-group warps of a lane quadrant
+  // row statistics over 64 columns held by the four column-group warps of a lane quadrant: only those four warps
+  // exchange partials (rows of different quadrants are disjoint), so they meet on a named barrier of their own
+  auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory"); };
   auto layernorm16 = [&](float (&v)[16], const float* g, const float* b) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) s += v[i];
     red[cg * 128 + row] = s;
-    __syncthreads();
+    quad_sync();
     const float mean = (red[row] + red[128 + row] + red[256 + row] + red[384 + row]) * (1.0f / 64.0f);
     float qq = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) { v[i] -= mean; qq += v[i] * v[i]; }
     red[512 + cg * 128 + row] = qq;
-    __syncthreads();
+    quad_sync();
     const float rstd = rsqrtf((red[512 + row] + red[640 + row] + red[768 + row] + red[896 + row]) * (1.0f / 64.0f) + 1e-5f);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * g[cg * 16 + i] + b[cg * 16 + i];
