@@ -200,6 +200,11 @@ struct Engine {
   int ana_force = 0, syn_force = 0;   // experiments: force that many streams per CTA regardless of the grid size (0 = auto)
   int ana_nb = 32, syn_sb = 16;   // caps on the streams per CTA of the analysis / synthesis kernels (8|16|32, 4|8|16)
   int post_pf = 1;                // k_dprnn_post_tc: L2 prefetch distance in units of the SM count (2 CTAs per SM -> 2), 0 = off
+  int post_pair = 0;              // k_dprnn_post_tc as CTA pairs (cta_group::2, M = 256): 0 never, 1 always, 2 = when not overlapped with its sweep.
+                                  // Bit-identical and parity-tested, but measured SLOWER (profiles/r2A_*: post 2.54 -> 2.79 ms per hop at 16 384
+                                  // streams): the 4-deep ring does cut phase 2 (15.0 k -> 8.2 k cycles per tile) but the pair runs in lock step -
+                                  // every phase waits for the slower CTA's staging plus a remote mbarrier arrive (phase 1: 2.0 k -> 8.2 k), and
+                                  // every slab needs a relay hop from the peer (a 1-D bulk copy cannot signal the leader's barrier)
   int post_tc = 1;                // DPRNN position-parallel half on tcgen05 (3xTF32) instead of FFMA2
   std::map<int, cudaGraphExec_t> graphs;     // keyed by B: one hop of all lanes (forked chains, joined)
   std::map<int, cudaGraphExec_t> lane_graphs; // keyed by B * MAX_LANES + lane: one hop of one lane (free-running lanes of a multi-hop run)

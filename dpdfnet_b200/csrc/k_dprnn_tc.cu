@@ -11,8 +11,18 @@
 // Operand layout: K-major, SWIZZLE_NONE ("interleave"): 8 rows x 16 B core matrices (128 B contiguous), core
 // matrices adjacent in K are LBO = 128 B apart, 8-row groups are SBO = (K/8)*128 B = 1 KB apart.
 // One CTA = 512 threads, thread (row = TMEM lane, 16-column group): LayerNorm and the GRU gate math are register
-// code straight out of tcgen05.ld.  103 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, so the
+// code straight out of tcgen05.ld.  104 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, so the
 // load -> MMA -> epilogue chain of one tile overlaps with the other's.
+//
+// PAIR = true (template parameter): the kernel is launched as clusters of two CTAs on the two SMs of a TPC and every
+// matrix product is ONE tcgen05.mma.cta_group::2 of M = 256 over the pair's two tiles.  The B operand of such an MMA is
+// split across the pair - each CTA holds 32 of a slab's 64 rows - so a weight slab costs 8 KB per CTA instead of 16:
+// the same 32 KB ring is FOUR slabs deep instead of two and every slab is pulled from L2 once per 256 rows.  What bounded
+// the single-CTA form was exactly that ring (profiles/r2z_post_timeline.txt: 11-17 k of a tile's 37-44 k cycles are
+// phase 2, 72 MMAs that need 3 k, because each pair of slabs is requested only when its buffer drains and a bulk copy
+// from L2 takes 1-2 us).  Only the leader (cluster rank 0) issues MMAs; the peer tells it with remote mbarrier arrives
+// when its half of a slab has landed and when its activation images of a phase are staged; commits are multicast to
+// the barriers of both CTAs.
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -53,6 +63,8 @@ struct PostTcParams {
   int tiles0, B;
   // overlapped mode: tile = (position f, 128-stream tile), erb tiles first, positions middle-out (the
   // order in which both sweep directions complete them); the CTA waits for the two intra CTAs it depends on
+  int tiles1;             // tile counts per branch as launched (PAIR: rounded up to even so that a CTA pair never straddles
+                          // the branches, which have different weights; the padding tile has no valid rows)
   const int* progress;    // sweep counters [df: 2 dirs x ptiles | erb: 2 dirs x stiles], nullptr = row-major tiles of a finished sweep
   int stiles;             // ceil(B / 128)
   int dup, ptiles;        // the df sweep's CTAs own 128 / dup streams each: ptiles = ceil(B * dup / 128) counters per direction (erb: dup = 1)
@@ -74,15 +86,22 @@ constexpr int PT_OFF_SP = PT_OFF_W + 2 * WSLAB;         // 640 floats of small p
 constexpr int PT_OFF_RED = PT_OFF_SP + 640 * 4;         // [2][4][128] LayerNorm partials
 constexpr int PT_OFF_HOFF = PT_OFF_RED + 1024 * 4;      // 128 x int64 state offsets
 constexpr int PT_OFF_COMMIT = PT_OFF_HOFF + 128 * 8;    // 128 x int
-constexpr int PT_OFF_BAR = PT_OFF_COMMIT + 128 * 4;     // 5 mbarriers + TMEM base slot
-constexpr size_t POST_TC_SMEM = PT_OFF_BAR + 64;
+constexpr int PT_OFF_BAR = PT_OFF_COMMIT + 128 * 4;     // 14 mbarriers + TMEM base slot
+constexpr size_t POST_TC_SMEM = PT_OFF_BAR + 128;
+// mbarriers: slab landed [0,4), slab consumed [4,8), peer's half of the slab landed [8,12) (leader of a pair only),
+// phase result ready [12], peer's activation images staged [13] (leader of a pair only)
+constexpr int BAR_FULL = 0, BAR_CONS = 4, BAR_PFULL = 8, BAR_PHASE = 12, BAR_ACT = 13, NBARS = 14;
 
-// One CTA = one 128-row tile.  Thread 0 is the single MMA issuer and streams the nine 16 KB weight slabs of the
-// block (fc_intra K-halves, six GRU gate slabs, fc_inter) through a two-buffer ring with 1-D bulk copies that
-// complete on mbarriers, two slabs ahead of the tensor core; the other 511 threads never wait for weights.
+// One CTA = one 128-row tile.  Thread 0 is the single MMA issuer (PAIR: thread 0 of the leader CTA, for both tiles) and
+// streams the nine weight slabs of the block (fc_intra K-halves, six GRU gate slabs, fc_inter) through a ring of NBUF
+// buffers with 1-D bulk copies that complete on mbarriers, NBUF slabs ahead of the tensor core; the other 511 threads
+// never wait for weights.
 // TMEM columns: [0,64) fc_intra, then the gate pre-activations r [0,64) z [64,128) in [128,192) hn [192,256),
 // then fc_inter in [0,64) again (each phase is drained by all threads before the next one is issued).
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
+  constexpr int NBUF = PAIR ? 4 : 2;                 // ring depth in slabs
+  constexpr int SLAB_B = PAIR ? WSLAB / 2 : WSLAB;   // bytes of a slab in this CTA's ring: hi | lo images of its 32 (PAIR) or all 64 rows
   pdl_trigger();
   if (!p.progress) pdl_wait();      // overlapped mode synchronises with the sweep through its progress counters instead
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -92,8 +111,9 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   float* red = reinterpret_cast<float*>(smem_raw + PT_OFF_RED);
   long long* s_hoff = reinterpret_cast<long long*>(smem_raw + PT_OFF_HOFF);
   int* s_commit = reinterpret_cast<int*>(smem_raw + PT_OFF_COMMIT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + PT_OFF_BAR);   // [0,1] slab full, [2,3] slab consumed, [4] phase result ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + PT_OFF_BAR);   // BAR_* above
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;                    // 0 = leader (issues the pair's MMAs)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
@@ -103,15 +123,15 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   __shared__ int s_abort;
   if (tid == 0) s_abort = 0;
   if (p.progress) {
-    const int tiles_e = p.br[1].Fp * p.stiles;
+    const int tiles_e = p.tiles1;                          // erb tiles first (PAIR: padded to even)
     bi = (int)blockIdx.x < tiles_e ? 1 : 0;
     const int local = (int)blockIdx.x - (bi ? 0 : tiles_e);
     const int k = local / p.stiles, stile = local % p.stiles, T = p.br[bi].Fp;
     fpos = (T - 1) / 2 + ((k & 1) ? (k + 1) / 2 : -(k / 2));
     rbase = (long long)stile * 128 * T + fpos;
     rstride = T;
-    valid = min(128, p.B - stile * 128);
-    if (tid == 0) {
+    valid = k < T ? min(128, p.B - stile * 128) : 0;       // k == T: the padding tile of an odd tile count
+    if (tid == 0 && valid > 0) {
       // the sweep CTAs this tile's 128 streams come from: dup per direction (branch index as in the intra kernel: 0 = df, 1 = erb)
       const int dup = bi ? 1 : p.dup, pt = bi ? p.stiles : p.ptiles;
       const volatile int* fw = p.progress + (bi ? 2 * p.ptiles : 0) + stile * dup;
@@ -139,7 +159,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     bi = (int)blockIdx.x >= p.tiles0 ? 1 : 0;
     rbase = (long long)(blockIdx.x - (bi ? p.tiles0 : 0)) * 128;
     rstride = 1;
-    valid = (int)min((long long)128, (long long)p.B * p.br[bi].Fp - rbase);
+    valid = (int)max(0ll, min((long long)128, (long long)p.B * p.br[bi].Fp - rbase));   // 0: padding tile (PAIR)
   }
   const PostTcBranch& q = p.br[bi];
 
@@ -149,13 +169,13 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   // round trip: ncu showed 38 % long-scoreboard stalls, hcat staging 9 k and the first epilogue 12 k of 44 k cycles.
   if (p.pf_dist > 0 && !p.progress) {
     const long long nt = (long long)blockIdx.x + p.pf_dist;
-    const int tiles1 = (int)(((long long)p.B * p.br[1].Fp + 127) / 128);
-    if (nt < (long long)p.tiles0 + tiles1) {
+    if (nt < (long long)p.tiles0 + p.tiles1) {
       const int nb = nt >= p.tiles0 ? 1 : 0;
       const PostTcBranch& nq = p.br[nb];
       const long long nbase = (nt - (nb ? p.tiles0 : 0)) * 128;
-      const int nvalid = (int)min((long long)128, (long long)p.B * nq.Fp - nbase);
-      if (tid == 0) {
+      const int nvalid = (int)max(0ll, min((long long)128, (long long)p.B * nq.Fp - nbase));
+      if (nvalid == 0) {
+      } else if (tid == 0) {
         bulk_prefetch_l2(nq.hcat + nbase * 2 * C, (uint32_t)nvalid * 2 * C * 4);
         bulk_prefetch_l2(nq.xin + nbase * C, (uint32_t)nvalid * C * 4);
       } else if (tid >= 128 && tid < 128 + nvalid) {
@@ -188,15 +208,23 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   if (tid < 256) sp[192 + tid] = q.bias[tid];
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+    for (int i = 0; i < NBARS; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
-  __syncthreads();                                       // barriers initialised, s_hoff visible
-  if (s_abort) {                                         // the sweep never delivered this tile's rows: skip it (see above)
-    tc_fence_after();
-    if (warp == 0) tmem_dealloc<256>(*tmem_slot);
-    return;
+  if constexpr (PAIR) {
+    cluster_sync_all();                                  // both CTAs' barriers exist before either signals across; s_hoff visible
+    if (warp == 0) tmem_alloc_2cta<256>(tmem_slot);
+    __syncthreads();
+    if (s_abort) valid = 0;                              // the sweep never delivered this tile's rows: the pair protocol still runs,
+                                                         // but nothing is read or written for this tile (see above)
+  } else {
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    __syncthreads();                                     // barriers initialised, s_hoff visible
+    if (s_abort) {                                       // the sweep never delivered this tile's rows: skip it (see above)
+      tc_fence_after();
+      if (warp == 0) tmem_dealloc<256>(*tmem_slot);
+      return;
+    }
   }
 
   // ---- weight slab ring (thread 0 only) --------------------------------------------------------------------
@@ -207,12 +235,20 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     return reinterpret_cast<const unsigned char*>(q.tc_gates) + (size_t)((pidx & 1) ? 3 + (pidx >> 1) : (pidx >> 1)) * WSLAB;
   };
   auto load_slab = [&](int i) {
-    const int buf = i & 1;
-    if (i >= 2) mbar_wait(bars + 2 + buf, ((i - 2) >> 1) & 1);      // MMAs of the previous tenant have completed
-    mbar_expect_tx(bars + buf, WSLAB);
-    bulk_g2s(RW + buf * WSLAB, slab_src(i), WSLAB, bars + buf);
+    const int buf = i % NBUF;
+    if (i >= NBUF) mbar_wait(bars + BAR_CONS + buf, (i / NBUF - 1) & 1);      // MMAs of the previous tenant have completed
+    mbar_expect_tx(bars + BAR_FULL + buf, SLAB_B);
+    if constexpr (PAIR) {                                  // rows [32 rank, 32 rank + 32) of the hi and of the lo image: 4 KB each
+      bulk_g2s(RW + buf * SLAB_B, slab_src(i) + rank * (WSLAB / 4), WSLAB / 4, bars + BAR_FULL + buf);
+      bulk_g2s(RW + buf * SLAB_B + WSLAB / 4, slab_src(i) + WSLAB / 2 + rank * (WSLAB / 4), WSLAB / 4, bars + BAR_FULL + buf);
+    } else {
+      bulk_g2s(RW + buf * SLAB_B, slab_src(i), WSLAB, bars + BAR_FULL + buf);
+    }
   };
-  if (tid == 0) { load_slab(0); load_slab(1); }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) load_slab(i);
+  }
   PTL(0);
 
   // ---- stage the hcat tile as two K=64 operand image pairs (split on the fly) --------------------------------
@@ -254,33 +290,59 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   const uint32_t tmem = *tmem_slot;
   PTL(1);
   const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16) + cg * 16;
-  constexpr uint32_t IDESC = idesc_f16(128, 64);
+  constexpr uint32_t IDESC = idesc_f16(PAIR ? 256 : 128, 64);
   const uint32_t a_base = smem_u32(RA), w_base = smem_u32(RW);
 
-  // slab i: D[col .. col+64) (+)= A[128][64] * W_i[64][64]^T, three FP16 passes per 16-wide k-step
+  // slab i: D[col .. col+64) (+)= A[128 or 256][64] * W_i[64][64]^T, three FP16 passes per 16-wide k-step
   auto run_slab = [&](int i, int a_img, uint32_t col, uint32_t accumulate) {
-    const int buf = i & 1;
-    mbar_wait(bars + buf, (i >> 1) & 1);                   // slab landed (async proxy write -> async proxy read)
+    const int buf = i % NBUF;
+    mbar_wait(bars + BAR_FULL + buf, (i / NBUF) & 1);      // slab landed (async proxy write -> async proxy read)
+    if constexpr (PAIR) {
+      if (rank != 0) {                                     // peer: relay "my half has landed" to the leader, which issues for both
+        mbar_arrive_remote(bars + BAR_PFULL + buf, 0);
+        return;
+      }
+      mbar_wait_cluster(bars + BAR_PFULL + buf, (i / NBUF) & 1);
+    }
     constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
-    const uint32_t ah = a_base + a_img * IMG, bh = w_base + buf * WSLAB;
-    const uint64_t dah = DESC0 | (ah >> 4), dal = dah + (IMG >> 4), dbh = DESC0 | (bh >> 4), dbl = dbh + (WSLAB / 2 >> 4);
+    const uint32_t ah = a_base + a_img * IMG, bh = w_base + buf * SLAB_B;
+    const uint64_t dah = DESC0 | (ah >> 4), dal = dah + (IMG >> 4), dbh = DESC0 | (bh >> 4), dbl = dbh + (SLAB_B / 2 >> 4);
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {                       // 16 halves of K per step = two core matrices = 256 B
-      umma_f16(tmem + col, dah + ks * 16, dbh + ks * 16, IDESC, accumulate);
-      umma_f16(tmem + col, dal + ks * 16, dbh + ks * 16, IDESC, 1);
-      umma_f16(tmem + col, dah + ks * 16, dbl + ks * 16, IDESC, 1);
+      if constexpr (PAIR) {
+        umma_f16_2cta(tmem + col, dah + ks * 16, dbh + ks * 16, IDESC, accumulate);
+        umma_f16_2cta(tmem + col, dal + ks * 16, dbh + ks * 16, IDESC, 1);
+        umma_f16_2cta(tmem + col, dah + ks * 16, dbl + ks * 16, IDESC, 1);
+      } else {
+        umma_f16(tmem + col, dah + ks * 16, dbh + ks * 16, IDESC, accumulate);
+        umma_f16(tmem + col, dal + ks * 16, dbh + ks * 16, IDESC, 1);
+        umma_f16(tmem + col, dah + ks * 16, dbl + ks * 16, IDESC, 1);
+      }
       accumulate = 1;
     }
-    umma_commit(bars + 2 + buf);
+    if constexpr (PAIR) umma_commit_2cta(bars + BAR_CONS + buf);
+    else umma_commit(bars + BAR_CONS + buf);
+  };
+  // All operands of a phase are staged in this CTA (the __syncthreads before); PAIR: the leader also needs the peer's
+  auto phase_begin = [&](unsigned use) {                   // thread 0 only; use = 0, 1, 2
+    if constexpr (PAIR) {
+      if (rank != 0) mbar_arrive_remote(bars + BAR_ACT, 0);
+      else { mbar_wait_cluster(bars + BAR_ACT, use & 1); tc_fence_after(); }
+    }
+  };
+  auto phase_commit = [&]() {                              // thread 0 only: phase result ready, in both CTAs of a pair
+    if constexpr (PAIR) { if (rank == 0) umma_commit_2cta(bars + BAR_PHASE); }
+    else umma_commit(bars + BAR_PHASE);
   };
 
   // ---- phase 1: acc[0,64) = hcat * fc_intra^T ---------------------------------------------------------------
   if (tid == 0) {
+    phase_begin(0);
     run_slab(0, 0, 0, 0);
     run_slab(1, 2, 0, 1);
-    umma_commit(bars + 4);
-    load_slab(2);
-    load_slab(3);
+    phase_commit();
+    load_slab(NBUF);
+    load_slab(NBUF + 1);
   }
   float4 hv[4];                                            // h_prev tile: its latency hides behind the phase-1 MMAs
 #pragma unroll
@@ -291,7 +353,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   }
   // one warp polls the mbarrier, the other fifteen park on the hardware barrier: 512 spinning threads cost a quarter of
   // the kernel's issued instructions (ncu, r2c: SYNCS + BRA + YIELD = 25 %) and stole issue slots from the co-resident CTA
-  if (warp == 0) mbar_wait(bars + 4, 0);
+  if (warp == 0) mbar_wait(bars + BAR_PHASE, 0);
   __syncthreads();
   tc_fence_after();
   PTL(2);
@@ -300,7 +362,12 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   unsigned char* h_hi = RA + 2 * IMG;                      // images 2, 3: h_prev, then h_new
   // row statistics over 64 columns held by the four column-group warps of a lane quadrant: only those four warps
   // exchange partials (rows of different quadrants are disjoint), so they meet on a named barrier of their own
-  auto quad_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + qd) : "memory"); };
+  auto quad_sync = [&]() {                                 // immediate barrier ids: a register id makes ptxas reserve all sixteen
+    if (qd == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else if (qd == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+    else if (qd == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
+    else asm volatile("bar.sync 4, 128;" ::: "memory");
+  };
   auto layernorm16 = [&](float (&v)[16], const float* g, const float* b) {
     float s = 0.f;
 #pragma unroll
@@ -354,20 +421,20 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   PTL(3);
   // ---- phase 2: GRU gate pre-activations in TMEM: r [0,64) z [64,128) in [128,192) hn [192,256) ---------------
   if (tid == 0) {
+    phase_begin(1);
     run_slab(2, 0, 0, 0);     // Wih_r * y
     run_slab(3, 2, 0, 1);     // Whh_r * h
-    load_slab(4);
-    load_slab(5);
+    if constexpr (!PAIR) { load_slab(4); load_slab(5); }   // PAIR: slabs 4, 5 were requested at the end of phase 1
     run_slab(4, 0, 64, 0);    // Wih_z * y
     run_slab(5, 2, 64, 1);    // Whh_z * h
     load_slab(6);
     load_slab(7);
     run_slab(6, 0, 128, 0);   // Wih_n * y
     run_slab(7, 2, 192, 0);   // Whh_n * h
-    umma_commit(bars + 4);
+    phase_commit();
     load_slab(8);
   }
-  if (warp == 0) mbar_wait(bars + 4, 1);
+  if (warp == 0) mbar_wait(bars + BAR_PHASE, 1);
   __syncthreads();
   tc_fence_after();
   PTL(4);
@@ -404,8 +471,9 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   PTL(5);
   // ---- phase 3: acc[0,64) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena --------------
   if (tid == 0) {
+    phase_begin(2);
     run_slab(8, 2, 0, 0);
-    umma_commit(bars + 4);
+    phase_commit();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -427,7 +495,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) yv[c * 8 + e] = t8[e];
   }
-  if (warp == 0) mbar_wait(bars + 4, 0);
+  if (warp == 0) mbar_wait(bars + BAR_PHASE, 0);
   __syncthreads();
   tc_fence_after();
   PTL(6);
@@ -453,7 +521,13 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   }
   PTL(7);
   if (ovf) p.io->err[DPDF_ERRW_RANGE] = 1;
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if constexpr (PAIR) {
+    tc_fence_before();
+    cluster_sync_all();                                    // both CTAs have drained their accumulators; no signal is in flight
+    if (warp == 0) tmem_dealloc_2cta<256>(tmem);
+  } else {
+    if (warp == 0) tmem_dealloc<256>(tmem);
+  }
 }
 
 void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
@@ -470,11 +544,37 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   };
   fill(p.br[0], e.w.dprnn_df[blk], e.sc.hcat_d, e.sc.c1, e.sc.c1, e.st.inter_df, NDF / 2);
   fill(p.br[1], e.w.dprnn_erb[blk], e.sc.hcat_e, blk == 0 ? e.sc.e3 : e.sc.xe, e.sc.xe, e.st.inter_erb, e.d.fe[3]);
-  p.tiles0 = (int)(((long long)B * (NDF / 2) + 127) / 128);
-  const int tiles1 = (int)(((long long)B * e.d.fe[3] + 127) / 128);
+  // CTA pairs (cta_group::2, Engine::post_pair): 1 = always, 2 = only when the kernel runs after its sweep (a pair needs
+  // both SMs of a TPC, which the CTAs of a concurrent sweep fragment)
+  const bool pair = e.post_pair == 1 || (e.post_pair == 2 && !e.overlap_now);
+  auto even = [&](int t) { return pair ? (t + 1) & ~1 : t; };
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(TC_NT);
+  cfg.dynamicSmemBytes = POST_TC_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (pair) {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+    attr[cfg.numAttrs].val.clusterDim.x = 2;
+    attr[cfg.numAttrs].val.clusterDim.y = 1;
+    attr[cfg.numAttrs].val.clusterDim.z = 1;
+    ++cfg.numAttrs;
+  }
+  auto pdl_attr = [&]() {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    ++cfg.numAttrs;
+  };
   if (!e.overlap_now) {
+    p.tiles0 = even((int)(((long long)B * (NDF / 2) + 127) / 128));
+    p.tiles1 = even((int)(((long long)B * e.d.fe[3] + 127) / 128));
     p.pf_dist = e.post_pf * e.num_sms;
-    launch_k(e, k_dprnn_post_tc, dim3(p.tiles0 + tiles1), dim3(TC_NT), POST_TC_SMEM, st, p);
+    cfg.gridDim = dim3((unsigned)(p.tiles0 + p.tiles1));
+    if (e.pdl_now && !e.pdl_first) pdl_attr();
+    if (pair) cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<true>, p);
+    else cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<false>, p);
     return;
   }
   // Overlapped with the sweep that feeds it: launched as a programmatic dependent of the intra kernel (it may start as
@@ -484,21 +584,17 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.stiles = (B + 127) / 128;
   p.dup = intra_tc_dup(e, B);
   p.ptiles = (B * p.dup + 127) / 128;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(p.stiles * (NDF / 2 + e.d.fe[3])));
-  cfg.blockDim = dim3(TC_NT);
-  cfg.dynamicSmemBytes = POST_TC_SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k_dprnn_post_tc, p);
+  p.tiles1 = even(p.stiles * e.d.fe[3]);
+  p.tiles0 = even(p.stiles * (NDF / 2));
+  cfg.gridDim = dim3((unsigned)(p.tiles0 + p.tiles1));
+  pdl_attr();
+  if (pair) cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<true>, p);
+  else cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<false>, p);
 }
 
 void init_dprnn_tc_kernels() {
-  cudaFuncSetAttribute(k_dprnn_post_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_post_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_post_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_TC_SMEM);
 }
 
 }  // namespace dpdf

@@ -140,7 +140,9 @@ int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the la
  * per CTA); "sep_tma" 0/1 tensor-core separable convs as the persistent TMA-fed kernel; "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel; "c0_fp16" 0/1 c0 ring stored in half precision (switch only on freshly reset streams); "ana_nb" / "syn_sb" caps on the
  * streams per CTA of the analysis / synthesis kernels; "post_pf" L2 prefetch distance of the post kernel; "dfp_ps" 0/1
  * df pathway conv as pending partial sums (switch only on freshly reset streams); "pdl" 0 / 1 chain every kernel of a
- * hop with programmatic dependent launches / 2 every segment but the DPRNN stack; "tail_pdl" 0/1 the dense tail only. */
+ * hop with programmatic dependent launches / 2 every segment but the DPRNN stack; "tail_pdl" 0/1 the dense tail only; "intra_pdl" 0/1 the sweep of block i >= 1 as a programmatic dependent of the previous
+ * post kernel; "post_pair" 0/1/2 post kernel as cta_group::2 CTA pairs (never / always / when not overlapped with its sweep;
+ * measured slower, off). */
 int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value);
 int dpdf_time_kernels(dpdf_engine* e, int32_t B, int32_t iters, float* ms_out, const char** names_out,
                       int32_t max_entries, int32_t* n_entries); /* per-kernel CUDA-event timing */

@@ -188,6 +188,33 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
         _engine(name, 4, 2).set_option("intra_dup", 3)
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 130), ("dpdfnet4", 300), ("dpdfnet2_48khz_hr", 67)])
+def test_post_kernel_as_cta_pairs(torch_cuda, name, B, overlap):
+    """k_dprnn_post_tc<PAIR>: clusters of two CTAs issue every product as one tcgen05.mma.cta_group::2 of M = 256 over the
+    pair's two tiles, each CTA holding half of every weight slab.  Same arithmetic per row as the single-CTA kernel, so
+    the results must be bit-identical - with odd tile counts per branch (a padding tile closes the pair), ragged last
+    tiles, after the sweep and overlapped with it - and match the oracle."""
+    T = 4
+    hop = get_spec(name).hop
+    rng = np.random.default_rng(41)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    outs = {}
+    for pair in (0, 1):
+        eng = _engine(name, 8, B)
+        eng.set_option("intra_tc", 1)
+        eng.set_option("overlap", overlap)
+        eng.set_option("lanes", 1)
+        eng.set_option("post_pair", pair)
+        outs[pair] = (eng.run_pcm_host(pcm), eng.debug_tensor("xd", B), eng.debug_tensor("xe", B), eng.state_export(B - 1))
+        eng.close()
+    for a, b in zip(outs[1], outs[0]):
+        assert np.array_equal(a, b)
+    ora = _oracle(name, 8, B)
+    ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    assert np.abs(outs[1][0] - ref).max() < WAVE_TOL
+
+
 @pytest.mark.parametrize("intra_tc", [0, 1])
 def test_lanes_match_single_chain(torch_cuda, intra_tc):
     """A batched step split into lanes (row ranges running as forked kernel chains inside one CUDA graph) must give

@@ -31,7 +31,20 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-    k_dprnn_post_tc<<<p.tiles0, TC_NT, POST_TC_SMEM>>>(p);
+#ifdef PT_PAIR     // CTA pairs: clusters of two, even tile count
+    {
+      p.tiles0 = (p.tiles0 + 1) & ~1;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(p.tiles0); cfg.blockDim = dim3(TC_NT); cfg.dynamicSmemBytes = POST_TC_SMEM;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<true>, p);
+    }
+#else
+    k_dprnn_post_tc<false><<<p.tiles0, TC_NT, POST_TC_SMEM>>>(p);
+#endif
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
