@@ -111,16 +111,20 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
     const int rsub = (tid & 7) | ((tid >> 7) << 3);
     pdl_wait();                                               // x and h_prev come from the kernels before this one
     uint32_t ovf = 0;                                         // FP16 range guard (tc_common.cuh:f16_nonfinite)
-    for (int s = 0; s < 8; ++s) {
-      const int buf = s & 1, k0 = (s & 3) * 64 + g * 4;
+    // the activation chunk of stage s + 1 is in flight while stage s is converted: with the loads issued only when their
+    // stage came up, every one of the eight stages ate a full L2 round trip (27 us per launch at 1024 streams)
+    auto load_stage = [&](int s, float4 (&v)[8]) {
+      const int k0 = (s & 3) * 64 + g * 4;
       const bool hpart = s >= 4;
-      float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rsub + 16 * i;
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < valid) v[i] = __ldg(reinterpret_cast<const float4*>((hpart ? q.hstate + s_hoff[r] : q.x + (size_t)(b0 + r) * H) + k0));
       }
+    };
+    auto convert_stage = [&](int s, const float4 (&v)[8]) {
+      const int buf = s & 1;
       if (s >= 2) mbar_wait(done + s - 2, 0);                 // MMAs that read this image pair are complete
       unsigned char* img = Asm + buf * 2 * GT_AIMG;
 #pragma unroll
@@ -137,6 +141,15 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
       fence_async_smem();
       if (buf == 0) asm volatile("bar.arrive 1, %0;" ::"n"(GT_NT) : "memory");
       else asm volatile("bar.arrive 2, %0;" ::"n"(GT_NT) : "memory");
+    };
+    float4 va[8], vb[8];
+    load_stage(0, va);
+#pragma unroll 1
+    for (int s = 0; s < 8; s += 2) {
+      load_stage(s + 1, vb);
+      convert_stage(s, va);
+      if (s + 2 < 8) load_stage(s + 2, va);
+      convert_stage(s + 1, vb);
     }
     if (ovf) p.io->err[DPDF_ERRW_RANGE] = 1;
     // ---- epilogue: thread = (stream row = TMEM lane, 32 units) ----------------------------------------------------

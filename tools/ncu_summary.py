@@ -78,7 +78,7 @@ def traffic(args):
     import os
     model, batch, reps = args[0], int(args[1]), args[2:]
     names = {"k_dprnn_intra_tc": "dprnn_intra", "k_dprnn_intra": "dprnn_intra", "k_dprnn_post_tc": "dprnn_post", "k_dprnn_post": "dprnn_post",
-             "k_sepconv_tc": "sepconv", "k_sepconv": "sepconv", "k_gru_tc": "gru", "k_gl": "gl", "k_analysis": "analysis",
+             "k_sepconv_tc": "sepconv", "k_sepconv_tma": "sepconv", "k_sepconv": "sepconv", "k_gru_tc": "gru", "k_gl": "gl", "k_analysis": "analysis",
              "k_synthesis": "synthesis", "k_df_pathway": "df_pathway"}
     out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "ncu_traffic.json")
     recs = json.load(open(out_path)) if os.path.exists(out_path) else []
