@@ -1170,6 +1170,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
       e.intra_tc_min = value;
     }
     drop_graphs(e);
+  } else if (strcmp(key, "gru_uc") == 0) {
+    if (value != 0 && value != 32 && value != 64) return fail(DPDF_ERR_INVALID, "gru_uc must be 0 (auto), 32 or 64");
+    e.gru_uc = value;
+    drop_graphs(e);
   } else if (strcmp(key, "post_pair") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "post_pair must be 0 (single CTAs), 1 (CTA pairs) or 2 (pairs when not overlapped with the sweep)");
     e.post_pair = value;

@@ -194,6 +194,7 @@ struct Engine {
   int intra_dup = 0;              // k_dprnn_intra_tc row duplication D (128 / D streams per CTA): 0 = auto (largest D whose sweep fits one wave), 1, 2, 4
   int gru_tc = 2;                 // GRUCell(256) gate GEMMs on tcgen05: 0 never, 1 always, 2 = when B >= gru_tc_min
   int gru_tc_min = 256;
+  int gru_uc = 0;                 // k_gru_tc hidden units per CTA: 0 = auto (32 while the doubled grid fits one wave), 32, 64
   int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min
   int sep_tc_min = 256;
   int sep_tma = 1;                // tensor-core separable convs as the persistent TMA-fed kernel (k_conv_tma.cu) instead of k_sepconv_tc

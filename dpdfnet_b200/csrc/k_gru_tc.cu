@@ -9,6 +9,12 @@
 // 48 KB weight slab ([192 gate rows][64 k], hi | lo; weights.py: tc_w) through a 3-deep ring of bulk copies and
 // fires 24 MMAs per stage; stage completion (tcgen05.commit) frees both rings.  Epilogue: thread = (TMEM lane =
 // stream, 32 units): gates, h' = (1 - z) n + z h  ->  hout (the state itself is committed by k_gru_commit).
+//
+// Template parameter UC = hidden units per CTA.  UC = 64 (above) is the throughput form.  At latency batch sizes the
+// launch is bound by the weight stream of each CTA - eight dependent 48 KB slabs through a 3-deep ring, 27 us per launch
+// at 1024 streams for 5 us of MMAs - so UC = 32 halves the slab (the three 4 KB row blocks r | z | n of the unit half are
+// pulled out of the same packed image), makes the ring six deep in the same shared memory and spreads the weight stream
+// over twice as many SMs.
 #include "engine.h"
 #include "tc_common.cuh"
 
@@ -21,10 +27,11 @@ using namespace tc;
 constexpr int GT_CONV = 256;                 // converter / epilogue threads
 constexpr int GT_NT = GT_CONV + 32;          // + issuer warp
 constexpr int GT_AIMG = 128 * 64 * 2;        // one FP16 [128][64] image
-constexpr int GT_WSLAB = 2 * 192 * 64 * 2;   // [192][64] hi | lo
+constexpr int GT_WSLAB = 2 * 192 * 64 * 2;   // packed slab of a 64-unit chunk: [192 gate rows][64 k], hi | lo (48 KB)
+constexpr int GT_WRING = 3 * GT_WSLAB;       // bytes of the weight ring
 constexpr int GT_OFF_W = 2 * 2 * GT_AIMG;    // A ring: 2 stages x (hi | lo)
-constexpr int GT_OFF_MISC = GT_OFF_W + 3 * GT_WSLAB;
-constexpr size_t GRU_TC_SMEM = GT_OFF_MISC + 1024 + 128;   // + slot offsets [128] int64 ... barriers
+constexpr int GT_OFF_MISC = GT_OFF_W + GT_WRING;
+constexpr size_t GRU_TC_SMEM = GT_OFF_MISC + 1024 + 192;   // + slot offsets [128] int64 ... barriers
 
 }  // namespace
 
@@ -34,29 +41,32 @@ struct GRUTcParams {
   int B;
 };
 
+template <int UC>
 __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
+  constexpr int SLAB = GT_WSLAB * UC / 64;                    // this CTA's slab: [3 UC gate rows][64 k], hi | lo
+  constexpr int NW = GT_WRING / SLAB;                         // ring depth: 3 (UC = 64) or 6 (UC = 32)
   pdl_trigger();        // griddepcontrol.wait comes after the prologue and the first weight slabs: neither depends on the previous kernel
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* Asm = smem_raw;
   unsigned char* Wsm = smem_raw + GT_OFF_W;
   long long* s_hoff = reinterpret_cast<long long*>(smem_raw + GT_OFF_MISC);
-  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem_raw + GT_OFF_MISC + 1024);   // [3]
-  uint64_t* done = full_w + 3;                                                     // [8], one per stage, single use
+  uint64_t* full_w = reinterpret_cast<uint64_t*>(smem_raw + GT_OFF_MISC + 1024);   // [NW]
+  uint64_t* done = full_w + NW;                                                    // [8], one per stage, single use
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 8);
 
   const GRUProblem& q = p.prob[blockIdx.z];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * 128;
-  const int uc = blockIdx.y;                                  // unit chunk: hidden units [64 uc, 64 uc + 64)
+  const int uc = blockIdx.y;                                  // unit chunk: hidden units [UC uc, UC uc + UC)
   const int valid = min(128, p.B - b0);
 
   if (tid < 128) s_hoff[tid] = tid < valid ? (long long)io_slot(p.io, b0 + tid) * q.hs_stride : 0;
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < 11; ++i) mbar_init(full_w + i, 1);
+    for (int i = 0; i < NW + 8; ++i) mbar_init(full_w + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  if (warp == 0) tmem_alloc<4 * UC>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -64,12 +74,27 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
 
   if (warp == 8) {
     // ---- issuer warp: weight slab ring + MMAs -----------------------------------------------------------------
-    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(q.w.tc_w) + (size_t)uc * 8 * GT_WSLAB;
+    // packed per 64-unit chunk (weights.py: tc_w): 8 stages x [r 64 | z 64 | n 64 rows][64 k] hi | lo, 8 rows per KB
+    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(q.w.tc_w) + (size_t)(uc * UC / 64) * 8 * GT_WSLAB;
     auto load_w = [&](int s) {
-      mbar_expect_tx(full_w + s % 3, GT_WSLAB);
-      bulk_g2s(Wsm + (s % 3) * GT_WSLAB, wsrc + (size_t)s * GT_WSLAB, GT_WSLAB, full_w + s % 3);
+      mbar_expect_tx(full_w + s % NW, SLAB);
+      unsigned char* dst = Wsm + (s % NW) * SLAB;
+      const unsigned char* src = wsrc + (size_t)s * GT_WSLAB;
+      if constexpr (UC == 64) {
+        bulk_g2s(dst, src, GT_WSLAB, full_w + s % NW);
+      } else {                                               // the unit half's row blocks of r, z and n, out of the hi and the lo image
+        const int sub = (uc % (64 / UC)) * UC * 128;         // byte offset of UC rows inside a 64-row gate block
+#pragma unroll
+        for (int img = 0; img < 2; ++img)
+#pragma unroll
+          for (int gate = 0; gate < 3; ++gate)
+            bulk_g2s(dst + img * (SLAB / 2) + gate * UC * 128, src + img * (GT_WSLAB / 2) + gate * 8192 + sub, UC * 128, full_w + s % NW);
+      }
     };
-    if (lane == 0) { load_w(0); load_w(1); load_w(2); }
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < NW; ++s) load_w(s);
+    }
     pdl_wait();
     for (int s = 0; s < 8; ++s) {
       const int buf = s & 1;
@@ -77,28 +102,28 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
       else asm volatile("bar.sync 2, %0;" ::"n"(GT_NT) : "memory");
       if (lane == 0) {
         tc_fence_after();
-        mbar_wait(full_w + s % 3, (s / 3) & 1);
+        mbar_wait(full_w + s % NW, (s / NW) & 1);
         const uint32_t ah = smem_u32(Asm) + buf * 2 * GT_AIMG, al = ah + GT_AIMG;
-        const uint32_t bh = smem_u32(Wsm) + (s % 3) * GT_WSLAB, bl = bh + GT_WSLAB / 2;
+        const uint32_t bh = smem_u32(Wsm) + (s % NW) * SLAB, bl = bh + SLAB / 2;
         const bool hpart = s >= 4;
-        const uint32_t ncol = hpart ? 192u : 128u;           // in (x part) / hn (h part)
+        const uint32_t ncol = hpart ? 3u * UC : 2u * UC;     // in (x part) / hn (h part)
         const uint32_t nfirst = (s & 3) == 0 ? 0u : 1u;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t dah = umma_desc(ah + ks * 256, 1024), dal = umma_desc(al + ks * 256, 1024);
           const uint64_t dbh = umma_desc(bh + ks * 256, 1024), dbl = umma_desc(bl + ks * 256, 1024);
-          const uint64_t dnh = umma_desc(bh + 16 * 1024 + ks * 256, 1024), dnl = umma_desc(bl + 16 * 1024 + ks * 256, 1024);
-          umma_f16(tmem, dah, dbh, idesc_f16(128, 128), (s > 0 || ks > 0) ? 1u : 0u);   // r | z: x and h parts add up
-          umma_f16(tmem, dal, dbh, idesc_f16(128, 128), 1);
-          umma_f16(tmem, dah, dbl, idesc_f16(128, 128), 1);
-          umma_f16(tmem + ncol, dah, dnh, idesc_f16(128, 64), ks > 0 ? 1u : nfirst);
-          umma_f16(tmem + ncol, dal, dnh, idesc_f16(128, 64), 1);
-          umma_f16(tmem + ncol, dah, dnl, idesc_f16(128, 64), 1);
+          const uint64_t dnh = umma_desc(bh + 2 * UC * 128 + ks * 256, 1024), dnl = umma_desc(bl + 2 * UC * 128 + ks * 256, 1024);
+          umma_f16(tmem, dah, dbh, idesc_f16(128, 2 * UC), (s > 0 || ks > 0) ? 1u : 0u);   // r | z: x and h parts add up
+          umma_f16(tmem, dal, dbh, idesc_f16(128, 2 * UC), 1);
+          umma_f16(tmem, dah, dbl, idesc_f16(128, 2 * UC), 1);
+          umma_f16(tmem + ncol, dah, dnh, idesc_f16(128, UC), ks > 0 ? 1u : nfirst);
+          umma_f16(tmem + ncol, dal, dnh, idesc_f16(128, UC), 1);
+          umma_f16(tmem + ncol, dah, dnl, idesc_f16(128, UC), 1);
         }
         umma_commit(done + s);
-        if (s >= 1 && s + 2 < 8) {                            // slab ring slot of stage s - 1 is free once its MMAs are done
+        if (s >= 1 && s + NW - 1 < 8) {                       // slab ring slot of stage s - 1 is free once its MMAs are done
           mbar_wait(done + s - 1, 0);
-          load_w(s + 2);
+          load_w(s + NW - 1);
         }
       }
       __syncwarp();
@@ -152,20 +177,20 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
       convert_stage(s + 1, vb);
     }
     if (ovf) p.io->err[DPDF_ERRW_RANGE] = 1;
-    // ---- epilogue: thread = (stream row = TMEM lane, 32 units) ----------------------------------------------------
+    // ---- epilogue: thread = (stream row = TMEM lane, UC / 2 units) ------------------------------------------------
     mbar_wait(done + 7, 0);
     tc_fence_after();
     const int qd = warp & 3, half = warp >> 2, row = qd * 32 + lane;
-    const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + half * 32;
+    const uint32_t ta = tmem + ((uint32_t)(qd * 32) << 16) + half * (UC / 2);
     const float* bias = q.w.bias;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < UC / 16; ++c) {
       uint32_t gr[8], gz[8], gi[8], gh[8];
       tmem_ld8_nowait(ta + c * 8, gr);
-      tmem_ld8_nowait(ta + 64 + c * 8, gz);
-      tmem_ld8_nowait(ta + 128 + c * 8, gi);
-      tmem_ld8_nowait(ta + 192 + c * 8, gh);
-      const int u = uc * 64 + half * 32 + c * 8;
+      tmem_ld8_nowait(ta + UC + c * 8, gz);
+      tmem_ld8_nowait(ta + 2 * UC + c * 8, gi);
+      tmem_ld8_nowait(ta + 3 * UC + c * 8, gh);
+      const int u = uc * UC + half * (UC / 2) + c * 8;
       float hp[8];
       if (row < valid) {
         const float4 a = *reinterpret_cast<const float4*>(q.hstate + s_hoff[row] + u);
@@ -194,7 +219,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if (warp == 0) tmem_dealloc<4 * UC>(tmem);
 }
 
 void launch_gru_tc(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st) {
@@ -202,12 +227,16 @@ void launch_gru_tc(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStr
   p.io = e.io_dev;
   p.B = B;
   for (int i = 0; i < nprob; ++i) p.prob[i] = probs[i];
-  dim3 grid((B + 127) / 128, H / 64, nprob);
-  launch_k(e, k_gru_tc, dim3(grid), dim3(GT_NT), GRU_TC_SMEM, st, p);
+  // 32-unit CTAs while twice the grid still fits one wave (Engine::gru_uc = 0: auto)
+  const int tiles = (std::max(B, e.total_B) + 127) / 128;
+  const bool small = e.gru_uc == 32 || (e.gru_uc == 0 && tiles * (H / 32) * nprob <= e.num_sms);
+  if (small) launch_k(e, k_gru_tc<32>, dim3((B + 127) / 128, H / 32, nprob), dim3(GT_NT), GRU_TC_SMEM, st, p);
+  else launch_k(e, k_gru_tc<64>, dim3((B + 127) / 128, H / 64, nprob), dim3(GT_NT), GRU_TC_SMEM, st, p);
 }
 
 void init_gru_tc_kernels() {
-  cudaFuncSetAttribute(k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRU_TC_SMEM);
+  cudaFuncSetAttribute(k_gru_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRU_TC_SMEM);
+  cudaFuncSetAttribute(k_gru_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRU_TC_SMEM);
 }
 
 }  // namespace dpdf

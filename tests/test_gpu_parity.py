@@ -215,6 +215,30 @@ def test_post_kernel_as_cta_pairs(torch_cuda, name, B, overlap):
     assert np.abs(outs[1][0] - ref).max() < WAVE_TOL
 
 
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 150), ("dpdfnet2_48khz_hr", 40)])
+def test_gru_tc_units_per_cta(torch_cuda, name, B):
+    """k_gru_tc<UC>: 64 hidden units per CTA (throughput form, 3-deep ring of 48 KB weight slabs) and 32 (latency form:
+    half slabs cut out of the same packed image, 6-deep ring, twice the CTAs).  Every output column sees the same MMA
+    sequence in both, so they must agree bit for bit; against the oracle through the waveform."""
+    T = 4
+    hop = get_spec(name).hop
+    rng = np.random.default_rng(51)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    outs = {}
+    for uc in (64, 32, 0):
+        eng = _engine(name, 13, B)
+        eng.set_option("gru_tc", 1)
+        eng.set_option("gru_uc", uc)
+        outs[uc] = (eng.run_pcm_host(pcm), eng.debug_tensor("emb", B), eng.debug_tensor("m", B), eng.state_export(B - 1))
+        eng.close()
+    for uc in (32, 0):
+        for a, b in zip(outs[uc], outs[64]):
+            assert np.array_equal(a, b), uc
+    ora = _oracle(name, 13, B)
+    ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    assert np.abs(outs[32][0] - ref).max() < WAVE_TOL
+
+
 @pytest.mark.parametrize("intra_tc", [0, 1])
 def test_lanes_match_single_chain(torch_cuda, intra_tc):
     """A batched step split into lanes (row ranges running as forked kernel chains inside one CUDA graph) must give
