@@ -297,6 +297,8 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   if (cudaMalloc(&e.progress_dev, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int)) != cudaSuccess)
     return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(progress) failed"));
   cudaMemset(e.progress_dev, 0, (size_t)Engine::MAX_LANES * 4 * e.progress_tiles * sizeof(int));
+  if (cudaMalloc(&e.post_ctr_dev, Engine::MAX_LANES * 4 * sizeof(int)) != cudaSuccess) return bail(fail(DPDF_ERR_NOMEM, "cudaMalloc(post counters) failed"));
+  cudaMemset(e.post_ctr_dev, 0, Engine::MAX_LANES * 4 * sizeof(int));
   if (cudaHostAlloc(&e.err_host, 4 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer(&e.err_dev, e.err_host, 0) != cudaSuccess)
     return bail(fail(DPDF_ERR_NOMEM, "cudaHostAlloc(error words) failed"));
@@ -342,7 +344,7 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
     if (e.lane_done[l]) cudaEventDestroy(e.lane_done[l]);
   }
   if (e.lane_fork) cudaEventDestroy(e.lane_fork);
-  cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_lanes); cudaFree(e.progress_dev);
+  cudaFree(e.weights_dev); cudaFree(e.arena); cudaFree(e.aux_int); cudaFree(e.io_lanes); cudaFree(e.progress_dev); cudaFree(e.post_ctr_dev);
   cudaFree(e.slots_dev); cudaFree(e.flags_dev); cudaFree(e.stage_in); cudaFree(e.stage_out);
   for (int k = 0; k < 2; ++k) {
     cudaFree(e.pipe.in[k]); cudaFree(e.pipe.out[k]); cudaFree(e.pipe.slots[k]); cudaFree(e.pipe.flags[k]);
@@ -1169,6 +1171,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     } else {
       e.intra_tc_min = value;
     }
+    drop_graphs(e);
+  } else if (strcmp(key, "post_res") == 0) {
+    e.post_res = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "gru_uc") == 0) {
     if (value != 0 && value != 32 && value != 64) return fail(DPDF_ERR_INVALID, "gru_uc must be 0 (auto), 32 or 64");

@@ -201,6 +201,11 @@ struct Engine {
   int ana_force = 0, syn_force = 0;   // experiments: force that many streams per CTA regardless of the grid size (0 = auto)
   int ana_nb = 32, syn_sb = 16;   // caps on the streams per CTA of the analysis / synthesis kernels (8|16|32, 4|8|16)
   int post_pf = 1;                // k_dprnn_post_tc: L2 prefetch distance in units of the SM count (2 CTAs per SM -> 2), 0 = off
+  int post_res = 0;               // k_dprnn_post_res (persistent, resident weights) when the post kernel runs after its sweep.  Bit-identical,
+                                  // parity-tested, measured on par / slightly slower (profiles/r2E_*: post 2.53 -> 2.58 ms per hop at 16 384
+                                  // streams): without weight waits a tile takes 21-26 k cycles, but one CTA per SM overlaps nothing, and two
+                                  // co-resident streaming CTAs at 37-44 k cycles each come to the same 19-22 k per tile
+  int* post_ctr_dev = nullptr;    // [MAX_LANES][4] tile counters of k_dprnn_post_res (self-resetting)
   int post_pair = 0;              // k_dprnn_post_tc as CTA pairs (cta_group::2, M = 256): 0 never, 1 always, 2 = when not overlapped with its sweep.
                                   // Bit-identical and parity-tested, but measured SLOWER (profiles/r2A_*: post 2.54 -> 2.79 ms per hop at 16 384
                                   // streams): the 4-deep ring does cut phase 2 (15.0 k -> 8.2 k cycles per tile) but the pair runs in lock step -

@@ -68,6 +68,8 @@ struct PostTcParams {
   const int* progress;    // sweep counters [df: 2 dirs x ptiles | erb: 2 dirs x stiles], nullptr = row-major tiles of a finished sweep
   int stiles;             // ceil(B / 128)
   int dup, ptiles;        // the df sweep's CTAs own 128 / dup streams each: ptiles = ceil(B * dup / 128) counters per direction (erb: dup = 1)
+  int* ctr;               // k_dprnn_post_res: [0] next df tile, [1] next erb tile, [2] CTAs that have finished (the last one zeroes all three)
+  int ctas_erb;           // k_dprnn_post_res: CTAs [0, ctas_erb) serve the erb branch, the others the df branch
   int pf_dist;            // row-major mode: warm L2 with the inputs of tile blockIdx.x + pf_dist (0 = off); CTAs are dispatched in
                           // index order, so with pf_dist = resident CTAs that tile starts about when this one ends
 #ifdef PT_TIMELINE
@@ -530,6 +532,363 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_dprnn_post_res: the same tile math as k_dprnn_post_tc, as a PERSISTENT kernel with RESIDENT weights (throughput form,
+// used when the kernel runs after its sweep).  The timeline of the streaming form (profiles/r2z_post_timeline.txt) shows
+// 11-17 k of a tile's 37-44 k cycles in phase 2 - 72 MMAs that need 3 k - and 2-4 k in phases 1 and 3, all of it waiting
+// for 16 KB weight slabs that are requested only when a ring buffer drains (1-2 us per bulk copy from L2, 144 KB per
+// tile).  Here one CTA per SM serves one branch, pulls that branch's nine slabs ONCE (144 KB next to the 64 KB of
+// operand images), takes tiles from an atomic counter and issues every phase back to back.  What two co-resident CTAs
+// used to hide - the DRAM latency of a tile's inputs - is hidden explicitly: the hcat tile of the NEXT tile is loaded
+// into registers (32 per thread; one CTA per SM leaves 128) right after the current one is staged, and its block input
+// and state rows are warmed in L2 a whole tile ahead.
+constexpr int PR_OFF_W = 4 * IMG;                        // nine resident weight slabs (processing order)
+constexpr int PR_OFF_SP = PR_OFF_W + 9 * WSLAB;
+constexpr int PR_OFF_RED = PR_OFF_SP + 640 * 4;
+constexpr int PR_OFF_HOFF = PR_OFF_RED + 1024 * 4;
+constexpr int PR_OFF_COMMIT = PR_OFF_HOFF + 128 * 8;
+constexpr int PR_OFF_BAR = PR_OFF_COMMIT + 128 * 4;      // weights landed, phase result ready, TMEM slot, tile ids [2]
+constexpr size_t POST_RES_SMEM = PR_OFF_BAR + 64;
+
+__global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_res(PostTcParams p) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* RA = smem_raw;
+  unsigned char* RW = smem_raw + PR_OFF_W;
+  float* sp = reinterpret_cast<float*>(smem_raw + PR_OFF_SP);
+  float* red = reinterpret_cast<float*>(smem_raw + PR_OFF_RED);
+  long long* s_hoff = reinterpret_cast<long long*>(smem_raw + PR_OFF_HOFF);
+  int* s_commit = reinterpret_cast<int*>(smem_raw + PR_OFF_COMMIT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + PR_OFF_BAR);   // [0] weights landed, [1] phase result ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  volatile int* s_tile = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [2] tile id of the current / next iteration
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
+  const int bi = (int)blockIdx.x < p.ctas_erb ? 1 : 0;
+  const PostTcBranch& q = p.br[bi];
+  const int ntiles = bi ? p.tiles1 : p.tiles0;
+  const long long nrows = (long long)p.B * q.Fp;
+  uint32_t ovf = 0;
+
+  if (tid < 64) {
+    sp[tid] = q.fc_b[tid]; sp[64 + tid] = q.ln_g[tid]; sp[128 + tid] = q.ln_b[tid];
+    sp[448 + tid] = q.fc2_b[tid]; sp[512 + tid] = q.ln2_g[tid]; sp[576 + tid] = q.ln2_b[tid];
+  }
+  if (tid < 256) sp[192 + tid] = q.bias[tid];
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_tile[0] = atomicAdd(p.ctr + bi, 1);
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {                                          // the branch's nine slabs, once, in processing order
+    mbar_expect_tx(bars, 9 * WSLAB);
+    const unsigned char* fc = reinterpret_cast<const unsigned char*>(q.tc_fc_w);
+    const unsigned char* gt = reinterpret_cast<const unsigned char*>(q.tc_gates);
+    bulk_g2s(RW, fc, 2 * WSLAB, bars);                                       // fc_intra K halves
+    const int order[6] = {0, 3, 1, 4, 2, 5};                                 // r(y), r(h), z(y), z(h), n(y), n(h)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) bulk_g2s(RW + (2 + i) * WSLAB, gt + (size_t)order[i] * WSLAB, WSLAB, bars);
+    bulk_g2s(RW + 8 * WSLAB, q.tc_fc2_w, WSLAB, bars);
+  }
+
+  const int rr = lane >> 2, cc = lane & 3;
+  const int sub_off = (cc >> 1) * 128 + rr * 16 + (cc & 1) * 8;
+  const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16) + cg * 16;
+  constexpr uint32_t IDESC = idesc_f16(128, 64);
+  const uint32_t a_base = smem_u32(RA), w_base = smem_u32(RW);
+  auto run_slab = [&](int i, int a_img, uint32_t col, uint32_t accumulate) {
+    constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint32_t ah = a_base + a_img * IMG, bh = w_base + i * WSLAB;
+    const uint64_t dah = DESC0 | (ah >> 4), dal = dah + (IMG >> 4), dbh = DESC0 | (bh >> 4), dbl = dbh + (WSLAB / 2 >> 4);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      umma_f16(tmem + col, dah + ks * 16, dbh + ks * 16, IDESC, accumulate);
+      umma_f16(tmem + col, dal + ks * 16, dbh + ks * 16, IDESC, 1);
+      umma_f16(tmem + col, dah + ks * 16, dbl + ks * 16, IDESC, 1);
+      accumulate = 1;
+    }
+  };
+  auto quad_sync = [&]() {
+    if (qd == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else if (qd == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+    else if (qd == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
+    else asm volatile("bar.sync 4, 128;" ::: "memory");
+  };
+  auto layernorm16 = [&](float (&v)[16], const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    red[cg * 128 + row] = s;
+    quad_sync();
+    const float mean = (red[row] + red[128 + row] + red[256 + row] + red[384 + row]) * (1.0f / 64.0f);
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] -= mean; qq += v[i] * v[i]; }
+    red[512 + cg * 128 + row] = qq;
+    quad_sync();
+    const float rstd = rsqrtf((red[512 + row] + red[640 + row] + red[768 + row] + red[896 + row]) * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] * rstd * g[cg * 16 + i] + b[cg * 16 + i];
+  };
+  // hcat tile (rows [base, base + 128)) -> registers: 128 blocks of 8 rows x 16 floats, 8 per warp
+  auto load_hcat = [&](long long base, float4 (&v)[8]) {
+    const int nvalid = (int)max(0ll, min(128ll, nrows - base));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int blk = warp + 16 * i, rg = blk >> 3, kb = blk & 7;
+      const int r = rg * 8 + rr;
+      v[i] = r < nvalid ? __ldg(reinterpret_cast<const float4*>(q.hcat + (base + r) * 2 * C + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  __syncthreads();                                         // s_tile[0]
+  int cur = s_tile[0];
+  float4 pv[8];
+  if (cur < ntiles) load_hcat((long long)cur * 128, pv);
+  uint32_t ph = 0;                                         // completions of the phase barrier so far
+  bool wait_w = true;
+#ifdef PT_TIMELINE
+#define PRL(slot) do { if (blockIdx.x == gridDim.x - 1 && tid == 64 && it == 2) p.tl[slot] = clock64(); } while (0)
+#else
+#define PRL(slot) do { } while (0)
+#endif
+  for (int it = 0; cur < ntiles; ++it) {
+    PRL(0);
+    const long long rbase = (long long)cur * 128;
+    const int valid = (int)min(128ll, nrows - rbase);
+    if (tid == 0) s_tile[(it + 1) & 1] = atomicAdd(p.ctr + bi, 1);
+    if (tid < 128) {
+      long long off = 0;
+      int commit = 0;
+      if (tid < valid) {
+        const long long r = rbase + tid;
+        const int b = (int)(r / q.Fp), f = (int)(r % q.Fp);
+        off = (long long)io_slot(p.io, b) * q.per_slot + (long long)f * C;
+        commit = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) ? 0 : 1;
+      }
+      s_hoff[tid] = off;
+      s_commit[tid] = commit;
+    }
+    // ---- stage the prefetched hcat tile as two K=64 operand image pairs (split on the fly) --------------------------
+    // (the barrier that ended the previous tile's write-out ordered its reads of the output staging before these writes)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int blk = warp + 16 * i, rg = blk >> 3, kb = blk & 7;
+      uint2 h, l;
+      split2_f16(pv[i].x, pv[i].y, h.x, l.x);
+      split2_f16(pv[i].z, pv[i].w, h.y, l.y);
+      unsigned char* dst = RA + (kb >> 2) * 2 * IMG + rg * 1024 + (kb & 3) * 256 + sub_off;
+      *reinterpret_cast<uint2*>(dst) = h;
+      *reinterpret_cast<uint2*>(dst + IMG) = l;
+    }
+    float4 xv[4];
+    {
+      const float* xr = q.xin + (rbase + row) * C + cg * 16;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) xv[c] = row < valid ? __ldg(reinterpret_cast<const float4*>(xr + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();                                       // images, s_hoff and the next tile id are visible
+    tc_fence_after();
+    const int nxt = s_tile[(it + 1) & 1];
+    PRL(1);
+
+    // ---- phase 1: acc[0,64) = hcat * fc_intra^T ---------------------------------------------------------------
+    if (tid == 0) {
+      if (wait_w) mbar_wait(bars, 0);                      // the resident weights have landed (first tile only)
+      run_slab(0, 0, 0, 0);
+      run_slab(1, 2, 0, 1);
+      umma_commit(bars + 1);
+    }
+    wait_w = false;
+    // the next tile: its hcat rows into registers, its block input and state rows into L2 (a whole tile ahead)
+    if (nxt < ntiles) {
+      const long long nbase = (long long)nxt * 128;
+      load_hcat(nbase, pv);
+      const int nvalid = (int)min(128ll, nrows - nbase);
+      if (tid == 0) {
+        bulk_prefetch_l2(q.xin + nbase * C, (uint32_t)nvalid * C * 4);
+      } else if (tid >= 128 && tid < 128 + nvalid) {
+        const long long r = nbase + (tid - 128);
+        const int b = (int)(r / q.Fp), f = (int)(r % q.Fp);
+        const float* hp = q.hstate + (long long)io_slot(p.io, b) * q.per_slot + (long long)f * C;
+        prefetch_l2(hp);
+        prefetch_l2(hp + 32);
+      }
+    }
+    float4 hv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+      const int r = rg * 8 + rr;
+      hv[i] = r < valid ? __ldg(reinterpret_cast<const float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (warp == 0) mbar_wait(bars + 1, ph & 1);
+    ++ph;
+    __syncthreads();
+    tc_fence_after();
+    PRL(2);
+
+    unsigned char* y_hi = RA;
+    unsigned char* h_hi = RA + 2 * IMG;
+    {
+      float v[16];
+      tmem_ld16(lane_base, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += sp[cg * 16 + i];
+      layernorm16(v, sp + 64, sp + 128);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float y[8];
+        y[0] = v[c * 8 + 0] + xv[2 * c].x; y[1] = v[c * 8 + 1] + xv[2 * c].y; y[2] = v[c * 8 + 2] + xv[2 * c].z; y[3] = v[c * 8 + 3] + xv[2 * c].w;
+        y[4] = v[c * 8 + 4] + xv[2 * c + 1].x; y[5] = v[c * 8 + 5] + xv[2 * c + 1].y; y[6] = v[c * 8 + 6] + xv[2 * c + 1].z; y[7] = v[c * 8 + 7] + xv[2 * c + 1].w;
+        uint4 h, l;
+        split8_f16(y, h, l);
+        ovf |= f16_nonfinite(h.x) | f16_nonfinite(h.y) | f16_nonfinite(h.z) | f16_nonfinite(h.w);
+        const int off = img16_off(row, cg * 2 + c);
+        *reinterpret_cast<uint4*>(y_hi + off) = h;
+        *reinterpret_cast<uint4*>(y_hi + IMG + off) = l;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+        uint2 h, l;
+        split2_f16(hv[i].x, hv[i].y, h.x, l.x);
+        split2_f16(hv[i].z, hv[i].w, h.y, l.y);
+        unsigned char* dst = h_hi + rg * 1024 + kb * 256 + sub_off;
+        *reinterpret_cast<uint2*>(dst) = h;
+        *reinterpret_cast<uint2*>(dst + IMG) = l;
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    PRL(3);
+    // ---- phase 2: GRU gate pre-activations: r [0,64) z [64,128) in [128,192) hn [192,256) -----------------------
+    if (tid == 0) {
+      run_slab(2, 0, 0, 0);
+      run_slab(3, 2, 0, 1);
+      run_slab(4, 0, 64, 0);
+      run_slab(5, 2, 64, 1);
+      run_slab(6, 0, 128, 0);
+      run_slab(7, 2, 192, 0);
+      umma_commit(bars + 1);
+    }
+    if (warp == 0) mbar_wait(bars + 1, ph & 1);
+    ++ph;
+    __syncthreads();
+    tc_fence_after();
+    PRL(4);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t gr[8], gz[8], gi[8], gh[8];
+      tmem_ld8_nowait(lane_base + c * 8, gr);
+      tmem_ld8_nowait(lane_base + 64 + c * 8, gz);
+      tmem_ld8_nowait(lane_base + 128 + c * 8, gi);
+      tmem_ld8_nowait(lane_base + 192 + c * 8, gh);
+      const int off = img16_off(row, cg * 2 + c);
+      float hp[8];
+      unsplit8(*reinterpret_cast<const uint4*>(h_hi + off), *reinterpret_cast<const uint4*>(h_hi + IMG + off), hp);
+      tmem_ld_wait();
+      float hn[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int u = cg * 16 + c * 8 + e;
+        const float r = sigmoidf_(__uint_as_float(gr[e]) + sp[192 + u]);
+        const float z = sigmoidf_(__uint_as_float(gz[e]) + sp[256 + u]);
+        const float n = tanhf_(__uint_as_float(gi[e]) + sp[320 + u] + r * (__uint_as_float(gh[e]) + sp[384 + u]));
+        hn[e] = (1.0f - z) * n + z * hp[e];
+      }
+      uint4 h, l;
+      split8_f16(hn, h, l);
+      *reinterpret_cast<uint4*>(h_hi + off) = h;
+      *reinterpret_cast<uint4*>(h_hi + IMG + off) = l;
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    PRL(5);
+
+    // ---- phase 3: acc[0,64) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena ----------------
+    if (tid == 0) {
+      run_slab(8, 2, 0, 0);
+      umma_commit(bars + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int blk = warp + 16 * i, rg = blk >> 2, kb = blk & 3;
+      const int r = rg * 8 + rr;
+      if (r < valid && s_commit[r]) {
+        const unsigned char* src = h_hi + rg * 1024 + kb * 256 + sub_off;
+        const uint2 a = *reinterpret_cast<const uint2*>(src), b = *reinterpret_cast<const uint2*>(src + IMG);
+        const float2 a0 = h2f(a.x), a1 = h2f(a.y), b0 = h2f(b.x), b1 = h2f(b.y);
+        *reinterpret_cast<float4*>(q.hstate + s_hoff[r] + kb * 16 + cc * 4) = make_float4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y);
+      }
+    }
+    float yv[16];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int off = img16_off(row, cg * 2 + c);
+      float t8[8];
+      unsplit8(*reinterpret_cast<const uint4*>(y_hi + off), *reinterpret_cast<const uint4*>(y_hi + IMG + off), t8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[c * 8 + e] = t8[e];
+    }
+    if (warp == 0) mbar_wait(bars + 1, ph & 1);
+    ++ph;
+    __syncthreads();
+    tc_fence_after();
+    PRL(6);
+    {
+      float v[16];
+      tmem_ld16(lane_base, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += sp[448 + cg * 16 + i];
+      layernorm16(v, sp + 512, sp + 576);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(RA + row * 256 + (((cg * 4 + c) ^ (row & 15)) << 4)) =
+            make_float4(v[c * 4] + yv[c * 4], v[c * 4 + 1] + yv[c * 4 + 1], v[c * 4 + 2] + yv[c * 4 + 2], v[c * 4 + 3] + yv[c * 4 + 3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (tid >> 4) + 32 * i, ch = tid & 15;
+      if (r < valid)
+        *reinterpret_cast<float4*>(q.xout + (rbase + r) * C + ch * 4) = *reinterpret_cast<const float4*>(RA + r * 256 + ((ch ^ (r & 15)) << 4));
+    }
+    __syncthreads();                                       // the output staging is free again before the next tile's images are written
+    PRL(7);
+    cur = nxt;
+  }
+  if (ovf) p.io->err[DPDF_ERRW_RANGE] = 1;
+  if (tid == 0) {
+    if (wait_w) mbar_wait(bars, 0);                        // a CTA that found no tile still owns nine bulk copies in flight
+    const int done = atomicAdd(p.ctr + 2, 1);
+    if (done == (int)gridDim.x - 1) {                      // every CTA of this launch has drawn its last tile id: reset for the next launch
+      p.ctr[0] = 0; p.ctr[1] = 0; p.ctr[2] = 0;
+      __threadfence();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   PostTcParams p{};
   p.io = e.io_dev;
@@ -567,6 +926,21 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
     attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
     ++cfg.numAttrs;
   };
+  if (!e.overlap_now && e.post_res) {
+    // persistent form with resident weights: one CTA per SM, each dedicated to one branch (the branches have different
+    // weights), CTAs split in proportion to the branches' tile counts, tiles drawn from per-lane atomic counters
+    p.tiles0 = (int)(((long long)B * (NDF / 2) + 127) / 128);
+    p.tiles1 = (int)(((long long)B * e.d.fe[3] + 127) / 128);
+    const int G = std::min(e.num_sms, p.tiles0 + p.tiles1);
+    p.ctas_erb = G < 2 ? 0 : std::min(G - 1, std::max(1, (int)((long long)G * p.tiles1 / (p.tiles0 + p.tiles1))));
+    p.ctr = e.post_ctr_dev + 4 * e.cur_lane;
+    cfg.dynamicSmemBytes = POST_RES_SMEM;
+    cfg.gridDim = dim3((unsigned)G);
+    cfg.numAttrs = 0;
+    if (e.pdl_now && !e.pdl_first) pdl_attr();
+    cudaLaunchKernelEx(&cfg, k_dprnn_post_res, p);
+    return;
+  }
   if (!e.overlap_now) {
     p.tiles0 = even((int)(((long long)B * (NDF / 2) + 127) / 128));
     p.tiles1 = even((int)(((long long)B * e.d.fe[3] + 127) / 128));
@@ -595,6 +969,7 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
 void init_dprnn_tc_kernels() {
   cudaFuncSetAttribute(k_dprnn_post_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_TC_SMEM);
   cudaFuncSetAttribute(k_dprnn_post_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_post_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_RES_SMEM);
 }
 
 }  // namespace dpdf

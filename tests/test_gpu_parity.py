@@ -239,6 +239,32 @@ def test_gru_tc_units_per_cta(torch_cuda, name, B):
     assert np.abs(outs[32][0] - ref).max() < WAVE_TOL
 
 
+@pytest.mark.parametrize("name,B,lanes", [("dpdfnet2", 130, 1), ("dpdfnet4", 700, 1), ("dpdfnet2_48khz_hr", 67, 1), ("dpdfnet2", 600, 3)])
+def test_post_kernel_persistent_with_resident_weights(torch_cuda, name, B, lanes):
+    """k_dprnn_post_res: one CTA per SM keeps its branch's nine weight slabs in shared memory, draws tiles from an atomic
+    counter (self-resetting: several hops and blocks reuse it) and prefetches the next tile's hcat rows into registers.
+    Same arithmetic per row as k_dprnn_post_tc, so bit-identical results - with more tiles than CTAs, ragged last tiles,
+    and lanes running their own counters side by side."""
+    T = 5
+    hop = get_spec(name).hop
+    rng = np.random.default_rng(61)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    outs = {}
+    for res in (0, 1):
+        eng = _engine(name, 9, B)
+        eng.set_option("intra_tc", 1)
+        eng.set_option("overlap", 0)
+        eng.set_option("lanes", lanes)
+        eng.set_option("post_res", res)
+        outs[res] = (eng.run_pcm_host(pcm), eng.debug_tensor("xd", B), eng.debug_tensor("xe", B), eng.state_export(B - 1))
+        eng.close()
+    for a, b in zip(outs[1], outs[0]):
+        assert np.array_equal(a, b)
+    ora = _oracle(name, 9, min(B, 8))
+    ref = np.concatenate([ora.step_pcm(pcm[:8, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    assert np.abs(outs[1][0][:8] - ref).max() < WAVE_TOL
+
+
 @pytest.mark.parametrize("intra_tc", [0, 1])
 def test_lanes_match_single_chain(torch_cuda, intra_tc):
     """A batched step split into lanes (row ranges running as forked kernel chains inside one CUDA graph) must give

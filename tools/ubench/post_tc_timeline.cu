@@ -31,7 +31,16 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-#ifdef PT_PAIR     // CTA pairs: clusters of two, even tile count
+#ifdef PT_RES      // persistent form with resident weights: one CTA per SM, stamps of the third tile of the last CTA
+    {
+      static int* ctr = nullptr;
+      if (!ctr) { cudaMalloc(&ctr, 16); cudaMemset(ctr, 0, 16); }
+      p.ctr = ctr; p.ctas_erb = 0; p.tiles1 = 0;
+      const int G = p.tiles0 < 148 ? p.tiles0 : 148;
+      cudaFuncSetAttribute(k_dprnn_post_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_RES_SMEM);
+      k_dprnn_post_res<<<G, TC_NT, POST_RES_SMEM>>>(p);
+    }
+#elif defined(PT_PAIR)     // CTA pairs: clusters of two, even tile count
     {
       p.tiles0 = (p.tiles0 + 1) & ~1;
       cudaLaunchConfig_t cfg{};
