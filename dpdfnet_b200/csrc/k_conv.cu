@@ -19,8 +19,11 @@ struct Conv0Params {
   int fe0, fe_feat, B;
 };
 
-// thread = (b, f, 4 channels): the nine ring taps are read once per thread (broadcast within the 16 threads of a
-// position), weights as float4, one 16-byte store
+// thread = (b, chunk of CH0_L positions, 4 channels): the 9 x 4 weights stay in registers and the three ring rows slide
+// along f, so a position costs three (broadcast) tap loads, 36 FMAs and one 16-byte store; the 16 channel threads of a
+// position write one whole 256-byte row.  (The first form - thread = (b, f, 4 channels), 25 loads per 16-byte store - was
+// load-issue bound: 127 us for the 252 MB it writes at 2048 streams of the 48 kHz model, 3 x the HBM time.)
+constexpr int CH0_L = 8;
 __global__ void __launch_bounds__(256) k_erb_conv0(Conv0Params p) {
   pdl_trigger();
   pdl_wait();
@@ -28,34 +31,51 @@ __global__ void __launch_bounds__(256) k_erb_conv0(Conv0Params p) {
     p.io->t_out = p.io->t_in;
     p.io->t_in = p.io->t_in + 1;
   }
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;      // < 2^32: B * fe0 * 16
-  const unsigned total = (unsigned)p.B * p.fe0 * (C / 4);
+  const int nch = (p.fe0 + CH0_L - 1) / CH0_L;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;      // < 2^32: B * nch * 16
+  const unsigned total = (unsigned)p.B * nch * (C / 4);
   if (idx >= total) return;
   const int c = (idx & 15) * 4;
-  const unsigned bf = idx >> 4;
-  const int f = bf % p.fe0, b = bf / p.fe0;
+  const unsigned bc = idx >> 4;
+  const int ch = bc % nch, b = bc / nch;
+  const int f0 = ch * CH0_L, f1 = min(p.fe0, f0 + CH0_L);
   const int slot = io_slot(p.io, b);
   const int pos = p.st.pos[slot];
   const float* ring = p.st.erb_ring + (size_t)slot * 3 * p.fe_feat;
-  float4 acc = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+  const float* rowp[3] = {ring + ((pos + 1) % 3) * p.fe_feat, ring + ((pos + 2) % 3) * p.fe_feat, ring + (pos % 3) * p.fe_feat};
+  float4 w[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(p.w + i * C + c));
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+  float xm[3], x0[3], xp[3];                      // taps at f - 1, f, f + 1 of the three frames
 #pragma unroll
   for (int kt = 0; kt < 3; ++kt) {
-    const float* row = ring + ((pos + 1 + kt) % 3) * p.fe_feat;
-#pragma unroll
-    for (int kf = 0; kf < 3; ++kf) {
-      const int fi = f + kf - 1;
-      const float x = (fi >= 0 && fi < p.fe0) ? row[fi] : 0.f;
-      const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (kt * 3 + kf) * C + c));
-      acc.x = fmaf(w.x, x, acc.x); acc.y = fmaf(w.y, x, acc.y); acc.z = fmaf(w.z, x, acc.z); acc.w = fmaf(w.w, x, acc.w);
-    }
+    xm[kt] = f0 > 0 ? rowp[kt][f0 - 1] : 0.f;
+    x0[kt] = rowp[kt][f0];
   }
-  *reinterpret_cast<float4*>(p.e0 + (size_t)bf * C + c) =
-      make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+  float* out = p.e0 + ((size_t)b * p.fe0 + f0) * C + c;
+  for (int f = f0; f < f1; ++f, out += C) {
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) xp[kt] = f + 1 < p.fe0 ? rowp[kt][f + 1] : 0.f;
+    float4 acc = bias;
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      const float x[3] = {xm[kt], x0[kt], xp[kt]};
+#pragma unroll
+      for (int kf = 0; kf < 3; ++kf) {
+        const float4 ww = w[kt * 3 + kf];
+        acc.x = fmaf(ww.x, x[kf], acc.x); acc.y = fmaf(ww.y, x[kf], acc.y); acc.z = fmaf(ww.z, x[kf], acc.z); acc.w = fmaf(ww.w, x[kf], acc.w);
+      }
+      xm[kt] = x0[kt];
+      x0[kt] = xp[kt];
+    }
+    *reinterpret_cast<float4*>(out) = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+  }
 }
 
 void launch_erb_conv0(Engine& e, int B, cudaStream_t st) {
   Conv0Params p{e.io_dev, e.st, e.w.erb_conv0_w, e.w.erb_conv0_b, e.sc.e0, e.d.fe[0], e.d.fe_feat, B};
-  const long long total = (long long)B * e.d.fe[0] * (C / 4);
+  const long long total = (long long)B * ((e.d.fe[0] + CH0_L - 1) / CH0_L) * (C / 4);
   launch_k(e, k_erb_conv0, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
 }
 
@@ -220,38 +240,64 @@ struct Conv0OutParams {
   int fe0, B;
 };
 
-__global__ void __launch_bounds__(256) k_conv0_out(Conv0OutParams p) {
+// warp = (b, chunk of `chunk` positions), lane = 2 channels.  u[f] = relu(e0[f] * a + pb) + d1[f] of a row is formed once
+// and slides through the three taps, four positions per round (eight 8-byte loads in flight per lane), and the four
+// lane-partial sums of a round are reduced together with 6 shuffles instead of 20.  (The first form - one warp per
+// position, three rows of e0 and d1 re-read per output - took 187 us for the 504 MB it reads at 2048 streams of the
+// 48 kHz model, 2.4 x the HBM time.)
+__global__ void __launch_bounds__(256) k_conv0_out(Conv0OutParams p, int chunk, int nch) {
   pdl_trigger();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= p.B * p.fe0) return;
-  const int b = warp / p.fe0, f = warp % p.fe0;
+  if (warp >= p.B * nch) return;
+  const int b = warp / nch, f0 = (warp % nch) * chunk, f1 = min(p.fe0, f0 + chunk);
   const float2 a = __ldg(reinterpret_cast<const float2*>(p.pa) + lane);
   const float2 pb = __ldg(reinterpret_cast<const float2*>(p.pb) + lane);
-  float acc = 0.f;
+  const float2 w0 = __ldg(reinterpret_cast<const float2*>(p.w) + lane), w1 = __ldg(reinterpret_cast<const float2*>(p.w + C) + lane),
+               w2 = __ldg(reinterpret_cast<const float2*>(p.w + 2 * C) + lane);
+  const float bias = __ldg(p.bias);
+  const float2* e0 = reinterpret_cast<const float2*>(p.e0 + (size_t)b * p.fe0 * C) + lane;
+  const float2* d1 = reinterpret_cast<const float2*>(p.d1 + (size_t)b * p.fe0 * C) + lane;
+  auto urow = [&](int fi) -> float2 {                       // zero outside [0, fe0): the conv's zero padding
+    if (fi < 0 || fi >= p.fe0) return make_float2(0.f, 0.f);
+    const float2 e = __ldg(e0 + (size_t)fi * (C / 2)), d = __ldg(d1 + (size_t)fi * (C / 2));
+    return make_float2(fmaxf(fmaf(e.x, a.x, pb.x), 0.f) + d.x, fmaxf(fmaf(e.y, a.y, pb.y), 0.f) + d.y);
+  };
+  auto dot = [&](const float2& um, const float2& u0, const float2& up) {
+    float acc = w0.x * um.x;
+    acc = fmaf(w0.y, um.y, acc);
+    acc = fmaf(w1.x, u0.x, acc); acc = fmaf(w1.y, u0.y, acc);
+    acc = fmaf(w2.x, up.x, acc); acc = fmaf(w2.y, up.y, acc);
+    return acc;
+  };
+  float2 um = urow(f0 - 1), u0 = urow(f0);
+  for (int f = f0; f < f1; f += 4) {
+    float2 u[4];
 #pragma unroll
-  for (int t = 0; t < 3; ++t) {
-    const int fi = f + t - 1;
-    if (fi < 0 || fi >= p.fe0) continue;
-    const size_t off = ((size_t)b * p.fe0 + fi) * C;
-    const float2 e = __ldg(reinterpret_cast<const float2*>(p.e0 + off) + lane);
-    const float2 d = __ldg(reinterpret_cast<const float2*>(p.d1 + off) + lane);
-    const float2 w = __ldg(reinterpret_cast<const float2*>(p.w + t * C) + lane);
-    const float u0 = fmaxf(fmaf(e.x, a.x, pb.x), 0.f) + d.x;
-    const float u1 = fmaxf(fmaf(e.y, a.y, pb.y), 0.f) + d.y;
-    acc = fmaf(w.x, u0, acc);
-    acc = fmaf(w.y, u1, acc);
+    for (int j = 0; j < 4; ++j) u[j] = urow(f + 1 + j);     // rows past f1 are only read for the halo of position f1 - 1
+    float s0 = dot(um, u0, u[0]), s1 = dot(u0, u[0], u[1]), s2 = dot(u[0], u[1], u[2]), s3 = dot(u[1], u[2], u[3]);
+    um = u[2];
+    u0 = u[3];
+    // four sums over the 32 lanes at once: halve the values twice, then reduce the remaining one over 8 lanes
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    const float k0 = hi16 ? s2 : s0, k1 = hi16 ? s3 : s1, g0 = hi16 ? s0 : s2, g1 = hi16 ? s1 : s3;
+    const float t0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 16), t1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 16);   // lanes < 16: positions 0, 1; others 2, 3
+    float r = (hi8 ? t1 : t0) + __shfl_xor_sync(0xffffffffu, hi8 ? t0 : t1, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    const int j = (hi16 ? 2 : 0) + (hi8 ? 1 : 0);           // the position this lane's sum belongs to
+    if ((lane & 7) == 0 && f + j < f1) p.m[(size_t)b * p.fe0 + f + j] = sigmoidf_(r + bias);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) p.m[(size_t)b * p.fe0 + f] = sigmoidf_(acc + __ldg(p.bias));
 }
 
 void launch_conv0_out(Engine& e, int B, cudaStream_t st) {
   Conv0OutParams p{e.sc.e0, e.sc.d1, e.w.convp_a[3], e.w.convp_b[3], e.w.conv0_out_w, e.w.conv0_out_b, e.sc.m, e.d.fe[0], B};
-  const long long warps = (long long)B * e.d.fe[0];
-  launch_k(e, k_conv0_out, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, p);
+  const int nch = (e.d.fe[0] + 31) / 32, chunk = ((e.d.fe[0] + nch - 1) / nch + 3) & ~3;      // <= 32 positions per warp, a multiple of 4
+  const int nch2 = (e.d.fe[0] + chunk - 1) / chunk;
+  const long long warps = (long long)B * nch2;
+  launch_k(e, k_conv0_out, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, p, chunk, nch2);
 }
 
 // ---------------------------------------------------------------------------------------------

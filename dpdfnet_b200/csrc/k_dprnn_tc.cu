@@ -133,6 +133,42 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     rbase = (long long)stile * 128 * T + fpos;
     rstride = T;
     valid = k < T ? min(128, p.B - stile * 128) : 0;       // k == T: the padding tile of an odd tile count
+  } else {
+    bi = (int)blockIdx.x >= p.tiles0 ? 1 : 0;
+    rbase = (long long)(blockIdx.x - (bi ? p.tiles0 : 0)) * 128;
+    rstride = 1;
+    valid = (int)max(0ll, min((long long)128, (long long)p.B * p.br[bi].Fp - rbase));   // 0: padding tile (PAIR)
+  }
+  const PostTcBranch& q = p.br[bi];
+
+  // ---- weight slab ring (thread 0 only) --------------------------------------------------------------------
+  auto slab_src = [&](int i) -> const unsigned char* {
+    if (i < 2) return reinterpret_cast<const unsigned char*>(q.tc_fc_w) + (size_t)i * WSLAB;
+    if (i == 8) return reinterpret_cast<const unsigned char*>(q.tc_fc2_w);
+    const int pidx = i - 2;                                // processing order r(y),r(h),z(y),z(h),n(y),n(h)
+    return reinterpret_cast<const unsigned char*>(q.tc_gates) + (size_t)((pidx & 1) ? 3 + (pidx >> 1) : (pidx >> 1)) * WSLAB;
+  };
+  auto load_slab = [&](int i) {
+    const int buf = i % NBUF;
+    if (i >= NBUF) mbar_wait(bars + BAR_CONS + buf, (i / NBUF - 1) & 1);      // MMAs of the previous tenant have completed
+    mbar_expect_tx(bars + BAR_FULL + buf, SLAB_B);
+    if constexpr (PAIR) {                                  // rows [32 rank, 32 rank + 32) of the hi and of the lo image: 4 KB each
+      bulk_g2s(RW + buf * SLAB_B, slab_src(i) + rank * (WSLAB / 4), WSLAB / 4, bars + BAR_FULL + buf);
+      bulk_g2s(RW + buf * SLAB_B + WSLAB / 4, slab_src(i) + WSLAB / 2 + rank * (WSLAB / 4), WSLAB / 4, bars + BAR_FULL + buf);
+    } else {
+      bulk_g2s(RW + buf * SLAB_B, slab_src(i), WSLAB, bars + BAR_FULL + buf);
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NBARS; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the first slabs do not depend on the sweep: in overlapped mode they land while this CTA waits for its rows
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) load_slab(i);
+  }
+  if (p.progress) {
+    const int stile = ((int)blockIdx.x - (bi ? 0 : p.tiles1)) % p.stiles, T = q.Fp;
     if (tid == 0 && valid > 0) {
       // the sweep CTAs this tile's 128 streams come from: dup per direction (branch index as in the intra kernel: 0 = df, 1 = erb)
       const int dup = bi ? 1 : p.dup, pt = bi ? p.stiles : p.ptiles;
@@ -157,13 +193,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
       }
       __threadfence();                                     // acquire: the rows those counts cover are visible (loads below bypass L1)
     }
-  } else {
-    bi = (int)blockIdx.x >= p.tiles0 ? 1 : 0;
-    rbase = (long long)(blockIdx.x - (bi ? p.tiles0 : 0)) * 128;
-    rstride = 1;
-    valid = (int)max(0ll, min((long long)128, (long long)p.B * p.br[bi].Fp - rbase));   // 0: padding tile (PAIR)
   }
-  const PostTcBranch& q = p.br[bi];
 
   // Warm L2 for the CTA that will take this CTA's place: its hcat tile (64 KB) and block input (32 KB) are contiguous,
   // its 128 inter-GRU state rows are scattered over the slot arena.  At throughput batch sizes none of them is L2
@@ -208,11 +238,6 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     sp[448 + tid] = q.fc2_b[tid]; sp[512 + tid] = q.ln2_g[tid]; sp[576 + tid] = q.ln2_b[tid];
   }
   if (tid < 256) sp[192 + tid] = q.bias[tid];
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < NBARS; ++i) mbar_init(bars + i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   if constexpr (PAIR) {
     cluster_sync_all();                                  // both CTAs' barriers exist before either signals across; s_hoff visible
     if (warp == 0) tmem_alloc_2cta<256>(tmem_slot);
@@ -224,33 +249,16 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     __syncthreads();                                     // barriers initialised, s_hoff visible
     if (s_abort) {                                       // the sweep never delivered this tile's rows: skip it (see above)
       tc_fence_after();
+      if (tid == 0) {                                      // ... once the slab copies already in flight have landed
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i) mbar_wait(bars + BAR_FULL + i, 0);
+      }
+      __syncthreads();
       if (warp == 0) tmem_dealloc<256>(*tmem_slot);
       return;
     }
   }
 
-  // ---- weight slab ring (thread 0 only) --------------------------------------------------------------------
-  auto slab_src = [&](int i) -> const unsigned char* {
-    if (i < 2) return reinterpret_cast<const unsigned char*>(q.tc_fc_w) + (size_t)i * WSLAB;
-    if (i == 8) return reinterpret_cast<const unsigned char*>(q.tc_fc2_w);
-    const int pidx = i - 2;                                // processing order r(y),r(h),z(y),z(h),n(y),n(h)
-    return reinterpret_cast<const unsigned char*>(q.tc_gates) + (size_t)((pidx & 1) ? 3 + (pidx >> 1) : (pidx >> 1)) * WSLAB;
-  };
-  auto load_slab = [&](int i) {
-    const int buf = i % NBUF;
-    if (i >= NBUF) mbar_wait(bars + BAR_CONS + buf, (i / NBUF - 1) & 1);      // MMAs of the previous tenant have completed
-    mbar_expect_tx(bars + BAR_FULL + buf, SLAB_B);
-    if constexpr (PAIR) {                                  // rows [32 rank, 32 rank + 32) of the hi and of the lo image: 4 KB each
-      bulk_g2s(RW + buf * SLAB_B, slab_src(i) + rank * (WSLAB / 4), WSLAB / 4, bars + BAR_FULL + buf);
-      bulk_g2s(RW + buf * SLAB_B + WSLAB / 4, slab_src(i) + WSLAB / 2 + rank * (WSLAB / 4), WSLAB / 4, bars + BAR_FULL + buf);
-    } else {
-      bulk_g2s(RW + buf * SLAB_B, slab_src(i), WSLAB, bars + BAR_FULL + buf);
-    }
-  };
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < NBUF; ++i) load_slab(i);
-  }
   PTL(0);
 
   // ---- stage the hcat tile as two K=64 operand image pairs (split on the fly) --------------------------------
