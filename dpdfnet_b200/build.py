@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libdpdfnet_b200.so"
-SOURCES = ["api.cu", "k_frontend.cu", "k_conv.cu", "k_dprnn.cu", "k_dprnn_tc.cu", "k_dprnn_intra_tc.cu", "k_conv_tc.cu", "k_conv_tma.cu", "k_gru_tc.cu", "k_dense.cu", "k_resample.cu"]
+SOURCES = ["api.cu", "k_frontend.cu", "k_conv.cu", "k_dprnn.cu", "k_dprnn_tc.cu", "k_dprnn_intra_tc.cu", "k_conv_tc.cu", "k_conv_tma.cu", "k_gru_tc.cu", "k_dft_tc.cu", "k_dense.cu", "k_resample.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

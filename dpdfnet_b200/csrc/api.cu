@@ -90,6 +90,19 @@ static int bind_weights(Engine& e) {
   Weights& w = e.w;
   w.dft_fwd = W("const.dft_fwd", (size_t)d.win * d.F * 2);
   w.dft_inv = W("const.dft_inv", (size_t)d.win * d.F * 2);
+  {
+    // optional (blobs packed before the tensor-core DFT existed lack them): without them the FFMA2 DFT stays
+    const size_t ncol = (size_t)(2 * d.F + 127) / 128 * 128, kpad = (size_t)(2 * d.F + 63) / 64 * 64;
+    auto itf = e.wtable.find("const.dft_fwd_tc"), iti = e.wtable.find("const.dft_inv_tc"), its = e.wtable.find("const.dft_tc_scale");
+    const bool ok = itf != e.wtable.end() && iti != e.wtable.end() && its != e.wtable.end() && its->second.second == 4 && itf->second.second == ncol * d.win &&
+                    iti->second.second == (size_t)(d.hop / 80) * (kpad / 64) * 160 * 64 && d.hop % 80 == 0 && d.win % 64 == 0 && d.win <= 1024;
+    w.dft_fwd_tc = ok ? e.weights_dev + itf->second.first : nullptr;
+    w.dft_inv_tc = ok ? e.weights_dev + iti->second.first : nullptr;
+    w.dft_tc_scale = ok ? e.weights_dev + its->second.first : nullptr;
+    e.spec_tc_ld = (int)ncol;
+    e.yspec_tc_ld = (int)kpad;
+    if (!ok) e.dft_tc = 0;
+  }
   w.mu0 = W("const.mu0", d.fe_feat);
   w.s0 = W("const.s0", NDF);
   w.erb_conv0_w = W("enc.erb_conv0.w", 9 * C);
@@ -275,6 +288,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
     add(c.x1, H); add(c.herb1, H); add(c.herb2, H); add(c.ed, 512); add(c.ed2, (size_t)d.fe[3] * C);
     add(c.x2, H); add(c.hdf1, H); add(c.hdf2, H); add(c.cc, H); add(c.co, NDF * 2 * ORD);
     add(c.d3, (size_t)d.fe[2] * C); add(c.d2, (size_t)d.fe[1] * C); add(c.d1, (size_t)d.fe[0] * C); add(c.m, d.fe[0]);
+    add(c.spec_tc, (size_t)e.spec_tc_ld); add(c.yspec_tc, (size_t)e.yspec_tc_ld);
     size_t total = 0;
     for (auto& it : items) total += (it.second * sizeof(float) + 255) / 256 * 256;
     total += (Bm * sizeof(int) + 255) / 256 * 256;
@@ -318,6 +332,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
   init_dense_kernels();
   init_dprnn_tc_kernels();
   init_dprnn_intra_tc_kernels();
+  init_dft_tc_kernels();
   init_conv_tc_kernels();
   init_conv_tma_kernels();
   init_gru_tc_kernels();
@@ -400,6 +415,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     if (use_gru_tc) launch_gru_tc(en, probs, nprob, Bn, s_);
     else launch_gru(en, probs, nprob, Bn, s_);
   };
+  if (dft_on_tc(e, B)) { RUN("dft_tc", launch_dft_tc(e, B, st)); ++n; }
   RUN("analysis", launch_analysis(e, B, st)); ++n;
   e.pdl_first = false;
   RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
@@ -535,6 +551,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   RUN("conv0_out", launch_conv0_out(e, B, st)); ++n;
   if (fork) cudaStreamWaitEvent(st, e.br_join[e.cur_lane], 0);
   RUN("synthesis", launch_synthesis(e, B, st)); ++n;
+  if (dft_on_tc(e, B)) { RUN("dft_tc", launch_idft_tc(e, B, st)); ++n; }
   e.pdl_now = false;
   e.launches = n;
 }
@@ -1170,6 +1187,15 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
       e.intra_tc = value;
     } else {
       e.intra_tc_min = value;
+    }
+    drop_graphs(e);
+  } else if (strcmp(key, "dft_tc") == 0 || strcmp(key, "dft_tc_min") == 0) {
+    if (key[6] == 0) {
+      if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "dft_tc must be 0 (FFMA2), 1 (tcgen05) or 2 (by batch size)");
+      if (value && !e.w.dft_fwd_tc) return fail(DPDF_ERR_INVALID, "the weight blob has no tensor-core DFT images (const.dft_fwd_tc / const.dft_inv_tc)");
+      e.dft_tc = value;
+    } else {
+      e.dft_tc_min = value;
     }
     drop_graphs(e);
   } else if (strcmp(key, "post_res") == 0) {

@@ -51,6 +51,7 @@ struct Scratch {         // all [max_streams][...]
   float *x1, *herb1, *herb2, *ed, *ed2;
   float *x2, *hdf1, *hdf2, *cc, *co;
   float *d3, *d2, *d1, *m;
+  float *spec_tc, *yspec_tc;      // k_dft_tc: spectrum of the hop [spec_tc_ld], masked / filtered spectrum Y [yspec_tc_ld] (zero padded)
 };
 
 struct SepW { const float *dw, *pw, *b, *tc_pw; };     // tc_pw: FP16 hi/lo tcgen05 image of pw (weights.py:umma_operand16)
@@ -66,6 +67,8 @@ struct DprnnW {
 
 struct Weights {
   const float *dft_fwd, *dft_inv, *mu0, *s0;
+  const float* dft_tc_scale;                 // [4] power-of-two (in, out) scales of the analysis and of the synthesis GEMM
+  const float *dft_fwd_tc, *dft_inv_tc;      // FP16 hi | lo operand images of the two bases (weights.py:dft_tc_images), or nullptr (older blobs)
   const float *erb_conv0_w, *erb_conv0_b;
   SepW erb_conv[3], df_conv1, convt[3];
   const float *df_conv0_w, *df_conv0_pw, *df_conv0_b, *df_conv0_tc_pw;
@@ -85,6 +88,10 @@ struct Engine;
 
 void launch_prime(Engine& e, const float* pcm, long long stride, const int* slot_ids, int B, cudaStream_t st);
 void launch_analysis(Engine& e, int B, cudaStream_t st);
+bool dft_on_tc(const Engine& e, int B);
+void launch_dft_tc(Engine& e, int B, cudaStream_t st);     // before launch_analysis when dft_on_tc
+void launch_idft_tc(Engine& e, int B, cudaStream_t st);    // after launch_synthesis when dft_on_tc
+void init_dft_tc_kernels();
 void launch_synthesis(Engine& e, int B, cudaStream_t st);
 void launch_reset(Engine& e, const int* slots_dev, int n, cudaStream_t st);
 
@@ -194,6 +201,9 @@ struct Engine {
   int intra_dup = 0;              // k_dprnn_intra_tc row duplication D (128 / D streams per CTA): 0 = auto (largest D whose sweep fits one wave), 1, 2, 4
   int gru_tc = 2;                 // GRUCell(256) gate GEMMs on tcgen05: 0 never, 1 always, 2 = when B >= gru_tc_min
   int gru_tc_min = 256;
+  int dft_tc = 2;                 // framed DFT / inverse DFT + OLA on tcgen05 (k_dft_tc.cu): 0 never, 1 always, 2 = when B >= dft_tc_min
+  int dft_tc_min = 512;
+  int spec_tc_ld = 0, yspec_tc_ld = 0;       // floats per stream of the two scratch rows
   int gru_uc = 0;                 // k_gru_tc hidden units per CTA: 0 = auto (32 while the doubled grid fits one wave), 32, 64
   int sep_tc = 2;                 // separable convs with the pointwise GEMM on tcgen05: 0 never, 1 always, 2 = when B >= sep_tc_min
   int sep_tc_min = 256;

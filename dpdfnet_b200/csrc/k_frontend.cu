@@ -21,6 +21,8 @@ struct AnaParams {
   const float* band_inv_w;   // [32]
   const int* band_start;     // [33]
   int B;
+  const float* pre_spec;     // spectrum of this hop from k_dft_tc ([B][pre_ld] floats, interleaved re / im, wnorm applied), or nullptr
+  int pre_ld;
 };
 
 // One CTA = NB streams, thread = frequency bin.  The windowed DFT is a [NB x win] x [win x F] product whose (cos, sin)
@@ -62,7 +64,28 @@ __global__ void __launch_bounds__(MAXT) k_analysis(AnaParams p, int ksplit) {
 #pragma unroll
   for (int q = 0; q < NB / 2; ++q) Xr[q] = Xi[q] = make_float2(0.f, 0.f);
 
-  if (pcm_mode) {
+  if (pcm_mode && p.pre_spec) {
+    // the DFT of this hop came from the tensor cores (k_dft_tc.cu): only the history update is left of the PCM side
+    const long long toff = (long long)io->t_in * hop;
+    const bool vec = ((io->in_stride | toff) & 3) == 0 && (reinterpret_cast<size_t>(io->in) & 15) == 0;
+    for (int i = tid; i < NB * (hop / 4); i += NT) {
+      const int bb = i / (hop / 4), n = (i % (hop / 4)) * 4;
+      if (bb < nb) {
+        const float* src = io->in + (size_t)(b0 + bb) * io->in_stride + toff + n;
+        const float4 v = vec ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+        *reinterpret_cast<float4*>(p.st.in_hist + (size_t)s_slot[bb] * hop + n) = v;
+      }
+    }
+    if (tid < F) {
+#pragma unroll
+      for (int bb = 0; bb < NB; ++bb) {
+        if (bb >= nb) break;
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p.pre_spec + (size_t)(b0 + bb) * p.pre_ld) + tid);
+        if (bb & 1) { Xr[bb / 2].y = v.x; Xi[bb / 2].y = v.y; }
+        else { Xr[bb / 2].x = v.x; Xi[bb / 2].x = v.y; }
+      }
+    }
+  } else if (pcm_mode) {
     const long long toff = (long long)io->t_in * hop;
     const bool vec = ((io->in_stride | toff) & 3) == 0 && (reinterpret_cast<size_t>(io->in) & 15) == 0;
     for (int i = tid; i < NB * (win / 4); i += NT) {              // item = (4 consecutive samples, stream); streams fastest
@@ -199,6 +222,8 @@ struct SynParams {
   const float* m;            // [B][fe0]
   const int* band_of_bin;    // [F]
   int B;
+  float* yout;               // PCM mode: hand Y to k_dft_tc ([B][yld] floats, interleaved re / im) instead of the inverse DFT here, or nullptr
+  int yld;
 };
 
 // One CTA = SB streams.  Prologue: thread = bin (mask, deep filter, spectral rings); inverse DFT: thread = output sample,
@@ -263,9 +288,17 @@ __global__ void __launch_bounds__(MAXT) k_synthesis(SynParams p) {
         if (!pcm_mode)
           reinterpret_cast<float2*>(io->out)[(size_t)b * F + k] = make_float2(Y.x * p.d.inv_wnorm, Y.y * p.d.inv_wnorm);
       }
-      Ys[(k * 2) * SB + bb] = Y.x;
-      Ys[(k * 2 + 1) * SB + bb] = Y.y;
+      if (p.yout) {
+        if (bb < nb && pcm_mode) reinterpret_cast<float2*>(p.yout + (size_t)(b0 + bb) * p.yld)[k] = Y;
+      } else {
+        Ys[(k * 2) * SB + bb] = Y.x;
+        Ys[(k * 2 + 1) * SB + bb] = Y.y;
+      }
     }
+  }
+  if (p.yout) {                                            // inverse DFT + overlap-add follow on the tensor cores (k_dft_tc.cu)
+    if (tid < nb) p.st.pos[s_slot[tid]] = (s_pos[tid] + 1) % 15;
+    return;
   }
   __syncthreads();
 
@@ -377,10 +410,22 @@ static void launch_analysis_t(Engine& e, const AnaParams& p, int B, int ntg, int
   launch_k(e, k_analysis<NB, MAXT>, dim3((B + NB - 1) / NB), dim3(ntg * ksplit), smem, st, p, ksplit);
 }
 
+bool dft_on_tc(const Engine& e, int B) {
+  return e.dft_tc == 1 || (e.dft_tc == 2 && std::max(B, e.total_B) >= e.dft_tc_min);
+}
+
 void launch_analysis(Engine& e, int B, cudaStream_t st) {
-  AnaParams p{e.io_dev, e.d, e.st, e.w.dft_fwd, e.w.band_inv_w, e.w.band_start, B};
+  AnaParams p{e.io_dev, e.d, e.st, e.w.dft_fwd, e.w.band_inv_w, e.w.band_start, B, nullptr, 0};
   const int ntg = (e.d.F + 31) / 32 * 32;
   const int Bt = std::max(B, e.total_B);          // total_B: all lanes of the step
+  if (dft_on_tc(e, B)) {
+    // spectrum from the tensor cores (k_dft_tc; a no-op in spectrum mode): features only, no reason to keep CTAs small
+    p.pre_spec = e.sc.spec_tc;
+    p.pre_ld = e.spec_tc_ld;
+    if ((Bt + 7) / 8 <= 4 * e.num_sms) launch_analysis_t<8, 1024>(e, p, B, ntg, 1, st);
+    else launch_analysis_t<16, 512>(e, p, B, ntg, 1, st);
+    return;
+  }
   // latency bound while 8-stream CTAs leave SMs idle: split the sum over thread groups (5 at 16 kHz, 2 at 48 kHz); above
   // that the basis traffic per stream decides.  Measured (profiles/r2i_sweep.log): 16 streams per CTA wins from 2048
   // streams up at both rates (48 kHz, 2048 streams: 0.33 -> 0.17 ms; 16 kHz, 16384: 0.32 -> 0.25 ms with the synthesis
@@ -400,12 +445,21 @@ void launch_analysis(Engine& e, int B, cudaStream_t st) {
 }
 
 void launch_synthesis(Engine& e, int B, cudaStream_t st) {
-  SynParams p{e.io_dev, e.d, e.st, e.w.dft_inv, e.sc.m, e.w.band_of_bin, B};
+  SynParams p{e.io_dev, e.d, e.st, e.w.dft_inv, e.sc.m, e.w.band_of_bin, B, nullptr, 0};
   const int nt = (e.d.win + 31) / 32 * 32;
   const int Bt = std::max(B, e.total_B);
   auto go = [&](auto kernel, int SB) {
     launch_k(e, kernel, dim3((B + SB - 1) / SB), dim3(nt), (size_t)(2 * e.d.F * SB) * sizeof(float), st, p);
   };
+  if (dft_on_tc(e, B)) {
+    // mask + deep filter only: Y goes to the scratch of k_dft_tc, which does the inverse DFT and the overlap-add
+    p.yout = e.sc.yspec_tc;
+    p.yld = e.yspec_tc_ld;
+    const int ntf = (e.d.F + 31) / 32 * 32;
+    if (ntf > 384) launch_k(e, k_synthesis<4, 16, 1024>, dim3((B + 3) / 4), dim3(ntf), 0, st, p);
+    else launch_k(e, k_synthesis<4, 16, 384>, dim3((B + 3) / 4), dim3(ntf), 0, st, p);
+    return;
+  }
   // 16 kHz: 320 threads per CTA (register budget is not an issue); 48 kHz: 960 threads, 64 registers each
   const int sforce = e.syn_force;
   if (sforce ? sforce == 16 : e.syn_sb >= 64) {

@@ -203,6 +203,49 @@ def dft_bases(spec: ModelSpec) -> Dict[str, np.ndarray]:
             "const.dft_inv": np.stack([inv_c, inv_s], -1)}      # [F, N, 2]
 
 
+DFT_TC_NC = 128      # output columns (re / im interleaved) per CTA of the analysis GEMM
+IDFT_TC_W = 80       # output samples of each frame half per CTA of the synthesis GEMM (NC = 2 * 80)
+
+
+def dft_tc_images(spec: ModelSpec, bases: Mapping[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """FP16 hi | lo tcgen05 operand images of the two DFT bases for k_dft_tc (csrc/k_dft_tc.cu): the framed DFT and the
+    inverse DFT + overlap-add as [128 streams x K] x [K x N] GEMMs.
+
+    Analysis: N = 2F columns (re_0, im_0, re_1, ...), padded with zero rows to a multiple of DFT_TC_NC; K = win in
+    64-wide stages.  Layout [chunk][stage][NC rows x 64 k] (hi image, lo image).
+    Synthesis: K = 2F (re_0, im_0, ...) zero-padded to a multiple of 64; a chunk owns IDFT_TC_W samples n of the first
+    frame half AND the samples n + hop of the second, so one CTA reads the old overlap-add tail, emits the hop and writes
+    the new tail of the same addresses.  Layout [chunk][stage][2 W rows x 64 k].
+
+    Scaling.  The hi / lo split is only FP32-accurate while ``lo`` stays a NORMAL half (|x| above ~1e-4 x 2^11): the
+    analysis basis peaks at wnorm = 1/320 (1/960) and -120 dBFS audio at 1e-6, both deep in the subnormals.  So the
+    basis is stored times a power of two that brings its peak to [0.5, 1), the kernel multiplies PCM (and Y) by 2^13
+    before splitting (full scale stays below the FP16 maximum up to |x| = 8) and the accumulators are scaled back
+    exactly: ``const.dft_tc_scale`` = (in, out) factors of the analysis, then of the synthesis."""
+    N, F, hop = spec.win, spec.freq_bins, spec.hop
+    fwd = np.asarray(bases["const.dft_fwd"], dtype=np.float64).reshape(N, 2 * F)      # [n][2 bin + ri]
+    inv = np.asarray(bases["const.dft_inv"], dtype=np.float64)                         # [bin][n][ri]
+    assert N % 64 == 0 and hop % IDFT_TC_W == 0
+    ncol = -(-2 * F // DFT_TC_NC) * DFT_TC_NC
+    s_in = 2.0 ** 13
+    s_bf = 2.0 ** np.floor(-np.log2(np.abs(fwd).max()))        # peak of the scaled basis in [0.5, 1)
+    s_bi = 2.0 ** np.floor(-np.log2(np.abs(inv).max()))
+    fwd_p = np.zeros((ncol, N), dtype=np.float32)
+    fwd_p[:2 * F] = fwd.T * s_bf
+    out_f = [umma_operand16(np.ascontiguousarray(fwd_p[c:c + DFT_TC_NC, k:k + 64]))
+             for c in range(0, ncol, DFT_TC_NC) for k in range(0, N, 64)]
+    kpad = -(-2 * F // 64) * 64
+    inv_p = np.zeros((N, kpad), dtype=np.float32)                                      # [n][2 bin + ri]
+    inv_p[:, :2 * F] = inv.transpose(1, 0, 2).reshape(N, 2 * F) * s_bi
+    out_i = []
+    for c in range(hop // IDFT_TC_W):
+        rows = np.concatenate([np.arange(c * IDFT_TC_W, (c + 1) * IDFT_TC_W), hop + np.arange(c * IDFT_TC_W, (c + 1) * IDFT_TC_W)])
+        for k in range(0, kpad, 64):
+            out_i.append(umma_operand16(np.ascontiguousarray(inv_p[rows, k:k + 64])))
+    scale = np.array([s_in, 1.0 / (s_in * s_bf), s_in, 1.0 / (s_in * s_bi)], dtype=np.float32)
+    return {"const.dft_fwd_tc": np.concatenate(out_f), "const.dft_inv_tc": np.concatenate(out_i), "const.dft_tc_scale": scale}
+
+
 def norm_init(spec: ModelSpec) -> Tuple[np.ndarray, np.ndarray]:
     """(mu0, s0): ErbNorm/SpecNorm linspace inits (layers.py:460-463, 519-522) or the 48 kHz tables."""
     if spec.hr48:
@@ -230,10 +273,13 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
         if tuple(sd[k].shape) != tuple(shp):
             raise ValueError(f"{k}: expected shape {shp}, got {tuple(sd[k].shape)}")
     t: "OrderedDict[str, np.ndarray]" = OrderedDict()
-    for k, v in dft_bases(spec).items():
+    bases = dft_bases(spec)
+    for k, v in bases.items():
         t[k] = v
     mu0, s0 = norm_init(spec)
     t["const.mu0"], t["const.s0"] = mu0, s0
+    for k, v in dft_tc_images(spec, bases).items():
+        t[k] = v
 
     def sep(prefix_out: str, dw_keys, pw_key: str, bn_prefix: str):
         # depthwise [S][3][C] (tap-major, channel contiguous); pointwise [C_out][C_in] with BN scale folded

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 SPEC_TOL = 2e-4
 WAVE_TOL = 1e-4
 STATE_TOL = 1e-4
-TC_OPTS = ("intra_tc", "post_tc", "sep_tc", "gru_tc")
+TC_OPTS = ("intra_tc", "post_tc", "sep_tc", "gru_tc", "dft_tc")
 
 
 @pytest.fixture(scope="module")

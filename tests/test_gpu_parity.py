@@ -44,7 +44,7 @@ def test_stream_golden(torch_cuda, golden_dir, name, tc):
     """Per-frame ONNX-shaped call with HOST buffers vs the reference streaming model's outputs (both kernel arms)."""
     g = np.load(golden_dir / f"stream_{name}.npz")
     eng = _engine(name, int(g["seed"]), 2)
-    for opt in ("intra_tc", "post_tc", "sep_tc", "gru_tc"):
+    for opt in ("intra_tc", "post_tc", "sep_tc", "gru_tc", "dft_tc"):
         eng.set_option(opt, tc)
     for t in range(g["spec_in"].shape[0]):
         y = eng.step_spec_host(g["spec_in"][t][None], slot_ids=[1])
@@ -67,7 +67,7 @@ def test_offline_golden(torch_cuda, golden_dir, name, tc):
     from dpdfnet_b200.offline import enhance_offline_exact
     g = np.load(golden_dir / f"offline_{name}.npz")
     eng = _engine(name, int(g["seed"]), g["wave_in"].shape[0])
-    for opt in ("intra_tc", "post_tc", "sep_tc", "gru_tc"):
+    for opt in ("intra_tc", "post_tc", "sep_tc", "gru_tc", "dft_tc"):
         eng.set_option(opt, tc)
     out = enhance_offline_exact(eng, g["wave_in"])
     assert out.shape == g["wave_out"].shape
@@ -261,6 +261,47 @@ def test_post_kernel_persistent_with_resident_weights(torch_cuda, name, B, lanes
     for a, b in zip(outs[1], outs[0]):
         assert np.array_equal(a, b)
     ora = _oracle(name, 9, min(B, 8))
+    ref = np.concatenate([ora.step_pcm(pcm[:8, t * hop:(t + 1) * hop]) for t in range(T)], 1)
+    assert np.abs(outs[1][0][:8] - ref).max() < WAVE_TOL
+
+
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 133), ("dpdfnet2_48khz_hr", 70), ("dpdfnet4", 300)])
+def test_dft_on_tensor_cores(torch_cuda, name, B):
+    """k_dft_tc: the framed DFT and the inverse DFT + overlap-add as FP16-split tcgen05 GEMMs over 128-stream tiles
+    (the feature / mask kernels then skip their own transforms).  Against the FFMA2 transforms (1e-5: different summation
+    order only) and the oracle; ragged tiles, slot indirection, graph replay over several hops (history and overlap-add
+    tail carried in state), a strided / unaligned device view, and lanes."""
+    torch = torch_cuda
+    T = 6
+    hop = get_spec(name).hop
+    rng = np.random.default_rng(71)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    slots = rng.permutation(B + 4)[:B].astype(np.int32)
+    outs = {}
+    for tc in (0, 1):
+        eng = _engine(name, 12, B + 4)
+        eng.set_option("dft_tc", tc)
+        a = eng.run_pcm_host(pcm)                                   # identity slots, graph replay over T hops
+        eng.reset()
+        b = np.concatenate([eng.step_pcm_host(pcm[:, t * hop:(t + 1) * hop], slot_ids=slots) for t in range(T)], 1)
+        st = eng.state_export(int(slots[B - 1]))
+        outs[tc] = (a, b, st)
+        if tc:
+            # unaligned rows: a device view with an odd stride and offset goes through the scalar PCM loads
+            eng.reset()
+            buf = torch.zeros(B, T * hop + 3, device="cuda")
+            buf[:, 1:1 + T * hop] = torch.from_numpy(pcm).cuda()
+            y = eng.run_pcm(buf[:, 1:1 + T * hop], out=torch.zeros(B, T * hop + 3, device="cuda")[:, 2:2 + T * hop])
+            torch.cuda.synchronize()
+            assert np.array_equal(y.cpu().numpy(), a)
+            eng.reset()
+            eng.set_option("lanes", 2)
+            assert np.array_equal(eng.run_pcm_host(pcm), a)
+        eng.close()
+    assert np.array_equal(outs[1][0], outs[1][1])                   # slot indirection does not change the arithmetic
+    assert np.abs(outs[1][0] - outs[0][0]).max() < 1e-5
+    assert np.abs(outs[1][2] - outs[0][2]).max() < 1e-5 * max(1.0, float(np.abs(outs[0][2]).max()))   # mu is in dB: |state| up to 90
+    ora = _oracle(name, 12, 8)
     ref = np.concatenate([ora.step_pcm(pcm[:8, t * hop:(t + 1) * hop]) for t in range(T)], 1)
     assert np.abs(outs[1][0][:8] - ref).max() < WAVE_TOL
 

@@ -28,7 +28,7 @@ def test_engine_stream_matches_reference_stream_enhancer(name, arm):
     B = 3
     eng = Engine(spec, ck, max_streams=B)
     if arm == "tcgen05":
-        for k in ("intra_tc", "post_tc", "sep_tc", "gru_tc"):
+        for k in ("intra_tc", "post_tc", "sep_tc", "gru_tc", "dft_tc"):
             eng.set_option(k, 1)
     pcm = np.tile(x[None], (B, 1))
     pcm[1] *= 0.5                                                  # the neighbours carry different signals

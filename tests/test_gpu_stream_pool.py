@@ -160,7 +160,7 @@ def test_device_raised_errors_surface_through_the_abi(random_weights):
     """A non-finite activation in a tensor-core operand converter must fail the hop, not poison the stream silently."""
     from dpdfnet_b200.engine import Engine
     eng = Engine("dpdfnet2", None, max_streams=4)
-    for k in ("intra_tc", "post_tc", "sep_tc", "gru_tc"):
+    for k in ("intra_tc", "post_tc", "sep_tc", "gru_tc", "dft_tc"):
         eng.set_option(k, 1)
     x = np.zeros((4, 160 * 3), np.float32)
     eng.run_pcm_host(x)                                   # digital silence is fine
