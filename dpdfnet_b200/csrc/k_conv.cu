@@ -294,7 +294,10 @@ __global__ void __launch_bounds__(256) k_conv0_out(Conv0OutParams p, int chunk, 
 
 void launch_conv0_out(Engine& e, int B, cudaStream_t st) {
   Conv0OutParams p{e.sc.e0, e.sc.d1, e.w.convp_a[3], e.w.convp_b[3], e.w.conv0_out_w, e.w.conv0_out_b, e.sc.m, e.d.fe[0], B};
-  const int nch = (e.d.fe[0] + 31) / 32, chunk = ((e.d.fe[0] + nch - 1) / nch + 3) & ~3;      // <= 32 positions per warp, a multiple of 4
+  // positions per warp, a multiple of 4: up to 32 (6 % halo rows) once the grid is large, 8 for small grids, where one
+  // warp walking all 32 bands of a stream is a 23 us serial chain at 1024 streams (13 us with 8)
+  const int cap = (long long)B * e.d.fe[0] >= (1 << 18) ? 32 : 8;
+  const int nch = (e.d.fe[0] + cap - 1) / cap, chunk = ((e.d.fe[0] + nch - 1) / nch + 3) & ~3;
   const int nch2 = (e.d.fe[0] + chunk - 1) / chunk;
   const long long warps = (long long)B * nch2;
   launch_k(e, k_conv0_out, dim3((unsigned)((warps * 32 + 255) / 256)), dim3(256), 0, st, p, chunk, nch2);
