@@ -323,6 +323,8 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
         cudaStreamCreateWithFlags(&e.br_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.br_fork[l], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.br_join[l], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.enc_fork[l], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.enc_join[l], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.lane_done[l], cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(DPDF_ERR_CUDA, "lane stream creation failed"));
   if (cudaEventCreateWithFlags(&e.lane_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "event creation failed"));
@@ -356,6 +358,8 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
     if (e.br_stream[l]) cudaStreamDestroy(e.br_stream[l]);
     if (e.br_fork[l]) cudaEventDestroy(e.br_fork[l]);
     if (e.br_join[l]) cudaEventDestroy(e.br_join[l]);
+    if (e.enc_fork[l]) cudaEventDestroy(e.enc_fork[l]);
+    if (e.enc_join[l]) cudaEventDestroy(e.enc_join[l]);
     if (e.lane_done[l]) cudaEventDestroy(e.lane_done[l]);
   }
   if (e.lane_fork) cudaEventDestroy(e.lane_fork);
@@ -383,7 +387,8 @@ namespace dpdf {
 
 #define RUN(name, call)                                           \
   do {                                                            \
-    if (e.timing) {                                               \
+    if (e.stop_after > 0 && e.run_idx++ >= e.stop_after) {        \
+    } else if (e.timing) {                                        \
       cudaEvent_t ev0, ev1;                                       \
       cudaEventCreate(&ev0); cudaEventCreate(&ev1);               \
       cudaEventRecord(ev0, st);                                   \
@@ -401,6 +406,7 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   const Weights& w = e.w;
   Scratch& c = e.sc;
   int n = 0;
+  e.run_idx = 0;
   const bool seg_pdl = e.pdl == 2 && !e.timing;            // PDL chains everywhere but across the DPRNN stack
   e.pdl_now = e.pdl && !e.timing;
   e.pdl_first = true;                                      // the analysis kernel follows a copy / an event, not a kernel
@@ -418,7 +424,6 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
   if (dft_on_tc(e, B)) { RUN("dft_tc", launch_dft_tc(e, B, st)); ++n; }
   RUN("analysis", launch_analysis(e, B, st)); ++n;
   e.pdl_first = false;
-  RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
   auto sepp = [&](const SepW& sw, const float* in1, const float* in2, int pidx, float* out, int Fin, int Fout, int stride, int up) {
     SepProblem q{};
     q.mode = 0; q.in1 = in1; q.in2 = in2;
@@ -426,16 +431,41 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     q.dw = sw.dw; q.pw = sw.pw; q.tc_pw = sw.tc_pw; q.bias = sw.b; q.out = out; q.Fin = Fin; q.Fout = Fout; q.stride = stride; q.up = up;
     return q;
   };
-  {
+  SepProblem dfc0{};
+  dfc0.mode = 1; dfc0.dw = w.df_conv0_w; dfc0.pw = w.df_conv0_pw; dfc0.tc_pw = w.df_conv0_tc_pw; dfc0.bias = w.df_conv0_b;
+  dfc0.Fin = NDF; dfc0.Fout = NDF; dfc0.stride = 1; dfc0.up = 1; dfc0.out = c.c0;
+  if (e.encoder_fork) {
+    // The two encoder branches share nothing between the analysis kernel and the DPRNN stack: the df chain (df_conv0 ->
+    // df_conv1, the bigger problems) runs on a forked stream beside erb_conv0 -> erb_conv1..3.  In the real chain of a
+    // 1024-stream hop the three merged launches added 41 + 22 + 10 us after erb_conv0 (profiles/r2L_chain_B1024.txt),
+    // of which the erb problems need a fraction each.
+    cudaStream_t sd = st;
+    const bool fork = !e.timing;
+    if (fork) {
+      cudaEventRecord(e.enc_fork[e.cur_lane], st);
+      sd = e.br_stream[e.cur_lane];
+      cudaStreamWaitEvent(sd, e.enc_fork[e.cur_lane], 0);
+      e.pdl_first = true;                                    // first kernel of the forked chain: its predecessor is an event
+    }
+    RUN("sepconv", sepconv(e, &dfc0, 1, B, sd)); ++n;
+    e.pdl_first = false;
+    SepProblem q = sepp(w.df_conv1, c.c0, nullptr, 0, c.c1, NDF, NDF / 2, 2, 1);
+    RUN("sepconv", sepconv(e, &q, 1, B, sd)); ++n;
+    if (fork) cudaEventRecord(e.enc_join[e.cur_lane], sd);
+    RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
+    for (int i = 0; i < 3; ++i) {
+      const float* in = i == 0 ? c.e0 : (i == 1 ? c.e1 : c.e2);
+      float* out = i == 0 ? c.e1 : (i == 1 ? c.e2 : c.e3);
+      q = sepp(w.erb_conv[i], in, nullptr, 0, out, d.fe[i], d.fe[i + 1], d.stride[i], 1);
+      RUN("sepconv", sepconv(e, &q, 1, B, st)); ++n;
+    }
+    if (fork) cudaStreamWaitEvent(st, e.enc_join[e.cur_lane], 0);
+  } else {
+    RUN("erb_conv0", launch_erb_conv0(e, B, st)); ++n;
     SepProblem pr[2];
-    pr[0] = SepProblem{};
-    pr[0].mode = 1; pr[0].dw = w.df_conv0_w; pr[0].pw = w.df_conv0_pw; pr[0].tc_pw = w.df_conv0_tc_pw; pr[0].bias = w.df_conv0_b;
-    pr[0].Fin = NDF; pr[0].Fout = NDF; pr[0].stride = 1; pr[0].up = 1; pr[0].out = c.c0;
+    pr[0] = dfc0;
     pr[1] = sepp(w.erb_conv[0], c.e0, nullptr, 0, c.e1, d.fe[0], d.fe[1], d.stride[0], 1);
     RUN("sepconv", sepconv(e, pr, 2, B, st)); ++n;
-  }
-  {
-    SepProblem pr[2];
     pr[0] = sepp(w.df_conv1, c.c0, nullptr, 0, c.c1, NDF, NDF / 2, 2, 1);
     pr[1] = sepp(w.erb_conv[1], c.e1, nullptr, 0, c.e2, d.fe[1], d.fe[2], d.stride[1], 1);
     RUN("sepconv", sepconv(e, pr, 2, B, st)); ++n;
@@ -520,16 +550,18 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     cudaStreamWaitEvent(sb, e.br_fork[e.cur_lane], 0);
   }
   {
-    // the new GRU states are committed to the slot arena on the forked chain as well: nothing reads them before the next
-    // hop, and the coefficient tail is the shorter of the two (13 us off the critical path of a 1024-stream hop)
+    // The new GRU states are committed to the slot arena beside the decoder tails: nothing reads them before the next hop.
+    // In the real chain of a 1024-stream hop (tools/chain_profile.py, profiles/r2L_chain_B1024.txt) the coefficient tail
+    // - df_out linear 9 us + pathway conv 44 us - is the LONGER of the two (the three transposed convs + conv0_out add
+    // 34 us), so the commit (7 us) rides on the main chain.
     GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc},
                          {c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1},
                          {c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
+    RUN("gru_commit", launch_gru_commit(e, all, 5, B, st)); ++n;
     if (fork) e.pdl_first = true;                            // first kernel of the forked chain: its predecessor is an event, not a kernel
-    RUN("gru_commit", launch_gru_commit(e, all, 5, B, sb)); ++n;
-    e.pdl_first = false;
     GLProblem q = glp(w.df_out, c.cc, H, c.co, NDF * 2 * ORD, 2);
     RUN("gl", launch_gl(e, &q, 1, B, sb)); ++n;
+    e.pdl_first = false;
   }
   if (e.dfp_ps) { RUN("df_pathway", launch_df_pathway_ps(e, B, sb)); }
   else { RUN("df_pathway", launch_df_pathway(e, B, sb)); }
@@ -1197,6 +1229,12 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     } else {
       e.dft_tc_min = value;
     }
+    drop_graphs(e);
+  } else if (strcmp(key, "encoder_fork") == 0) {
+    e.encoder_fork = value ? 1 : 0;
+    drop_graphs(e);
+  } else if (strcmp(key, "stop_after") == 0) {
+    e.stop_after = value;                                    // profiling only (tools/chain_profile.py): the streams' state is garbage afterwards
     drop_graphs(e);
   } else if (strcmp(key, "post_res") == 0) {
     e.post_res = value ? 1 : 0;

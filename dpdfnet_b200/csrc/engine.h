@@ -211,6 +211,7 @@ struct Engine {
   int ana_force = 0, syn_force = 0;   // experiments: force that many streams per CTA regardless of the grid size (0 = auto)
   int ana_nb = 32, syn_sb = 16;   // caps on the streams per CTA of the analysis / synthesis kernels (8|16|32, 4|8|16)
   int post_pf = 1;                // k_dprnn_post_tc: L2 prefetch distance in units of the SM count (2 CTAs per SM -> 2), 0 = off
+  int stop_after = 0, run_idx = 0;   // profiling (tools/chain_profile.py): enqueue only the first stop_after kernels of a hop
   int post_res = 0;               // k_dprnn_post_res (persistent, resident weights) when the post kernel runs after its sweep.  Bit-identical,
                                   // parity-tested, measured on par / slightly slower (profiles/r2E_*: post 2.53 -> 2.58 ms per hop at 16 384
                                   // streams): without weight waits a tile takes 21-26 k cycles, but one CTA per SM overlaps nothing, and two
@@ -229,6 +230,8 @@ struct Engine {
   int decoder_fork = 1;           // run the deep-filter coefficient tail beside the ERB decoder's conv stack (forked stream)
   cudaStream_t br_stream[MAX_LANES] = {};
   cudaEvent_t br_fork[MAX_LANES] = {}, br_join[MAX_LANES] = {};
+  int encoder_fork = 1;           // df encoder chain (df_conv0 -> df_conv1) on the forked stream beside erb_conv0..3
+  cudaEvent_t enc_fork[MAX_LANES] = {}, enc_join[MAX_LANES] = {};
   int dfp_ps = 0;                 // df pathway conv as pending partial sums: 38 KB of accumulator traffic instead of the 120 KB c0 ring
                                   // read per stream-hop, but measured slower (0.48 vs 0.27 ms at 8192 streams: the 50-value
                                   // reduce-scatter and the dependent read-modify-writes cost more than the ring read saves)

@@ -318,81 +318,88 @@ struct DfPathParams {
 template <bool RING16>       // c0 ring stored in half precision (option c0_fp16); a template so that the FP32 path costs nothing
 __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
   pdl_trigger();
-  pdl_wait();
   __shared__ __align__(16) float ws[2 * ORD * 8 * 5 * 4];        // [g][kt][ci/4][o][4]
   __shared__ float pws[100], bs[10];
   const int tid = threadIdx.x, lane = tid & 31;
+  // The 6.8 KB of weights are staged ONCE per CTA (before the grid dependency resolves) and the CTA then walks its share
+  // of the (stream, 4-bin) items: with one item per warp every one of the 3072 CTAs of a 1024-stream hop paid the staging
+  // and its barrier before its first ring load (47 us for 126 MB, where this kernel is the critical path of the forked
+  // decoder tail).
   for (int i = tid; i < 2 * ORD * 8 * 5 * 4; i += 256) {
     const int e = i & 3, o = (i >> 2) % 5, c4 = (i / 20) % 8, kt = (i / 160) % ORD, g = i / 800;
     ws[i] = __ldg(p.w + ((g * 5 + o) * ORD + kt) * 32 + c4 * 4 + e);
   }
   if (tid < 100) pws[tid] = __ldg(p.pw + tid);
   if (tid < 10) bs[tid] = __ldg(p.bias + tid);
+  pdl_wait();
   __syncthreads();
-  const long long witem = ((long long)blockIdx.x * 256 + tid) >> 5;       // (b, group of 4 bins)
-  if (witem >= (long long)p.B * (NDF / 4)) return;
-  const int b = (int)(witem / (NDF / 4)), f = (int)(witem % (NDF / 4)) * 4 + (lane >> 3), c8 = lane & 7;
-  const int slot = io_slot(p.io, b);
-  const int pos = p.st.pos[slot];
-  const float* ring = p.st.c0_ring + (size_t)slot * ORD * NDF * C;
-  float t[10];
+  const long long nitems = (long long)p.B * (NDF / 4);
+  const int c8 = lane & 7;
+  for (long long witem = (long long)blockIdx.x * 8 + (tid >> 5); witem < nitems; witem += (long long)gridDim.x * 8) {   // (b, group of 4 bins)
+    const int b = (int)(witem / (NDF / 4)), f = (int)(witem % (NDF / 4)) * 4 + (lane >> 3);
+    const int slot = io_slot(p.io, b);
+    const int pos = p.st.pos[slot];
+    const float* ring = p.st.c0_ring + (size_t)slot * ORD * NDF * C;
+    float4 x[ORD][2];
+    if (RING16) {                                      // half the bytes of the 120 KB ring read per stream
+      const __half* ringh = reinterpret_cast<const __half*>(ring);
 #pragma unroll
-  for (int o = 0; o < 10; ++o) t[o] = 0.f;
-  float4 x[ORD][2];
-  if (RING16) {                                        // half the bytes of the 120 KB ring read per stream (measured: not faster)
-    const __half* ringh = reinterpret_cast<const __half*>(ring);
+      for (int kt = 0; kt < ORD; ++kt) {
+        const __half* src = ringh + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
+        x[kt][0] = unpack4_f16(*reinterpret_cast<const uint2*>(src));
+        x[kt][1] = unpack4_f16(*reinterpret_cast<const uint2*>(src + 32));
+      }
+    } else {
 #pragma unroll
-    for (int kt = 0; kt < ORD; ++kt) {
-      const __half* src = ringh + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
-      x[kt][0] = unpack4_f16(*reinterpret_cast<const uint2*>(src));
-      x[kt][1] = unpack4_f16(*reinterpret_cast<const uint2*>(src + 32));
-    }
-  } else {
-#pragma unroll
-    for (int kt = 0; kt < ORD; ++kt) {
-      const float* src = ring + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
-      x[kt][0] = *reinterpret_cast<const float4*>(src);
-      x[kt][1] = *reinterpret_cast<const float4*>(src + 32);
-    }
-  }
-#pragma unroll
-  for (int kt = 0; kt < ORD; ++kt)
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const float4* wp = reinterpret_cast<const float4*>(ws) + (g * ORD + kt) * 40 + c8 * 5;
-      const float4 xv = x[kt][g];
-#pragma unroll
-      for (int o = 0; o < 5; ++o) {
-        const float4 w = wp[o];
-        t[g * 5 + o] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, t[g * 5 + o]))));
+      for (int kt = 0; kt < ORD; ++kt) {
+        const float* src = ring + ((size_t)((pos + 1 + kt) % ORD) * NDF + f) * C + c8 * 4;
+        x[kt][0] = *reinterpret_cast<const float4*>(src);
+        x[kt][1] = *reinterpret_cast<const float4*>(src + 32);
       }
     }
+    float t[10];
 #pragma unroll
-  for (int o = 0; o < 10; ++o) {
-    t[o] += __shfl_xor_sync(0xffffffffu, t[o], 1);
-    t[o] += __shfl_xor_sync(0xffffffffu, t[o], 2);
-    t[o] += __shfl_xor_sync(0xffffffffu, t[o], 4);
-  }
-  const bool warm = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) != 0;
-  float* dst = p.st.coef_ring + (((size_t)slot * 3 + pos % 3) * NDF + f) * 10;
-  const float* cop = p.co + ((size_t)b * NDF + f) * 10;
+    for (int o = 0; o < 10; ++o) t[o] = 0.f;
 #pragma unroll
-  for (int rep = 0; rep < 2; ++rep) {
-    const int oo = c8 + 8 * rep;                      // lanes 0..7 of a bin finish outputs 0..7, lanes 0,1 also 8,9
-    if (oo < 10) {
-      float u = bs[oo];
+    for (int kt = 0; kt < ORD; ++kt)
 #pragma unroll
-      for (int i = 0; i < 10; ++i) u = fmaf(pws[oo * 10 + i], t[i], u);
-      dst[oo] = warm ? 0.f : cop[oo] + fmaxf(u, 0.f);
+      for (int g = 0; g < 2; ++g) {
+        const float4* wp = reinterpret_cast<const float4*>(ws) + (g * ORD + kt) * 40 + c8 * 5;
+        const float4 xv = x[kt][g];
+#pragma unroll
+        for (int o = 0; o < 5; ++o) {
+          const float4 w = wp[o];
+          t[g * 5 + o] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, t[g * 5 + o]))));
+        }
+      }
+#pragma unroll
+    for (int o = 0; o < 10; ++o) {
+      t[o] += __shfl_xor_sync(0xffffffffu, t[o], 1);
+      t[o] += __shfl_xor_sync(0xffffffffu, t[o], 2);
+      t[o] += __shfl_xor_sync(0xffffffffu, t[o], 4);
+    }
+    const bool warm = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) != 0;
+    float* dst = p.st.coef_ring + (((size_t)slot * 3 + pos % 3) * NDF + f) * 10;
+    const float* cop = p.co + ((size_t)b * NDF + f) * 10;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+      const int oo = c8 + 8 * rep;                    // lanes 0..7 of a bin finish outputs 0..7, lanes 0,1 also 8,9
+      if (oo < 10) {
+        float u = bs[oo];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) u = fmaf(pws[oo * 10 + i], t[i], u);
+        dst[oo] = warm ? 0.f : cop[oo] + fmaxf(u, 0.f);
+      }
     }
   }
 }
 
 void launch_df_pathway(Engine& e, int B, cudaStream_t st) {
   DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B};
-  const long long threads = (long long)B * (NDF / 4) * 32;
-  if (e.st.c0_fp16) launch_k(e, k_df_pathway<true>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
-  else launch_k(e, k_df_pathway<false>, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, p);
+  const long long ctas = ((long long)B * (NDF / 4) + 7) / 8;             // one item per warp ...
+  const unsigned grid = (unsigned)std::min<long long>(ctas, 4LL * e.num_sms);   // ... or the four resident CTAs per SM (62 registers) walking the items
+  if (e.st.c0_fp16) launch_k(e, k_df_pathway<true>, dim3(grid), dim3(256), 0, st, p);
+  else launch_k(e, k_df_pathway<false>, dim3(grid), dim3(256), 0, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------
