@@ -144,7 +144,8 @@ int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the la
  * post kernel; "post_pair" 0/1/2 post kernel as cta_group::2 CTA pairs (never / always / when not overlapped with its sweep;
  * measured slower, off); "post_res" 0/1 post kernel as a persistent kernel with resident weights when it runs after its sweep
  * (measured on par, off); "gru_uc" 0 auto / 32 / 64 hidden units per CTA of the tcgen05 GRU(256) kernel; "dft_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch size
- * (+ "dft_tc_min") framed DFT and inverse DFT + overlap-add as tensor-core GEMMs. */
+ * (+ "dft_tc_min") framed DFT and inverse DFT + overlap-add as tensor-core GEMMs; "encoder_fork" 0/1 df encoder chain on a
+ * forked stream; "stop_after" k enqueue only the first k kernels of a hop (profiling: tools/chain_profile.py, outputs invalid). */
 int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value);
 int dpdf_time_kernels(dpdf_engine* e, int32_t B, int32_t iters, float* ms_out, const char** names_out,
                       int32_t max_entries, int32_t* n_entries); /* per-kernel CUDA-event timing */
