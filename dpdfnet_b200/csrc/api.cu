@@ -1236,6 +1236,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "stop_after") == 0) {
     e.stop_after = value;                                    // profiling only (tools/chain_profile.py): the streams' state is garbage afterwards
     drop_graphs(e);
+  } else if (strcmp(key, "post_dual") == 0) {
+    if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "post_dual must be 0 (one tile per CTA), 1 (two) or 2 (two when not overlapped with the sweep)");
+    e.post_dual = value;
+    drop_graphs(e);
   } else if (strcmp(key, "post_res") == 0) {
     e.post_res = value ? 1 : 0;
     drop_graphs(e);

@@ -212,6 +212,10 @@ struct Engine {
   int ana_nb = 32, syn_sb = 16;   // caps on the streams per CTA of the analysis / synthesis kernels (8|16|32, 4|8|16)
   int post_pf = 1;                // k_dprnn_post_tc: L2 prefetch distance in units of the SM count (2 CTAs per SM -> 2), 0 = off
   int stop_after = 0, run_idx = 0;   // profiling (tools/chain_profile.py): enqueue only the first stop_after kernels of a hop
+  int post_dual = 0;              // k_dprnn_post_tc<2>: two tiles per 1024-thread CTA sharing a 5-slab weight ring: 0 never, 1 always, 2 = after the sweep only.
+                                  // Bit-identical, parity-tested, measured 33 % SLOWER (profiles/r2Q_*: post 2.53 -> 3.37 ms per hop at 16 384 streams):
+                                  // no weight wait is left, but the two tiles advance in lock step - what makes two co-resident CTAs fast is that
+                                  // they are NOT synchronised: one tile's epilogue runs under the other's MMAs and loads
   int post_res = 0;               // k_dprnn_post_res (persistent, resident weights) when the post kernel runs after its sweep.  Bit-identical,
                                   // parity-tested, measured on par / slightly slower (profiles/r2E_*: post 2.53 -> 2.58 ms per hop at 16 384
                                   // streams): without weight waits a tile takes 21-26 k cycles, but one CTA per SM overlaps nothing, and two

@@ -83,16 +83,26 @@ struct PostTcParams {
 #define PTL(slot) do { } while (0)
 #endif
 
-constexpr int PT_OFF_W = 4 * IMG;                       // two weight slab buffers
-constexpr int PT_OFF_SP = PT_OFF_W + 2 * WSLAB;         // 640 floats of small parameters
-constexpr int PT_OFF_RED = PT_OFF_SP + 640 * 4;         // [2][4][128] LayerNorm partials
-constexpr int PT_OFF_HOFF = PT_OFF_RED + 1024 * 4;      // 128 x int64 state offsets
-constexpr int PT_OFF_COMMIT = PT_OFF_HOFF + 128 * 8;    // 128 x int
-constexpr int PT_OFF_BAR = PT_OFF_COMMIT + 128 * 4;     // 14 mbarriers + TMEM base slot
-constexpr size_t POST_TC_SMEM = PT_OFF_BAR + 128;
-// mbarriers: slab landed [0,4), slab consumed [4,8), peer's half of the slab landed [8,12) (leader of a pair only),
-// phase result ready [12], peer's activation images staged [13] (leader of a pair only)
-constexpr int BAR_FULL = 0, BAR_CONS = 4, BAR_PFULL = 8, BAR_PHASE = 12, BAR_ACT = 13, NBARS = 14;
+// Shared-memory layout per kernel form (MODE 0: one tile, 2-slab ring; 1: CTA pair, 4 half slabs; 2: two tiles per CTA,
+// 5-slab ring shared by both): operand images | weight ring | small parameters | LayerNorm partials | state offsets |
+// commit flags | mbarriers + TMEM base slot
+template <int MODE>
+struct PostLayout {
+  static constexpr int NT = MODE == 2 ? 2 : 1;                          // tiles per CTA
+  static constexpr int NBUF = MODE == 1 ? 4 : (MODE == 2 ? 5 : 2);      // ring depth in slabs
+  static constexpr int SLAB_B = MODE == 1 ? WSLAB / 2 : WSLAB;          // bytes of a slab in this CTA's ring
+  static constexpr int OFF_W = NT * 4 * IMG;
+  static constexpr int OFF_SP = OFF_W + NBUF * SLAB_B;                  // 640 floats of small parameters
+  static constexpr int OFF_RED = OFF_SP + 640 * 4;                      // [NT][2][4][128] LayerNorm partials
+  static constexpr int OFF_HOFF = OFF_RED + NT * 1024 * 4;              // [NT][128] int64 state offsets
+  static constexpr int OFF_COMMIT = OFF_HOFF + NT * 128 * 8;            // [NT][128] int
+  static constexpr int OFF_BAR = OFF_COMMIT + NT * 128 * 4;             // 16 mbarriers + TMEM base slot
+  static constexpr size_t SMEM = OFF_BAR + 144;
+};
+constexpr size_t POST_TC_SMEM = PostLayout<0>::SMEM;
+// mbarriers: slab landed [0,5), slab consumed [5,10), peer's half of the slab landed [10,14) (leader of a pair only),
+// phase result ready [14], peer's activation images staged [15] (leader of a pair only)
+constexpr int BAR_FULL = 0, BAR_CONS = 5, BAR_PFULL = 10, BAR_PHASE = 14, BAR_ACT = 15, NBARS = 16;
 
 // One CTA = one 128-row tile.  Thread 0 is the single MMA issuer (PAIR: thread 0 of the leader CTA, for both tiles) and
 // streams the nine weight slabs of the block (fc_intra K-halves, six GRU gate slabs, fc_inter) through a ring of NBUF
@@ -100,42 +110,54 @@ constexpr int BAR_FULL = 0, BAR_CONS = 4, BAR_PFULL = 8, BAR_PHASE = 12, BAR_ACT
 // never wait for weights.
 // TMEM columns: [0,64) fc_intra, then the gate pre-activations r [0,64) z [64,128) in [128,192) hn [192,256),
 // then fc_inter in [0,64) again (each phase is drained by all threads before the next one is issued).
-template <bool PAIR>
-__global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
-  constexpr int NBUF = PAIR ? 4 : 2;                 // ring depth in slabs
-  constexpr int SLAB_B = PAIR ? WSLAB / 2 : WSLAB;   // bytes of a slab in this CTA's ring: hi | lo images of its 32 (PAIR) or all 64 rows
+//
+// MODE 2 (DUAL): one CTA of 1024 threads per SM works on TWO consecutive tiles in lock step - thread group g = tid >> 9 is the
+// 512-thread tile team of MODE 0 with its own operand images, LayerNorm scratch and 256 TMEM columns - and the two teams
+// share ONE weight ring: every slab is pulled once per 256 rows and, with 128 KB instead of 2 x 64 KB of images, five
+// slabs fit where two co-resident CTAs hold 2 x 2.  Unlike the CTA pair (MODE 1) the teams meet on CTA barriers, not on
+// remote mbarriers, and unlike the persistent form (k_dprnn_post_res) two tiles are in flight per SM.
+template <int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 2 * TC_NT : TC_NT, MODE == 2 ? 1 : 2) k_dprnn_post_tc(PostTcParams p) {
+  constexpr bool PAIR = MODE == 1, DUAL = MODE == 2;
+  using L = PostLayout<MODE>;
+  constexpr int NBUF = L::NBUF, SLAB_B = L::SLAB_B;
   pdl_trigger();
   if (!p.progress) pdl_wait();      // overlapped mode synchronises with the sweep through its progress counters instead
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* RA = smem_raw;                     // four activation operand images
-  unsigned char* RW = smem_raw + PT_OFF_W;
-  float* sp = reinterpret_cast<float*>(smem_raw + PT_OFF_SP);
-  float* red = reinterpret_cast<float*>(smem_raw + PT_OFF_RED);
-  long long* s_hoff = reinterpret_cast<long long*>(smem_raw + PT_OFF_HOFF);
-  int* s_commit = reinterpret_cast<int*>(smem_raw + PT_OFF_COMMIT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + PT_OFF_BAR);   // BAR_* above
+  const int tid_all = threadIdx.x;
+  const int grp = DUAL ? tid_all >> 9 : 0;                 // tile team
+  const int tid = DUAL ? (tid_all & 511) : tid_all;        // thread inside its team
+  unsigned char* RA = smem_raw + grp * 4 * IMG;     // four activation operand images (per team)
+  unsigned char* RW = smem_raw + L::OFF_W;
+  float* sp = reinterpret_cast<float*>(smem_raw + L::OFF_SP);
+  float* red = reinterpret_cast<float*>(smem_raw + L::OFF_RED) + grp * 1024;
+  long long* s_hoff = reinterpret_cast<long long*>(smem_raw + L::OFF_HOFF) + grp * 128;
+  int* s_commit = reinterpret_cast<int*>(smem_raw + L::OFF_COMMIT) + grp * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L::OFF_BAR);   // BAR_* above
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
   const uint32_t rank = PAIR ? cluster_ctarank() : 0;                    // 0 = leader (issues the pair's MMAs)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   const int qd = warp & 3, cg = warp >> 2, row = qd * 32 + lane;
+  const int tile = DUAL ? (int)blockIdx.x * 2 + grp : (int)blockIdx.x;
   int bi, valid, fpos = 0;
   long long rbase, rstride;
   uint32_t ovf = 0;                                        // FP16 range guard of the y converter (tc_common.cuh:f16_nonfinite)
-  __shared__ int s_abort;
+  __shared__ int s_abort_[2];
+  int& s_abort = s_abort_[grp];
   if (tid == 0) s_abort = 0;
   if (p.progress) {
-    const int tiles_e = p.tiles1;                          // erb tiles first (PAIR: padded to even)
-    bi = (int)blockIdx.x < tiles_e ? 1 : 0;
-    const int local = (int)blockIdx.x - (bi ? 0 : tiles_e);
+    const int tiles_e = p.tiles1;                          // erb tiles first (PAIR / DUAL: padded to even)
+    bi = tile < tiles_e ? 1 : 0;
+    const int local = tile - (bi ? 0 : tiles_e);
     const int k = local / p.stiles, stile = local % p.stiles, T = p.br[bi].Fp;
     fpos = (T - 1) / 2 + ((k & 1) ? (k + 1) / 2 : -(k / 2));
     rbase = (long long)stile * 128 * T + fpos;
     rstride = T;
     valid = k < T ? min(128, p.B - stile * 128) : 0;       // k == T: the padding tile of an odd tile count
   } else {
-    bi = (int)blockIdx.x >= p.tiles0 ? 1 : 0;
-    rbase = (long long)(blockIdx.x - (bi ? p.tiles0 : 0)) * 128;
+    bi = tile >= p.tiles0 ? 1 : 0;
+    rbase = (long long)(tile - (bi ? p.tiles0 : 0)) * 128;
     rstride = 1;
     valid = (int)max(0ll, min((long long)128, (long long)p.B * p.br[bi].Fp - rbase));   // 0: padding tile (PAIR)
   }
@@ -159,7 +181,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
       bulk_g2s(RW + buf * SLAB_B, slab_src(i), WSLAB, bars + BAR_FULL + buf);
     }
   };
-  if (tid == 0) {
+  if (tid_all == 0) {
 #pragma unroll
     for (int i = 0; i < NBARS; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -168,7 +190,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     for (int i = 0; i < NBUF; ++i) load_slab(i);
   }
   if (p.progress) {
-    const int stile = ((int)blockIdx.x - (bi ? 0 : p.tiles1)) % p.stiles, T = q.Fp;
+    const int stile = (tile - (bi ? 0 : p.tiles1)) % p.stiles, T = q.Fp;
     if (tid == 0 && valid > 0) {
       // the sweep CTAs this tile's 128 streams come from: dup per direction (branch index as in the intra kernel: 0 = df, 1 = erb)
       const int dup = bi ? 1 : p.dup, pt = bi ? p.stiles : p.ptiles;
@@ -200,7 +222,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   // resident any more (hcat alone is 0.4 GB at 16 384 streams) and the tile's dependent phases would each eat a DRAM
   // round trip: ncu showed 38 % long-scoreboard stalls, hcat staging 9 k and the first epilogue 12 k of 44 k cycles.
   if (p.pf_dist > 0 && !p.progress) {
-    const long long nt = (long long)blockIdx.x + p.pf_dist;
+    const long long nt = (long long)tile + p.pf_dist;
     if (nt < (long long)p.tiles0 + p.tiles1) {
       const int nb = nt >= p.tiles0 ? 1 : 0;
       const PostTcBranch& nq = p.br[nb];
@@ -244,6 +266,10 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     __syncthreads();
     if (s_abort) valid = 0;                              // the sweep never delivered this tile's rows: the pair protocol still runs,
                                                          // but nothing is read or written for this tile (see above)
+  } else if constexpr (DUAL) {
+    if (tid_all < 32) tmem_alloc<512>(tmem_slot);
+    __syncthreads();
+    if (s_abort) valid = 0;                              // as for the pair: the other team's tile goes on
   } else {
     if (warp == 0) tmem_alloc<256>(tmem_slot);
     __syncthreads();                                     // barriers initialised, s_hoff visible
@@ -299,9 +325,9 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   PTL(1);
-  const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16) + cg * 16;
+  const uint32_t lane_base = tmem + ((uint32_t)(qd * 32) << 16) + grp * 256 + cg * 16;   // a team's 256 TMEM columns
   constexpr uint32_t IDESC = idesc_f16(PAIR ? 256 : 128, 64);
-  const uint32_t a_base = smem_u32(RA), w_base = smem_u32(RW);
+  const uint32_t a_base = smem_u32(smem_raw), w_base = smem_u32(RW);      // MMAs are issued by thread 0 for every tile of the CTA
 
   // slab i: D[col .. col+64) (+)= A[128 or 256][64] * W_i[64][64]^T, three FP16 passes per 16-wide k-step
   auto run_slab = [&](int i, int a_img, uint32_t col, uint32_t accumulate) {
@@ -318,17 +344,23 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     const uint32_t ah = a_base + a_img * IMG, bh = w_base + buf * SLAB_B;
     const uint64_t dah = DESC0 | (ah >> 4), dal = dah + (IMG >> 4), dbh = DESC0 | (bh >> 4), dbl = dbh + (SLAB_B / 2 >> 4);
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {                       // 16 halves of K per step = two core matrices = 256 B
-      if constexpr (PAIR) {
-        umma_f16_2cta(tmem + col, dah + ks * 16, dbh + ks * 16, IDESC, accumulate);
-        umma_f16_2cta(tmem + col, dal + ks * 16, dbh + ks * 16, IDESC, 1);
-        umma_f16_2cta(tmem + col, dah + ks * 16, dbl + ks * 16, IDESC, 1);
-      } else {
-        umma_f16(tmem + col, dah + ks * 16, dbh + ks * 16, IDESC, accumulate);
-        umma_f16(tmem + col, dal + ks * 16, dbh + ks * 16, IDESC, 1);
-        umma_f16(tmem + col, dah + ks * 16, dbl + ks * 16, IDESC, 1);
+    for (int g = 0; g < L::NT; ++g) {                      // DUAL: the same slab serves both teams' tiles
+      const uint64_t ga = (uint64_t)(g * 4 * IMG >> 4);
+      const uint32_t d = tmem + g * 256 + col;
+      uint32_t acc = accumulate;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {                     // 16 halves of K per step = two core matrices = 256 B
+        if constexpr (PAIR) {
+          umma_f16_2cta(d, dah + ks * 16, dbh + ks * 16, IDESC, acc);
+          umma_f16_2cta(d, dal + ks * 16, dbh + ks * 16, IDESC, 1);
+          umma_f16_2cta(d, dah + ks * 16, dbl + ks * 16, IDESC, 1);
+        } else {
+          umma_f16(d, dah + ga + ks * 16, dbh + ks * 16, IDESC, acc);
+          umma_f16(d, dal + ga + ks * 16, dbh + ks * 16, IDESC, 1);
+          umma_f16(d, dah + ga + ks * 16, dbl + ks * 16, IDESC, 1);
+        }
+        acc = 1;
       }
-      accumulate = 1;
     }
     if constexpr (PAIR) umma_commit_2cta(bars + BAR_CONS + buf);
     else umma_commit(bars + BAR_CONS + buf);
@@ -346,7 +378,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   };
 
   // ---- phase 1: acc[0,64) = hcat * fc_intra^T ---------------------------------------------------------------
-  if (tid == 0) {
+  if (tid_all == 0) {
     phase_begin(0);
     run_slab(0, 0, 0, 0);
     run_slab(1, 2, 0, 1);
@@ -373,10 +405,15 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
   // row statistics over 64 columns held by the four column-group warps of a lane quadrant: only those four warps
   // exchange partials (rows of different quadrants are disjoint), so they meet on a named barrier of their own
   auto quad_sync = [&]() {                                 // immediate barrier ids: a register id makes ptxas reserve all sixteen
-    if (qd == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-    else if (qd == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
-    else if (qd == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
-    else asm volatile("bar.sync 4, 128;" ::: "memory");
+    const int id = qd + 4 * grp;
+    if (id == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else if (id == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+    else if (id == 2) asm volatile("bar.sync 3, 128;" ::: "memory");
+    else if (id == 3) asm volatile("bar.sync 4, 128;" ::: "memory");
+    else if (id == 4) asm volatile("bar.sync 5, 128;" ::: "memory");
+    else if (id == 5) asm volatile("bar.sync 6, 128;" ::: "memory");
+    else if (id == 6) asm volatile("bar.sync 7, 128;" ::: "memory");
+    else asm volatile("bar.sync 8, 128;" ::: "memory");
   };
   auto layernorm16 = [&](float (&v)[16], const float* g, const float* b) {
     float s = 0.f;
@@ -430,19 +467,19 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
 
   PTL(3);
   // ---- phase 2: GRU gate pre-activations in TMEM: r [0,64) z [64,128) in [128,192) hn [192,256) ---------------
-  if (tid == 0) {
+  if (tid_all == 0) {
     phase_begin(1);
     run_slab(2, 0, 0, 0);     // Wih_r * y
     run_slab(3, 2, 0, 1);     // Whh_r * h
-    if constexpr (!PAIR) { load_slab(4); load_slab(5); }   // PAIR: slabs 4, 5 were requested at the end of phase 1
+    if constexpr (MODE == 0) { load_slab(4); load_slab(5); }   // PAIR / DUAL: slabs 4, 5 were requested before
     run_slab(4, 0, 64, 0);    // Wih_z * y
     run_slab(5, 2, 64, 1);    // Whh_z * h
-    load_slab(6);
-    load_slab(7);
+    if constexpr (DUAL) { load_slab(7); load_slab(8); }        // slab 6 came in under the first epilogue
+    else { load_slab(6); load_slab(7); }
     run_slab(6, 0, 128, 0);   // Wih_n * y
     run_slab(7, 2, 192, 0);   // Whh_n * h
     phase_commit();
-    load_slab(8);
+    if constexpr (!DUAL) load_slab(8);
   }
   if (warp == 0) mbar_wait(bars + BAR_PHASE, 1);
   __syncthreads();
@@ -480,7 +517,7 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
 
   PTL(5);
   // ---- phase 3: acc[0,64) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena --------------
-  if (tid == 0) {
+  if (tid_all == 0) {
     phase_begin(2);
     run_slab(8, 2, 0, 0);
     phase_commit();
@@ -535,6 +572,10 @@ __global__ void __launch_bounds__(TC_NT, 2) k_dprnn_post_tc(PostTcParams p) {
     tc_fence_before();
     cluster_sync_all();                                    // both CTAs have drained their accumulators; no signal is in flight
     if (warp == 0) tmem_dealloc_2cta<256>(tmem);
+  } else if constexpr (DUAL) {
+    tc_fence_before();
+    __syncthreads();                                       // both teams have drained their accumulators
+    if (tid_all < 32) tmem_dealloc<512>(tmem);
   } else {
     if (warp == 0) tmem_dealloc<256>(tmem);
   }
@@ -914,10 +955,17 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   // CTA pairs (cta_group::2, Engine::post_pair): 1 = always, 2 = only when the kernel runs after its sweep (a pair needs
   // both SMs of a TPC, which the CTAs of a concurrent sweep fragment)
   const bool pair = e.post_pair == 1 || (e.post_pair == 2 && !e.overlap_now);
-  auto even = [&](int t) { return pair ? (t + 1) & ~1 : t; };
+  // two tiles per 1024-thread CTA sharing a 5-slab weight ring (Engine::post_dual): 1 = always, 2 = only after the sweep
+  const bool dual = !pair && (e.post_dual == 1 || (e.post_dual == 2 && !e.overlap_now));
+  auto even = [&](int t) { return (pair || dual) ? (t + 1) & ~1 : t; };
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(TC_NT);
-  cfg.dynamicSmemBytes = POST_TC_SMEM;
+  cfg.blockDim = dim3(dual ? 2 * TC_NT : TC_NT);
+  cfg.dynamicSmemBytes = dual ? PostLayout<2>::SMEM : (pair ? PostLayout<1>::SMEM : PostLayout<0>::SMEM);
+  auto launch = [&]() {
+    if (dual) { cfg.gridDim.x /= 2; cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<2>, p); }
+    else if (pair) cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<1>, p);
+    else cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<0>, p);
+  };
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
@@ -955,8 +1003,7 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
     p.pf_dist = e.post_pf * e.num_sms;
     cfg.gridDim = dim3((unsigned)(p.tiles0 + p.tiles1));
     if (e.pdl_now && !e.pdl_first) pdl_attr();
-    if (pair) cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<true>, p);
-    else cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<false>, p);
+    launch();
     return;
   }
   // Overlapped with the sweep that feeds it: launched as a programmatic dependent of the intra kernel (it may start as
@@ -970,13 +1017,13 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.tiles0 = even(p.stiles * (NDF / 2));
   cfg.gridDim = dim3((unsigned)(p.tiles0 + p.tiles1));
   pdl_attr();
-  if (pair) cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<true>, p);
-  else cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<false>, p);
+  launch();
 }
 
 void init_dprnn_tc_kernels() {
-  cudaFuncSetAttribute(k_dprnn_post_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_TC_SMEM);
-  cudaFuncSetAttribute(k_dprnn_post_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_post_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PostLayout<0>::SMEM);
+  cudaFuncSetAttribute(k_dprnn_post_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PostLayout<1>::SMEM);
+  cudaFuncSetAttribute(k_dprnn_post_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PostLayout<2>::SMEM);
   cudaFuncSetAttribute(k_dprnn_post_res, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POST_RES_SMEM);
 }
 

@@ -143,7 +143,7 @@ int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the la
  * hop with programmatic dependent launches / 2 every segment but the DPRNN stack; "tail_pdl" 0/1 the dense tail only; "intra_pdl" 0/1 the sweep of block i >= 1 as a programmatic dependent of the previous
  * post kernel; "post_pair" 0/1/2 post kernel as cta_group::2 CTA pairs (never / always / when not overlapped with its sweep;
  * measured slower, off); "post_res" 0/1 post kernel as a persistent kernel with resident weights when it runs after its sweep
- * (measured on par, off); "gru_uc" 0 auto / 32 / 64 hidden units per CTA of the tcgen05 GRU(256) kernel; "dft_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch size
+ * (measured on par, off); "post_dual" 0/1/2 two tiles per 1024-thread CTA sharing one weight ring (measured slower, off); "gru_uc" 0 auto / 32 / 64 hidden units per CTA of the tcgen05 GRU(256) kernel; "dft_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch size
  * (+ "dft_tc_min") framed DFT and inverse DFT + overlap-add as tensor-core GEMMs; "encoder_fork" 0/1 df encoder chain on a
  * forked stream; "stop_after" k enqueue only the first k kernels of a hop (profiling: tools/chain_profile.py, outputs invalid). */
 int dpdf_set_option(dpdf_engine* e, const char* key, int32_t value);

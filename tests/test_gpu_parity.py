@@ -190,7 +190,7 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
 
 @pytest.mark.parametrize("overlap", [0, 1])
 @pytest.mark.parametrize("name,B", [("dpdfnet2", 130), ("dpdfnet4", 300), ("dpdfnet2_48khz_hr", 67)])
-def test_post_kernel_as_cta_pairs(torch_cuda, name, B, overlap):
+def test_post_kernel_as_cta_pairs_and_dual_tiles(torch_cuda, name, B, overlap):
     """k_dprnn_post_tc<PAIR>: clusters of two CTAs issue every product as one tcgen05.mma.cta_group::2 of M = 256 over the
     pair's two tiles, each CTA holding half of every weight slab.  Same arithmetic per row as the single-CTA kernel, so
     the results must be bit-identical - with odd tile counts per branch (a padding tile closes the pair), ragged last
@@ -200,16 +200,19 @@ def test_post_kernel_as_cta_pairs(torch_cuda, name, B, overlap):
     rng = np.random.default_rng(41)
     pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
     outs = {}
-    for pair in (0, 1):
+    for form in (None, "post_pair", "post_dual"):           # post_dual: two tiles per 1024-thread CTA sharing one 5-slab weight ring
         eng = _engine(name, 8, B)
         eng.set_option("intra_tc", 1)
         eng.set_option("overlap", overlap)
         eng.set_option("lanes", 1)
-        eng.set_option("post_pair", pair)
-        outs[pair] = (eng.run_pcm_host(pcm), eng.debug_tensor("xd", B), eng.debug_tensor("xe", B), eng.state_export(B - 1))
+        if form:
+            eng.set_option(form, 1)
+        outs[form] = (eng.run_pcm_host(pcm), eng.debug_tensor("xd", B), eng.debug_tensor("xe", B), eng.state_export(B - 1))
         eng.close()
-    for a, b in zip(outs[1], outs[0]):
-        assert np.array_equal(a, b)
+    for form in ("post_pair", "post_dual"):
+        for a, b in zip(outs[form], outs[None]):
+            assert np.array_equal(a, b), form
+    outs[1] = outs["post_dual"]
     ora = _oracle(name, 8, B)
     ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
     assert np.abs(outs[1][0] - ref).max() < WAVE_TOL

@@ -49,10 +49,10 @@ int main(int argc, char** argv) {
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<true>, p);
+      cudaLaunchKernelEx(&cfg, k_dprnn_post_tc<1>, p);
     }
 #else
-    k_dprnn_post_tc<false><<<p.tiles0, TC_NT, POST_TC_SMEM>>>(p);
+    k_dprnn_post_tc<0><<<p.tiles0, TC_NT, POST_TC_SMEM>>>(p);
 #endif
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
