@@ -234,14 +234,16 @@ struct GRUCommitParams {
 __global__ void k_gru_commit(GRUCommitParams p) {
   pdl_trigger();
   pdl_wait();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // float4 index within one cell
-  if (idx >= p.B * (H / 4)) return;
-  const int b = idx / (H / 4), c = (idx % (H / 4)) * 4;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // (stream, 16-float chunk) of one cell: four 16-byte copies in flight per thread
+  if (idx >= p.B * (H / 16)) return;
+  const int b = idx / (H / 16), t = idx % (H / 16);            // 16 threads per row: float4 t, t + 16, t + 32, t + 48 (coalesced)
   if (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) return;
   const int slot = io_slot(p.io, b);
   const int cell = blockIdx.y;
-  *reinterpret_cast<float4*>(p.hstate[cell] + (size_t)slot * p.stride[cell] + c) =
-      *reinterpret_cast<const float4*>(p.hout[cell] + (size_t)b * H + c);
+  const float4* src = reinterpret_cast<const float4*>(p.hout[cell] + (size_t)b * H) + t;
+  float4* dst = reinterpret_cast<float4*>(p.hstate[cell] + (size_t)slot * p.stride[cell]) + t;
+  const float4 v0 = src[0], v1 = src[16], v2 = src[32], v3 = src[48];
+  dst[0] = v0; dst[16] = v1; dst[32] = v2; dst[48] = v3;
 }
 
 void launch_gru(Engine& e, const GRUProblem* probs, int nprob, int B, cudaStream_t st) {
@@ -264,7 +266,7 @@ void launch_gru_commit(Engine& e, const GRUProblem* probs, int nprob, int B, cud
   p.n = nprob;
   p.B = B;
   for (int i = 0; i < nprob; ++i) { p.hout[i] = probs[i].hout; p.hstate[i] = probs[i].hstate; p.stride[i] = probs[i].hs_stride; }
-  dim3 grid((B * (H / 4) + 255) / 256, nprob);
+  dim3 grid((B * (H / 16) + 255) / 256, nprob);
   launch_k(e, k_gru_commit, dim3(grid), dim3(256), 0, st, p);
 }
 
