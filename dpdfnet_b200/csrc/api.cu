@@ -1254,6 +1254,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "intra_pdl") == 0) {
     e.intra_pdl = value ? 1 : 0;
     drop_graphs(e);
+  } else if (strcmp(key, "intra_sr") == 0) {
+    if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "intra_sr must be 0 (off), 1 (whenever rows are duplicated) or 2 (with intra_dup = 4 only)");
+    e.intra_sr = value;
+    drop_graphs(e);
   } else if (strcmp(key, "intra_dup") == 0) {
     if (value != 0 && value != 1 && value != 2 && value != 4) return fail(DPDF_ERR_INVALID, "intra_dup must be 0 (auto), 1, 2 or 4");
     e.intra_dup = value;

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 3) k_sepconv_tc(SepTcParam
   const uint32_t tmem = *tmem_slot;
   STL(3);
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one()) {                              // elect.sync, not `tid == 0`: tc_common.cuh:elect_one
     mbar_wait(bars, 0);
     const uint32_t ah = smem_u32(Aimg), al = ah + SCT_IMG, bh = smem_u32(Wsm), bl = bh + 64 * 64 * 2;
     constexpr uint32_t IDESC = idesc_f16(128, 64);

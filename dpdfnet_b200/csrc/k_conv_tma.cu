@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
       }
     };
     if (warp == ST_NT / 32) {                                    // ---- producer warp: runs ahead of the compute warps by up to NS units
-      if (lane == 0) {
+      if (elect_one()) {
         if (prev_seg >= 0) mbar_wait(seg_done + prev_seg, 0);      // the ring is re-cut: wait until the previous segment has drained
         for (int lu = 0; lu < n_units; ++lu) {
           if (lu >= NS) mbar_wait(empty + lu % NS, (lu / NS - 1) & 1);
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(ST_NTB, 2) k_sepconv_tma(const __grid_constant
 
       // ---- pointwise GEMM of the tile: 12 tcgen05.mma (hi*hi + lo*hi + hi*lo per 16-wide k step) -------------------
       tc_fence_after();
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {                            // elect.sync, not `tid == 0`: tc_common.cuh:elect_one
         mbar_wait(bars, (w_loads - 1) & 1);                      // the slab of this problem has landed (returns at once later on)
         const uint32_t ah = smem_u32(Aimg), al = ah + ST_IMG, bh = smem_u32(Wsm), bl = bh + 64 * 64 * 2;
         constexpr uint32_t IDESC = idesc_f16(128, 64);

@@ -87,13 +87,13 @@ __global__ void __launch_bounds__(DT_NT, 1) k_dft_tc(DftTcParams p) {
       mbar_expect_tx(full_w + s % DT_NW, SLAB);
       bulk_g2s(Wsm + (s % DT_NW) * SLAB, wsrc + (size_t)s * SLAB, SLAB, full_w + s % DT_NW);
     };
-    if (lane == 0)
+    if (elect_one())                                         // elect.sync, not `lane == 0`: tc_common.cuh:elect_one
       for (int s = 0; s < DT_NW && s < NS; ++s) load_w(s);
     pdl_wait();
     for (int s = 0; s < NS; ++s) {
       if ((s & 1) == 0) asm volatile("bar.sync 1, %0;" ::"n"(DT_NT) : "memory");      // A images of stage s written
       else asm volatile("bar.sync 2, %0;" ::"n"(DT_NT) : "memory");
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
         mbar_wait(full_w + s % DT_NW, (s / DT_NW) & 1);
         const uint32_t ah = smem_u32(Asm) + (s & 1) * 2 * DT_AIMG, al = ah + DT_AIMG;

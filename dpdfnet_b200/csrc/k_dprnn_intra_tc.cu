@@ -116,9 +116,10 @@ struct IntraTcParams {
 #endif
 
 // The sweep of one CTA: branch br, direction dir, stream tile `tile` of 128 / D streams.
-template <int D>
+template <int D, bool SR = false>
 __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br, const int dir, const int tile) {
   static_assert(D == 1 || D == 2 || D == 4, "row duplication factor");
+  static_assert(!SR || D > 1, "split rows need at least two rows per stream");
   constexpr int SPC = 128 / D;        // streams per CTA
   constexpr int LPQ = 32 / D;         // lanes of a warp (TMEM lane quadrant) that hold distinct streams
   constexpr int UPS = 4 / D;          // units per gate thread and K slice
@@ -135,6 +136,7 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
   const int qd = warp & 3, cg = warp >> 2;
   const int part = lane / LPQ;                               // which of the D rows of its stream this thread is
   const int srow = qd * LPQ + (lane % LPQ);                  // the stream's row in the CTA's staging tiles
+  const bool lo_row = SR && part >= D / 2;                   // split rows: the upper half of a stream's D rows carries the lo halves
   const int T = br ? p.Fp[1] : p.Fp[0];
   const int b0 = tile * SPC;
   const float* __restrict__ xg = br ? p.x[1] : p.x[0];
@@ -194,8 +196,12 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
     for (int pt = 0; pt < D; ++pt) {                         // operand row of (stream, part): quadrant, part block, lane
       const int r = (xr_[i] / LPQ) * 32 + pt * LPQ + (xr_[i] % LPQ);
       unsigned char* dst = Xsm + buf * 2 * A_IMG + img16_off(r, xkc);
-      *reinterpret_cast<uint4*>(dst) = hi;
-      *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
+      if constexpr (SR) {                                    // one image: hi in the lower half of the stream's rows, lo in the upper
+        *reinterpret_cast<uint4*>(dst) = pt < D / 2 ? hi : lo;
+      } else {
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + A_IMG) = lo;
+      }
     }
   };
   auto store_x = [&](int buf, const float (&v)[NX][8]) {
@@ -234,7 +240,8 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
   __syncthreads();
   tc_fence_after();
 
-  // ---- MMA issue (warp 16, one elected lane) ------------------------------------------------------------------
+  // ---- MMA issue (warp 16, one lane elected with elect.sync: with `lane == 0` every tcgen05.mma sat in an elect /
+  // broadcast loop of its own, ~100 cycles per issued instruction on the critical path of a step) -----------------
   // The recurrent product of step t+1 is issued K-slice by K-slice: slice ks only needs units [16 ks, 16 ks + 16) of
   // h_t, and the gate warps produce the units in exactly that order (every thread owns 4 units of each slice), so the
   // tensor core works on slice ks while the gate math of slices ks+1.. is still running.  Only the last slice's six
@@ -242,6 +249,10 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
   if (warp == 16) {
     int* my_progress = progress_ptr();
     const uint32_t w_base = smem_u32(Wsm), x_base = smem_u32(Xsm);
+    // The TMEM base comes out of shared memory, i.e. out of a per-thread register: unless the compiler can see that it is
+    // warp-uniform it wraps EVERY tcgen05.mma in an elect / broadcast loop (~100 cycles per issued MMA on the critical
+    // path of the step).  A shuffle from lane 0 is uniform by construction.
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
     auto x_mma = [&](int t) {                                // P[t & 1][0, 192) = x_t * W_ih^T
       const uint32_t xa = x_base + (t & 1) * 2 * A_IMG, d = tmem + TM_P + (t & 1) * 192;
@@ -250,7 +261,7 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {                       // K = 64 in steps of 16 halves = two core matrices = 256 B
         umma_f16(d, dah + ks * 16, dbh + ks * 16, idesc_f16(128, 192), ks > 0);
-        umma_f16(d, dal + ks * 16, dbh + ks * 16, idesc_f16(128, 192), 1);
+        if constexpr (!SR) umma_f16(d, dal + ks * 16, dbh + ks * 16, idesc_f16(128, 192), 1);
         umma_f16(d, dah + ks * 16, dbl + ks * 16, idesc_f16(128, 192), 1);
       }
     };
@@ -263,13 +274,13 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
       const uint32_t ah = tmem + TM_HHI + ks * 8, al = tmem + TM_HLO + ks * 8;
       const uint32_t drz = tmem + TM_P + (t & 1) * 192, dn = tmem + TM_HN;
       umma_f16_ts(drz, ah, rz_h, idesc_f16(128, 128), 1);    // r, z += h * W_hh[r,z]^T (on top of the x part)
-      umma_f16_ts(drz, al, rz_h, idesc_f16(128, 128), 1);
+      if constexpr (!SR) umma_f16_ts(drz, al, rz_h, idesc_f16(128, 128), 1);
       umma_f16_ts(drz, ah, rz_l, idesc_f16(128, 128), 1);
       umma_f16_ts(dn, ah, n_h, idesc_f16(128, 64), ks > 0);  // hn = h * W_hh[n]^T
-      umma_f16_ts(dn, al, n_h, idesc_f16(128, 64), 1);
+      if constexpr (!SR) umma_f16_ts(dn, al, n_h, idesc_f16(128, 64), 1);
       umma_f16_ts(dn, ah, n_l, idesc_f16(128, 64), 1);
     };
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(bars, 0);                                    // weight images landed (async proxy -> async proxy)
       x_mma(0);
 #pragma unroll
@@ -287,13 +298,13 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
         if (ks == 2) asm volatile("bar.sync 3, %0;" ::"n"(ITC_NT) : "memory");
         if (ks == 3) asm volatile("bar.sync 4, %0;" ::"n"(ITC_NT) : "memory");
         if (ks == 3) TL(5);
-        if (lane == 0) {
+        if (elect_one()) {
           tc_fence_after();
           h_mma_slice(t + 1, ks);
         }
         __syncwarp();
       }
-      if (lane == 0) {
+      if (elect_one()) {
         umma_commit(bars + 1);
         TL(6);
 #ifndef ITC_NO_X
@@ -336,10 +347,21 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
     };
     // the thread's own UPS units out of the four columns of its cg group (a tcgen05.ld address is warp-uniform, so the
     // D parts of a warp load the same four columns and select)
-    auto own = [&](const uint32_t (&g)[4], int j) -> float {
+    auto own_raw = [&](const uint32_t (&g)[4], int j) -> float {
       if constexpr (D == 1) return __uint_as_float(g[j]);
       else if constexpr (D == 2) return __uint_as_float(part ? g[2 + j] : g[j]);
       else return __uint_as_float((part & 2) ? ((part & 1) ? g[3] : g[2]) : ((part & 1) ? g[1] : g[0]));
+    };
+    // Split rows: this row's accumulators hold only the (hi | lo) * W part of the sum; the other part sits in the row of
+    // the partner thread 16 lanes away (part ^ D/2), which owns other units - each sends the column the other one owns.
+    auto own = [&](const uint32_t (&g)[4], int j) -> float {
+      if constexpr (!SR) return own_raw(g, j);
+      else {
+        float theirs;
+        if constexpr (D == 2) theirs = __uint_as_float(part ? g[j] : g[2 + j]);
+        else theirs = __uint_as_float((part & 2) ? ((part & 1) ? g[1] : g[0]) : ((part & 1) ? g[3] : g[2]));
+        return own_raw(g, j) + __shfl_xor_sync(0xffffffffu, theirs, 16);
+      }
     };
     const int uoff = UPS * part;                             // first own unit inside the cg group's four
     for (int t = 0; t < T; ++t) {
@@ -458,6 +480,22 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
           split2_f16(hn[0], hn[1], hi0, lo0);
           split2_f16(hn[2], hn[3], hi1, lo1);
           *reinterpret_cast<float4*>(srow_w + hchunk) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+        } else if constexpr (SR) {
+          // split rows: a hi row needs the partner's hi halves of the other column, a lo row the partner's lo halves -
+          // and the partner (16 lanes away) is always a row of the other kind, so each sends what it does not store
+          uint32_t hi, lo;
+          if constexpr (D == 2) {
+            split2_f16(hn[0], hn[1], hi, lo);
+            *reinterpret_cast<float2*>(srow_w + hchunk) = make_float2(hn[0], hn[1]);
+          } else {
+            const float o = __shfl_xor_sync(0xffffffffu, hn[0], 8);                // the other unit of this thread's column
+            split2_f16((part & 1) ? o : hn[0], (part & 1) ? hn[0] : o, hi, lo);
+            *reinterpret_cast<float*>(srow_w + hchunk) = hn[0];
+          }
+          const uint32_t recv = __shfl_xor_sync(0xffffffffu, lo_row ? hi : lo, 16);
+          hi0 = lo_row ? recv : hi;                              // (column 0, column 1) of this row's kind
+          hi1 = lo_row ? lo : recv;
+          lo0 = lo1 = 0u;
         } else if constexpr (D == 2) {
           uint32_t hi, lo;
           split2_f16(hn[0], hn[1], hi, lo);
@@ -474,8 +512,12 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
           lo0 = (part & 2) ? olo : lo; lo1 = (part & 2) ? lo : olo;
           *reinterpret_cast<float*>(srow_w + hchunk) = hn[0];
         }
-        tmem_st2(lane_base + TM_HHI + 8 * ks + 2 * cg, hi0, hi1);
-        tmem_st2(lane_base + TM_HLO + 8 * ks + 2 * cg, lo0, lo1);
+        if constexpr (SR) {
+          tmem_st2(lane_base + TM_HHI + 8 * ks + 2 * cg, hi0, hi1);
+        } else {
+          tmem_st2(lane_base + TM_HHI + 8 * ks + 2 * cg, hi0, hi1);
+          tmem_st2(lane_base + TM_HLO + 8 * ks + 2 * cg, lo0, lo1);
+        }
         if (ks == 1 && t > 0) write_out(t - 1);
         if (ks == 2 && t + 2 < T) store_x(t & 1, xv);        // x_mma(t) (reader of this buffer) completed with the commit
         if (ks == 3) {
@@ -521,7 +563,7 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
 // Grid = df CTAs (2 directions x tiles[0]) followed by erb CTAs.  The erb sweep has F'e = 8 positions against the df
 // sweep's 48, so it is never the critical path: it keeps full 128-stream tiles (DERB = 1) while the df branch is
 // split DDF ways, which leaves more SMs to the overlapped post kernel than duplicating both branches.
-template <int DDF, int DERB>
+template <int DDF, int DERB, bool SRDF = false>
 #ifdef ITC_MAXNREG
 __global__ void __maxnreg__(ITC_MAXNREG) k_dprnn_intra_tc(const __grid_constant__ IntraTcParams p) {
 #else
@@ -530,7 +572,7 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(const __grid_const
   const int item = blockIdx.x, ndf = 2 * p.tiles[0];
   // two inlined copies of the sweep even for DDF == DERB: the branch index is then a compile-time constant in each
   // (one generic copy costs the gate warps live registers: 56 instead of 16 bytes of spills)
-  if (item < ndf) intra_sweep<DDF>(p, 0, item / p.tiles[0], item % p.tiles[0]);
+  if (item < ndf) intra_sweep<DDF, SRDF>(p, 0, item / p.tiles[0], item % p.tiles[0]);
   else intra_sweep<DERB>(p, 1, (item - ndf) / p.tiles[1], (item - ndf) % p.tiles[1]);
 }
 
@@ -565,7 +607,10 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.progress = e.overlap_now ? e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles : nullptr;
   p.err = e.err_dev;
   const dim3 grid(2 * (p.tiles[0] + p.tiles[1]));
-  if (D == 4) launch_k(e, k_dprnn_intra_tc<4, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  const bool sr = e.intra_sr == 1 ? D > 1 : (e.intra_sr == 2 && D == 4);    // auto: where the step is tensor bound (profiles/r3b_*)
+  if (D == 4 && sr) launch_k(e, k_dprnn_intra_tc<4, 1, true>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else if (D == 2 && sr) launch_k(e, k_dprnn_intra_tc<2, 1, true>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else if (D == 4) launch_k(e, k_dprnn_intra_tc<4, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else if (D == 2) launch_k(e, k_dprnn_intra_tc<2, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else launch_k(e, k_dprnn_intra_tc<1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
 }
@@ -574,6 +619,8 @@ void init_dprnn_intra_tc_kernels() {
   cudaFuncSetAttribute(k_dprnn_intra_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
   cudaFuncSetAttribute(k_dprnn_intra_tc<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
   cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
 }
 
 }  // namespace dpdf

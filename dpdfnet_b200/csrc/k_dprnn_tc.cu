@@ -378,7 +378,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 2 * TC_NT : TC_NT, MODE == 2 ? 1 :
   };
 
   // ---- phase 1: acc[0,64) = hcat * fc_intra^T ---------------------------------------------------------------
-  if (tid_all == 0) {
+  // The issuing lane is chosen with elect.sync in the converged warp 0 (tc_common.cuh:elect_one): under `tid == 0` the
+  // compiler wrapped every tcgen05.mma and bulk copy in an elect / broadcast loop of its own (626 of them in this file).
+  if (tid_all < 32 && elect_one()) {
     phase_begin(0);
     run_slab(0, 0, 0, 0);
     run_slab(1, 2, 0, 1);
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 2 * TC_NT : TC_NT, MODE == 2 ? 1 :
 
   PTL(3);
   // ---- phase 2: GRU gate pre-activations in TMEM: r [0,64) z [64,128) in [128,192) hn [192,256) ---------------
-  if (tid_all == 0) {
+  if (tid_all < 32 && elect_one()) {
     phase_begin(1);
     run_slab(2, 0, 0, 0);     // Wih_r * y
     run_slab(3, 2, 0, 1);     // Whh_r * h
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 2 * TC_NT : TC_NT, MODE == 2 ? 1 :
 
   PTL(5);
   // ---- phase 3: acc[0,64) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena --------------
-  if (tid_all == 0) {
+  if (tid_all < 32 && elect_one()) {
     phase_begin(2);
     run_slab(8, 2, 0, 0);
     phase_commit();
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_res(PostTcParams p) {
     PRL(1);
 
     // ---- phase 1: acc[0,64) = hcat * fc_intra^T ---------------------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       if (wait_w) mbar_wait(bars, 0);                      // the resident weights have landed (first tile only)
       run_slab(0, 0, 0, 0);
       run_slab(1, 2, 0, 1);
@@ -826,7 +828,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_res(PostTcParams p) {
 
     PRL(3);
     // ---- phase 2: GRU gate pre-activations: r [0,64) z [64,128) in [128,192) hn [192,256) -----------------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       run_slab(2, 0, 0, 0);
       run_slab(3, 2, 0, 1);
       run_slab(4, 0, 64, 0);
@@ -872,7 +874,7 @@ __global__ void __launch_bounds__(TC_NT, 1) k_dprnn_post_res(PostTcParams p) {
     PRL(5);
 
     // ---- phase 3: acc[0,64) = h_new * fc_inter^T; meanwhile commit the new state to the slot arena ----------------
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       run_slab(8, 2, 0, 0);
       umma_commit(bars + 1);
     }

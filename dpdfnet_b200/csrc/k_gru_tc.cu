@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
             bulk_g2s(dst + img * (SLAB / 2) + gate * UC * 128, src + img * (GT_WSLAB / 2) + gate * 8192 + sub, UC * 128, full_w + s % NW);
       }
     };
-    if (lane == 0) {
+    if (elect_one()) {                                       // elect.sync, not `lane == 0`: tc_common.cuh:elect_one
 #pragma unroll
       for (int s = 0; s < NW; ++s) load_w(s);
     }
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
       const int buf = s & 1;
       if (buf == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT_NT) : "memory");      // A images of stage s written
       else asm volatile("bar.sync 2, %0;" ::"n"(GT_NT) : "memory");
-      if (lane == 0) {
+      if (elect_one()) {
         tc_fence_after();
         mbar_wait(full_w + s % NW, (s / NW) & 1);
         const uint32_t ah = smem_u32(Asm) + buf * 2 * GT_AIMG, al = ah + GT_AIMG;

@@ -7,6 +7,9 @@
 #ifndef ITC_DUP
 #define ITC_DUP 1    // -DITC_DUP=2|4: row-duplicated tiles (128 / D streams per CTA)
 #endif
+#ifndef ITC_SR
+#define ITC_SR 0     // -DITC_SR=1 (with ITC_DUP > 1): split rows, hi | lo halves in the stream's rows, two MMA passes
+#endif
 #include "../../dpdfnet_b200/csrc/k_dprnn_intra_tc.cu"
 
 int main(int argc, char** argv) {
@@ -34,7 +37,7 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-    k_dprnn_intra_tc<ITC_DUP, 1><<<2 * (p.tiles[0] + p.tiles[1]), ITC_NT, INTRA_TC_SMEM>>>(p);
+    k_dprnn_intra_tc<ITC_DUP, 1, (ITC_SR != 0)><<<2 * (p.tiles[0] + p.tiles[1]), ITC_NT, INTRA_TC_SMEM>>>(p);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
