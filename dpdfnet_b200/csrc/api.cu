@@ -132,6 +132,10 @@ static int bind_weights(Engine& e) {
       x.tc_fc2_w = W(q + ".tc.fc2_w", C * C);
       x.tc_intra = W(q + ".tc.intra", 2 * 4 * 192 * C / 2);
       x.tc_intra_bias = W(q + ".tc.intra_bias", 2 * 4 * C);
+      if (br) {                                              // optional (blobs packed before the fragment form existed): absent = form off
+        auto it = e.wtable.find(q + ".tc.intra_f");
+        x.tc_intra_f = it != e.wtable.end() && it->second.second == (size_t)(2 * 4 * 192 * C / 2) ? e.weights_dev + it->second.first : nullptr;
+      }
     }
   }
   auto gl = [&](const std::string& n, int G, int Ng, int Kg) { return GLW{W(n + ".w", (size_t)G * Ng * Kg), W(n + ".b", (size_t)G * Ng), G, Ng, Kg}; };
@@ -1253,6 +1257,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     drop_graphs(e);
   } else if (strcmp(key, "intra_pdl") == 0) {
     e.intra_pdl = value ? 1 : 0;
+    drop_graphs(e);
+  } else if (strcmp(key, "intra_frag") == 0) {
+    e.intra_frag = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "intra_sr") == 0) {
     if (value < 0 || value > 2) return fail(DPDF_ERR_INVALID, "intra_sr must be 0 (off), 1 (whenever rows are duplicated) or 2 (with intra_dup = 4 only)");

@@ -63,6 +63,7 @@ struct DprnnW {
   const float *tc_fc_w, *tc_gates, *tc_fc2_w;      // tcgen05 operand images (hi | lo), weights.py:umma_operand
   const float* tc_intra_bias;                      // [2][4][64] with the same exponent scales as the images
   const float* tc_intra;                           // FP16 operand images of the intra GRU, weights.py:umma_operand16
+  const float* tc_intra_f = nullptr;               // df branch: the same with W_hh's K axis in fragment order (k_dprnn_intra_tc.cu:intra_sweep_f)
 };
 
 struct Weights {
@@ -199,6 +200,7 @@ struct Engine {
   int intra_tc_min = 640;         // measured (profiles/r2v_sweep.log, dpdfnet4 ms/hop FFMA2 vs tcgen05): 512 streams 0.763 / 0.800, 768 streams 1.114 / 0.866
   int intra_pdl = 0;              // sweep of block i >= 1 launched as a programmatic dependent of the previous block's post kernel (prologue under its tail)
   int intra_sr = 2;               // k_dprnn_intra_tc "split rows": the D rows of a stream carry the hi | lo operand halves, two MMA passes instead of three; 0 off, 1 whenever D > 1, 2 = with D = 4 only (measured)
+  int intra_frag = 1;             // k_dprnn_intra_tc fragment form where the sweep runs 32 streams per CTA (intra_dup 4): two rows per stream, .16x128b TMEM fragments
   int intra_dup = 0;              // k_dprnn_intra_tc row duplication D (128 / D streams per CTA): 0 = auto (largest D whose sweep fits one wave), 1, 2, 4
   int gru_tc = 2;                 // GRUCell(256) gate GEMMs on tcgen05: 0 never, 1 always, 2 = when B >= gru_tc_min
   int gru_tc_min = 256;

@@ -95,6 +95,7 @@ struct IntraTcParams {
   float* hcat[2];         // [B][Fp][128]
   int Fp[2];
   const float* wimg[2];   // [2 dirs][W_ih hi | W_ih lo | W_hh hi | W_hh lo] FP16 operand images
+  const float* wimg_f;    // df branch, fragment form: the same with the K axis of W_hh in the order of intra_sweep_f (weights.py: tc.intra_f)
   const float* bias[2];   // [2][4][64], exponent scales folded in (weights.py: tc.intra_bias)
   int tiles[2];           // stream tiles of the sweep per branch: ceil(B / (128 / D)) with the branch's row duplication D
   int B;
@@ -560,10 +561,286 @@ __device__ __forceinline__ void intra_sweep(const IntraTcParams& p, const int br
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// tcgen05.ld / tcgen05.st .16x128b.x1: thread T of the warp <-> (TMEM lane T / 4, column T % 4) in the first register and
+// (lane 8 + T / 4, column T % 4) in the second (measured: tools/ubench/tmem_layout_probe.cu, profiles/r3d_*)
+__device__ __forceinline__ void tmem_ld_16x128b_nowait(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_16x128b(uint32_t taddr, uint32_t r0, uint32_t r1) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x1.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
+}
+
+// The sweep of one df-branch CTA in FRAGMENT form: 32 streams per CTA like D = 4, but a stream owns just TWO rows of the
+// M = 128 tile - quadrant q, lanes i (hi halves of the operands) and 8 + i (lo halves), i = 0..7, lanes 16..31 idle - and
+// its four gate threads are the four ADJACENT lanes 4 i + j of warp (q, cg): a .16x128b fragment load hands thread
+// (i, j) column j of both rows at once, so a pre-activation is one tcgen05.ld and one add (hi * W + lo * W) instead of a
+// 4-column load, six selects and a shuffle, and h goes back with one .16x128b fragment store per PAIR of K slices and no
+// shuffle at all: thread (i, j) packs its units of slices 2p and 2p + 1 (16 (2p + e) + 4 cg + j, e = 0, 1) into ONE operand
+// column 16 p + 4 cg + j (two K halves), the hi word to row i and the lo word to row 8 + i.  The recurrent matrix is
+// packed with its K axis in that order (weights.py: tc.intra_f).  The gate math of a pair runs on packed f32x2 lanes.
+__device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int dir, const int tile) {
+  constexpr int SPC = 32;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* Wsm = smem_raw;
+  unsigned char* Xsm = smem_raw + OFF_X;
+  unsigned char* Ssm = smem_raw + OFF_ST;
+  float* sb = reinterpret_cast<float*>(smem_raw + OFF_BIAS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + OFF_BAR);       // [0] weights landed, [1] step accumulators complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qd = warp & 3, cg = warp >> 2;
+  const int si = lane >> 2, j = lane & 3;                    // stream of the quadrant, unit of the cg group
+  const int srow = qd * 8 + si;                              // the stream's row in the staging tiles
+  const int T = p.Fp[0];
+  const int b0 = tile * SPC;
+  const float* __restrict__ xg = p.x[0];
+  float* __restrict__ hg = p.hcat[0];
+
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (tid < 256) {                                           // biases of a pair's two units side by side: [gate][p][cg][j][e]
+    const int u = tid & 63, ks = u >> 4;
+    sb[(tid >> 6) * C + (((ks >> 1) * 4 + ((u >> 2) & 3)) * 4 + (u & 3)) * 2 + (ks & 1)] = __ldg(p.bias[0] + dir * 4 * C + tid);
+  }
+  for (int i = tid; i < ST_BUF / 16; i += ITC_NT) reinterpret_cast<uint4*>(Ssm + ST_BUF)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0
+  for (int i = tid; i < 4 * A_IMG / 16; i += ITC_NT) reinterpret_cast<uint4*>(Xsm)[i] = make_uint4(0u, 0u, 0u, 0u);        // idle operand rows stay 0
+  auto progress_ptr = [&]() -> int* { return p.progress ? p.progress + dir * p.tiles[0] + tile : nullptr; };
+  __syncthreads();                                           // barriers initialised
+  if (tid == 0) {
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wimg_f) + (size_t)dir * 4 * W_IMG;
+    mbar_expect_tx(bars, 4 * W_IMG);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bulk_g2s(Wsm + i * W_IMG, src + (size_t)i * W_IMG, W_IMG, bars);
+  }
+
+  // ---- x tile staging: 32 streams x 8 chunks of 8 floats = 256 items, one per thread of warps 0..7 ----------------
+  const bool x_active = warp < 8;
+  const int xr = (warp >> 1) * 8 + (lane & 7), xkc = (warp & 1) * 4 + (lane >> 3);
+  const int xrow = (xr >> 3) * 32 + (xr & 7);                // operand row of the stream's hi halves (lo: + 8)
+  auto load_x = [&](int t, float (&v)[8]) {
+    const int f = dir ? T - 1 - t : t;
+    const int bb = b0 + xr;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (bb < p.B && x_active) {
+      const float4* src = reinterpret_cast<const float4*>(xg + ((size_t)bb * T + f) * C + xkc * 8);
+      a = __ldg(src);
+      c = __ldg(src + 1);
+    }
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  };
+  auto store_x = [&](int buf, const float (&v)[8]) {
+    if (!x_active) return;
+    uint4 hi, lo;
+    split8_f16(v, hi, lo);
+    if ((f16_nonfinite(hi.x) | f16_nonfinite(hi.y) | f16_nonfinite(hi.z) | f16_nonfinite(hi.w)) && p.err) p.err[DPDF_ERRW_RANGE] = 1;
+    unsigned char* dst = Xsm + buf * 2 * A_IMG + img16_off(xrow, xkc);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + 1024) = lo;              // row + 8 = the next 8-row group of the image
+  };
+  pdl_wait();
+  if (tid == 0 && progress_ptr()) {
+    *reinterpret_cast<volatile int*>(progress_ptr()) = 0;    // the previous consumer of these counters has completed
+    __threadfence();
+  }
+  __syncthreads();
+  pdl_trigger();
+  float xv[8];
+  if (warp < 16) {
+    load_x(0, xv);
+    store_x(0, xv);
+    if (T > 1) {
+      load_x(1, xv);
+      store_x(1, xv);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 16) {                                           // h_0 = 0 in the TMEM operand columns (all 32 lanes of the quadrant)
+    const uint32_t a = *tmem_slot + ((uint32_t)(qd * 32) << 16) + TM_HHI + cg * 8;
+    tmem_st4(a, 0u, 0u, 0u, 0u); tmem_st4(a + 4, 0u, 0u, 0u, 0u);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 16) {
+    // ---- MMA issue: two passes per product (A rows carry hi | lo, B = W hi then W lo) ------------------------------
+    int* my_progress = progress_ptr();
+    const uint32_t w_base = smem_u32(Wsm), x_base = smem_u32(Xsm);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    constexpr uint64_t DESC0 = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
+    auto x_mma = [&](int t) {                                // P[t & 1][0, 192) = x_t * W_ih^T
+      const uint32_t xa = x_base + (t & 1) * 2 * A_IMG, d = tmem + TM_P + (t & 1) * 192;
+      const uint64_t da = DESC0 | (xa >> 4);
+      const uint64_t dbh = DESC0 | (w_base >> 4), dbl = DESC0 | ((w_base + W_IMG) >> 4);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        umma_f16(d, da + ks * 16, dbh + ks * 16, idesc_f16(128, 192), ks > 0);
+        umma_f16(d, da + ks * 16, dbl + ks * 16, idesc_f16(128, 192), 1);
+      }
+    };
+    auto h_mma_slice = [&](int t, int kk) {                  // K slice kk = operand columns [8 kk, 8 kk + 8)
+      const uint32_t whi = w_base + 2 * W_IMG + kk * 256, wlo = w_base + 3 * W_IMG + kk * 256;
+      const uint64_t rz_h = DESC0 | (whi >> 4), rz_l = DESC0 | (wlo >> 4);
+      const uint64_t n_h = DESC0 | ((whi + 16 * 1024) >> 4), n_l = DESC0 | ((wlo + 16 * 1024) >> 4);
+      const uint32_t a = tmem + TM_HHI + kk * 8;
+      const uint32_t drz = tmem + TM_P + (t & 1) * 192, dn = tmem + TM_HN;
+      umma_f16_ts(drz, a, rz_h, idesc_f16(128, 128), 1);
+      umma_f16_ts(drz, a, rz_l, idesc_f16(128, 128), 1);
+      umma_f16_ts(dn, a, n_h, idesc_f16(128, 64), kk > 0);
+      umma_f16_ts(dn, a, n_l, idesc_f16(128, 64), 1);
+    };
+    if (elect_one()) {
+      mbar_wait(bars, 0);
+      x_mma(0);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) h_mma_slice(0, kk);
+      umma_commit(bars + 1);
+      if (T > 1) x_mma(1);
+    }
+    for (int t = 0; t + 1 < T; ++t) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        // K slice kk = pair kk >> 1 of the eight gate warps with cg >> 1 == (kk & 1): they and this warp meet on barrier 1 + kk
+        if (kk == 0) asm volatile("bar.sync 1, 288;" ::: "memory");
+        if (kk == 1) asm volatile("bar.sync 2, 288;" ::: "memory");
+        if (kk == 2) asm volatile("bar.sync 3, 288;" ::: "memory");
+        if (kk == 3) asm volatile("bar.sync 4, 288;" ::: "memory");
+        if (kk == 3) TL(5);
+        if (elect_one()) {
+          tc_fence_after();
+          h_mma_slice(t + 1, kk);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        umma_commit(bars + 1);
+        TL(6);
+        if (t + 2 < T) x_mma(t + 2);
+        TL(7);
+        if (my_progress) {
+          __threadfence();
+          *reinterpret_cast<volatile int*>(my_progress) = t;
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- the sweep (gate warps) -----------------------------------------------------------------------------------
+    const uint32_t lane_base = *tmem_slot + ((uint32_t)(qd * 32) << 16);
+    const int nvalid = min(SPC, p.B - b0);
+    auto write_out = [&](int s_) {
+      const int f = dir ? T - 1 - s_ : s_;
+      const int r = tid >> 4;
+      const float4 v = *reinterpret_cast<const float4*>(Ssm + (s_ & 1) * ST_BUF + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
+      if (r < nvalid) *reinterpret_cast<float4*>(hg + ((size_t)(b0 + r) * T + f) * 2 * C + dir * C + (tid & 15) * 4) = v;
+    };
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2* bp = reinterpret_cast<const float2*>(sb) + cg * 4 + j;          // + 16 p (+ 32 per gate)
+    for (int t = 0; t < T; ++t) {
+      TL(0);
+      if (t + 2 < T) load_x(t + 2, xv);                      // in flight during the wait
+      mbar_wait(bars + 1, t & 1);
+      tc_fence_after();
+      TL(1);
+      const uint32_t pa = lane_base + TM_P + (t & 1) * 192 + 4 * cg;
+      uint32_t ghn[4][2], gr[2][2][2], gz[2][2][2], gi[2][2][2];                  // [pair][e][hi row | lo row]
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tmem_ld_16x128b_nowait(lane_base + TM_HN + 16 * ks + 4 * cg, ghn[ks][0], ghn[ks][1]);   // hn is single buffered: drain first
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        tmem_ld_16x128b_nowait(pa + 16 * e, gr[0][e][0], gr[0][e][1]);
+        tmem_ld_16x128b_nowait(pa + 64 + 16 * e, gz[0][e][0], gz[0][e][1]);
+        tmem_ld_16x128b_nowait(pa + 128 + 16 * e, gi[0][e][0], gi[0][e][1]);
+      }
+      tmem_ld_wait();
+      TL(2);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {                          // the second pair's pre-activations arrive under the first pair's math
+        tmem_ld_16x128b_nowait(pa + 32 + 16 * e, gr[1][e][0], gr[1][e][1]);
+        tmem_ld_16x128b_nowait(pa + 64 + 32 + 16 * e, gz[1][e][0], gz[1][e][1]);
+        tmem_ld_16x128b_nowait(pa + 128 + 32 + 16 * e, gi[1][e][0], gi[1][e][1]);
+      }
+      unsigned char* srow_w = Ssm + (t & 1) * ST_BUF + srow * 256 + j * 4;
+      const unsigned char* prow = Ssm + ((t + 1) & 1) * ST_BUF + srow * 256 + j * 4;      // h_{t-1} of this thread's units (FP32)
+      auto f2 = [](uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); };
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        if (pp == 1) tmem_ld_wait();
+        const int hc0 = ((8 * pp + cg) ^ (srow & 15)) << 4, hc1 = ((8 * pp + 4 + cg) ^ (srow & 15)) << 4;      // staging chunks of the two units
+        const float2 hp = make_float2(*reinterpret_cast<const float*>(prow + hc0), *reinterpret_cast<const float*>(prow + hc1));
+        // pre-activation = hi-row accumulator + lo-row accumulator (+ bias); sigmoid / tanh with the exponent scales folded in
+        const float2 ar = __fadd2_rn(__fadd2_rn(f2(gr[pp][0][0], gr[pp][1][0]), f2(gr[pp][0][1], gr[pp][1][1])), bp[16 * pp]);
+        const float2 az = __fadd2_rn(__fadd2_rn(f2(gz[pp][0][0], gz[pp][1][0]), f2(gz[pp][0][1], gz[pp][1][1])), bp[16 * pp + 32]);
+        const float2 pr = __fadd2_rn(make_float2(ex2_ftz(fminf(ar.x, 60.f)), ex2_ftz(fminf(ar.y, 60.f))), one);
+        const float2 pz = __fadd2_rn(make_float2(ex2_ftz(fminf(az.x, 60.f)), ex2_ftz(fminf(az.y, 60.f))), one);
+        const float2 pq = __fmul2_rn(pr, pz);
+        const float2 ip = make_float2(rcp_ftz(pq.x), rcp_ftz(pq.y));
+        const float2 rr = __fmul2_rn(ip, pz), zz = __fmul2_rn(ip, pr);
+        const float2 vin = __fadd2_rn(__fadd2_rn(f2(gi[pp][0][0], gi[pp][1][0]), f2(gi[pp][0][1], gi[pp][1][1])), bp[16 * pp + 64]);
+        const float2 vhn = __fadd2_rn(__fadd2_rn(f2(ghn[2 * pp][0], ghn[2 * pp + 1][0]), f2(ghn[2 * pp][1], ghn[2 * pp + 1][1])), bp[16 * pp + 96]);
+        const float2 c = __ffma2_rn(rr, vhn, vin);
+        const float2 pc = __fadd2_rn(make_float2(ex2_ftz(c.x), ex2_ftz(c.y)), one);
+        const float2 q = make_float2(rcp_ftz(pc.x), rcp_ftz(pc.y));
+        const float2 n = __ffma2_rn(make_float2(-2.0f, -2.0f), q, one);
+        const float2 hv = __ffma2_rn(zz, __fadd2_rn(hp, make_float2(-n.x, -n.y)), n);
+        uint32_t hi, lo;
+        split2_f16(hv.x, hv.y, hi, lo);
+        tmem_st_16x128b(lane_base + TM_HHI + 16 * pp + 4 * cg, hi, lo);
+        *reinterpret_cast<float*>(srow_w + hc0) = hv.x;
+        *reinterpret_cast<float*>(srow_w + hc1) = hv.y;
+        if (pp == 0 && t > 0) write_out(t - 1);
+        if (pp == 1) {
+          if (t + 2 < T) store_x(t & 1, xv);                 // x_mma(t) (reader of this buffer) completed with the commit
+          TL(3);
+          TL(4);
+          fence_async_smem();                                // generic-proxy smem writes -> visible to the tensor core
+        }
+        tmem_st_wait();
+        if (t + 1 < T) {                                     // hand the pair's K slice over to the issuer, do not wait
+          tc_fence_before();
+          if (pp == 0) {
+            if (cg < 2) asm volatile("bar.arrive 1, 288;" ::: "memory");
+            else asm volatile("bar.arrive 2, 288;" ::: "memory");
+          } else {
+            if (cg < 2) asm volatile("bar.arrive 3, 288;" ::: "memory");
+            else asm volatile("bar.arrive 4, 288;" ::: "memory");
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 16) {                                           // write-out of the last step (all staging rows visible after the barrier)
+    const int s_ = T - 1, f = dir ? 0 : T - 1;
+    const int nvalid = min(SPC, p.B - b0), r = tid >> 4;
+    if (r < nvalid)
+      *reinterpret_cast<float4*>(hg + ((size_t)(b0 + r) * T + f) * 2 * C + dir * C + (tid & 15) * 4) =
+          *reinterpret_cast<const float4*>(Ssm + (s_ & 1) * ST_BUF + r * 256 + (((tid & 15) ^ (r & 15)) << 4));
+  }
+  if (progress_ptr()) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile int*>(progress_ptr()) = T;
+  }
+  if (warp == 0) tmem_dealloc<512>(*tmem_slot);
+}
+
 // Grid = df CTAs (2 directions x tiles[0]) followed by erb CTAs.  The erb sweep has F'e = 8 positions against the df
 // sweep's 48, so it is never the critical path: it keeps full 128-stream tiles (DERB = 1) while the df branch is
 // split DDF ways, which leaves more SMs to the overlapped post kernel than duplicating both branches.
-template <int DDF, int DERB, bool SRDF = false>
+template <int DDF, int DERB, int FORM = 0>      // FORM of the df sweep: 0 = D copies of a row, 1 = split rows, 2 = fragment form (32 streams)
 #ifdef ITC_MAXNREG
 __global__ void __maxnreg__(ITC_MAXNREG) k_dprnn_intra_tc(const __grid_constant__ IntraTcParams p) {
 #else
@@ -572,7 +849,10 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(const __grid_const
   const int item = blockIdx.x, ndf = 2 * p.tiles[0];
   // two inlined copies of the sweep even for DDF == DERB: the branch index is then a compile-time constant in each
   // (one generic copy costs the gate warps live registers: 56 instead of 16 bytes of spills)
-  if (item < ndf) intra_sweep<DDF, SRDF>(p, 0, item / p.tiles[0], item % p.tiles[0]);
+  if (item < ndf) {
+    if constexpr (FORM == 2) intra_sweep_f(p, item / p.tiles[0], item % p.tiles[0]);
+    else intra_sweep<DDF, FORM == 1>(p, 0, item / p.tiles[0], item % p.tiles[0]);
+  }
   else intra_sweep<DERB>(p, 1, (item - ndf) / p.tiles[1], (item - ndf) % p.tiles[1]);
 }
 
@@ -608,8 +888,10 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.err = e.err_dev;
   const dim3 grid(2 * (p.tiles[0] + p.tiles[1]));
   const bool sr = e.intra_sr == 1 ? D > 1 : (e.intra_sr == 2 && D == 4);    // auto: where the step is tensor bound (profiles/r3b_*)
-  if (D == 4 && sr) launch_k(e, k_dprnn_intra_tc<4, 1, true>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
-  else if (D == 2 && sr) launch_k(e, k_dprnn_intra_tc<2, 1, true>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  p.wimg_f = e.w.dprnn_df[blk].tc_intra_f;
+  if (D == 4 && e.intra_frag && p.wimg_f) launch_k(e, k_dprnn_intra_tc<4, 1, 2>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else if (D == 4 && sr) launch_k(e, k_dprnn_intra_tc<4, 1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else if (D == 2 && sr) launch_k(e, k_dprnn_intra_tc<2, 1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else if (D == 4) launch_k(e, k_dprnn_intra_tc<4, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else if (D == 2) launch_k(e, k_dprnn_intra_tc<2, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else launch_k(e, k_dprnn_intra_tc<1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
@@ -619,8 +901,9 @@ void init_dprnn_intra_tc_kernels() {
   cudaFuncSetAttribute(k_dprnn_intra_tc<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
   cudaFuncSetAttribute(k_dprnn_intra_tc<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
   cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
-  cudaFuncSetAttribute(k_dprnn_intra_tc<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
-  cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
 }
 
 }  // namespace dpdf

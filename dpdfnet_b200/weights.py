@@ -339,6 +339,17 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             gscale = np.repeat(np.array([-LOG2E, -LOG2E, 2.0 * LOG2E]), C).astype(np.float32)[:, None]
             t[f"{q}.tc.intra"] = np.concatenate([
                 umma_operand16(sd[f"{p}.intra_gru.{m}_l0{sfx}"] * gscale) for sfx in ("", "_reverse") for m in ("weight_ih", "weight_hh")])
+            if br == "df":
+                # fragment form of the sweep (k_dprnn_intra_tc.cu:intra_sweep_f): the thread of unit (cg, j) packs its units
+                # of K slices 2p and 2p + 1 into ONE operand column 16 p + 4 cg + j, so K element k = 2 c + e of the
+                # recurrent product is hidden unit 16 (2 p + e) + 4 cg + j; W_ih is unchanged
+                kk = np.arange(C)
+                cc, ee = kk >> 1, kk & 1
+                perm = 16 * (2 * (cc >> 4) + ee) + 4 * ((cc >> 2) & 3) + (cc & 3)
+                assert sorted(perm.tolist()) == list(range(C))
+                t[f"{q}.tc.intra_f"] = np.concatenate([
+                    umma_operand16((sd[f"{p}.intra_gru.{m}_l0{sfx}"] * gscale)[:, perm if m == "weight_hh" else kk])
+                    for sfx in ("", "_reverse") for m in ("weight_ih", "weight_hh")])
             t[f"{q}.tc.intra_bias"] = t[f"{q}.intra.bias"] * np.repeat(
                 np.array([-LOG2E, -LOG2E, 2.0 * LOG2E, 2.0 * LOG2E]), C).astype(np.float32).reshape(1, 4, C)
 

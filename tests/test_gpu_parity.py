@@ -168,7 +168,7 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
     rng = np.random.default_rng(31)
     pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
     outs = {}
-    for D in (1, 2, 4, 0, "2sr", "4sr"):
+    for D in (1, 2, 4, 0, "2sr", "4sr", "4f"):
         eng = _engine(name, 4, B)
         eng.set_option("intra_tc", 1)
         eng.set_option("overlap", overlap)
@@ -176,7 +176,11 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
         # split rows (intra_sr): the D rows of a stream carry the hi | lo halves of the operands instead of copies, two
         # MMA passes instead of three and the partner rows' accumulators are added in registers - the same products plus
         # the lo * lo term, in another order: equal to rounding, not bit for bit
-        eng.set_option("intra_sr", 1 if isinstance(D, str) else 0)
+        # fragment form (intra_frag, 32 streams per CTA): two rows per stream (hi | lo), .16x128b TMEM fragments hand each
+        # of a stream's four gate threads its own column of both rows, K axis of W_hh permuted on the host
+        if D != 0:                                          # 0: the engine's own choice of form
+            eng.set_option("intra_sr", 1 if D in ("2sr", "4sr") else 0)
+            eng.set_option("intra_frag", 1 if D == "4f" else 0)
         eng.set_option("intra_dup", int(D[0]) if isinstance(D, str) else D)
         outs[D] = (eng.run_pcm_host(pcm), eng.debug_tensor("xd", B), eng.state_export(B - 1))
         eng.close()
@@ -185,14 +189,14 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
             assert np.array_equal(a, b), D
     for a, b in zip(outs[0], outs[1]):                      # the auto choice may be a split-row form
         assert np.abs(a - b).max() < 2e-5
-    for D in ("2sr", "4sr"):
+    for D in ("2sr", "4sr", "4f"):
         assert np.abs(outs[D][0] - outs[1][0]).max() < 2e-6, D
         assert np.abs(outs[D][1] - outs[1][1]).max() < 2e-5, D
         assert np.abs(outs[D][2] - outs[1][2]).max() < 2e-5, D
     ora = _oracle(name, 4, B)
     ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
     N = get_spec(name).n_blocks
-    for D in (4, "2sr", "4sr"):
+    for D in (4, "2sr", "4sr", "4f"):
         assert np.abs(outs[D][0] - ref).max() < WAVE_TOL, D
         assert np.abs(outs[D][1] - np.asarray(ora.dbg[f"xd{N - 1}"]).reshape(B, -1)).max() < 2e-4, D
     with pytest.raises(ValueError):

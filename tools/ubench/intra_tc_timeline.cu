@@ -8,7 +8,7 @@
 #define ITC_DUP 1    // -DITC_DUP=2|4: row-duplicated tiles (128 / D streams per CTA)
 #endif
 #ifndef ITC_SR
-#define ITC_SR 0     // -DITC_SR=1 (with ITC_DUP > 1): split rows, hi | lo halves in the stream's rows, two MMA passes
+#define ITC_SR 0     // -DITC_SR=1 (with ITC_DUP > 1): split rows, hi | lo halves in the stream's rows, two MMA passes; 2 (ITC_DUP = 4): fragment form
 #endif
 #include "../../dpdfnet_b200/csrc/k_dprnn_intra_tc.cu"
 
@@ -29,7 +29,7 @@ int main(int argc, char** argv) {
   cudaMemset(tl, 0, T * 12 * 8);
   IntraTcParams p{};
   p.x[0] = p.x[1] = x; p.hcat[0] = p.hcat[1] = hcat; p.Fp[0] = T; p.Fp[1] = 8;
-  p.wimg[0] = p.wimg[1] = w; p.bias[0] = p.bias[1] = bias; p.B = B; p.tiles[0] = (B * ITC_DUP + 127) / 128; p.tiles[1] = (B + 127) / 128;
+  p.wimg[0] = p.wimg[1] = w; p.wimg_f = w; p.bias[0] = p.bias[1] = bias; p.B = B; p.tiles[0] = (B * ITC_DUP + 127) / 128; p.tiles[1] = (B + 127) / 128;
 #ifdef ITC_TIMELINE
   p.tl = tl;
 #endif
@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-    k_dprnn_intra_tc<ITC_DUP, 1, (ITC_SR != 0)><<<2 * (p.tiles[0] + p.tiles[1]), ITC_NT, INTRA_TC_SMEM>>>(p);
+    k_dprnn_intra_tc<ITC_DUP, 1, ITC_SR><<<2 * (p.tiles[0] + p.tiles[1]), ITC_NT, INTRA_TC_SMEM>>>(p);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
