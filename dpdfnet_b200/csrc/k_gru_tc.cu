@@ -76,27 +76,30 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
     // ---- issuer warp: weight slab ring + MMAs -----------------------------------------------------------------
     // packed per 64-unit chunk (weights.py: tc_w): 8 stages x [r 64 | z 64 | n 64 rows][64 k] hi | lo, 8 rows per KB
     const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(q.w.tc_w) + (size_t)(uc * UC / 64) * 8 * GT_WSLAB;
-    auto load_w = [&](int s) {
-      mbar_expect_tx(full_w + s % NW, SLAB);
-      unsigned char* dst = Wsm + (s % NW) * SLAB;
-      const unsigned char* src = wsrc + (size_t)s * GT_WSLAB;
+    // Step i of the walk is K stage (i + 4) & 7: the RECURRENT half (h_prev * W_hh, stages 4..7) comes first.  It depends on
+    // nothing but the state of the previous hop, so as a programmatic dependent (dense tail, Engine::tail_pdl) the CTA
+    // loads, converts and multiplies it while the kernel that produces x is still running; only the x half waits.
+    auto load_w = [&](int i) {
+      mbar_expect_tx(full_w + i % NW, SLAB);
+      unsigned char* dst = Wsm + (i % NW) * SLAB;
+      const unsigned char* src = wsrc + (size_t)((i + 4) & 7) * GT_WSLAB;
       if constexpr (UC == 64) {
-        bulk_g2s(dst, src, GT_WSLAB, full_w + s % NW);
+        bulk_g2s(dst, src, GT_WSLAB, full_w + i % NW);
       } else {                                               // the unit half's row blocks of r, z and n, out of the hi and the lo image
         const int sub = (uc % (64 / UC)) * UC * 128;         // byte offset of UC rows inside a 64-row gate block
 #pragma unroll
         for (int img = 0; img < 2; ++img)
 #pragma unroll
           for (int gate = 0; gate < 3; ++gate)
-            bulk_g2s(dst + img * (SLAB / 2) + gate * UC * 128, src + img * (GT_WSLAB / 2) + gate * 8192 + sub, UC * 128, full_w + s % NW);
+            bulk_g2s(dst + img * (SLAB / 2) + gate * UC * 128, src + img * (GT_WSLAB / 2) + gate * 8192 + sub, UC * 128, full_w + i % NW);
       }
     };
     if (elect_one()) {                                       // elect.sync, not `lane == 0`: tc_common.cuh:elect_one
 #pragma unroll
       for (int s = 0; s < NW; ++s) load_w(s);
     }
-    pdl_wait();
-    for (int s = 0; s < 8; ++s) {
+    // (no griddepcontrol.wait in this warp: it touches weights and shared memory only)
+    for (int s = 0; s < 8; ++s) {                               // s = step of the walk (see load_w)
       const int buf = s & 1;
       if (buf == 0) asm volatile("bar.sync 1, %0;" ::"n"(GT_NT) : "memory");      // A images of stage s written
       else asm volatile("bar.sync 2, %0;" ::"n"(GT_NT) : "memory");
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
         mbar_wait(full_w + s % NW, (s / NW) & 1);
         const uint32_t ah = smem_u32(Asm) + buf * 2 * GT_AIMG, al = ah + GT_AIMG;
         const uint32_t bh = smem_u32(Wsm) + (s % NW) * SLAB, bl = bh + SLAB / 2;
-        const bool hpart = s >= 4;
+        const bool hpart = s < 4;
         const uint32_t ncol = hpart ? 3u * UC : 2u * UC;     // in (x part) / hn (h part)
         const uint32_t nfirst = (s & 3) == 0 ? 0u : 1u;
 #pragma unroll
@@ -134,13 +137,13 @@ __global__ void __launch_bounds__(GT_NT, 1) k_gru_tc(GRUTcParams p) {
     // so a warp's 8-byte stores fill two whole 128-byte core matrices
     const int g = (tid >> 3) & 15;
     const int rsub = (tid & 7) | ((tid >> 7) << 3);
-    pdl_wait();                                               // x and h_prev come from the kernels before this one
     uint32_t ovf = 0;                                         // FP16 range guard (tc_common.cuh:f16_nonfinite)
     // the activation chunk of stage s + 1 is in flight while stage s is converted: with the loads issued only when their
     // stage came up, every one of the eight stages ate a full L2 round trip (27 us per launch at 1024 streams)
-    auto load_stage = [&](int s, float4 (&v)[8]) {
-      const int k0 = (s & 3) * 64 + g * 4;
-      const bool hpart = s >= 4;
+    auto load_stage = [&](int s, float4 (&v)[8]) {              // s = step of the walk: h_prev chunks first (previous hop's state),
+      const int k0 = (s & 3) * 64 + g * 4;                      // then, once the grid dependency has resolved, the x chunks
+      const bool hpart = s < 4;
+      if (s == 4) pdl_wait();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = rsub + 16 * i;
