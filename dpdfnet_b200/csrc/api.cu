@@ -290,7 +290,7 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
     add(c.hcat_e, (size_t)d.fe[3] * 2 * C); add(c.hcat_d, (NDF / 2) * 2 * C);
     add(c.emb_e, 512); add(c.cemb, 512); add(c.g0, H); add(c.henc, H); add(c.emb, 512);
     add(c.x1, H); add(c.herb1, H); add(c.herb2, H); add(c.ed, 512); add(c.ed2, (size_t)d.fe[3] * C);
-    add(c.x2, H); add(c.hdf1, H); add(c.hdf2, H); add(c.cc, H); add(c.co, NDF * 2 * ORD);
+    add(c.x2, H); add(c.hdf1, H); add(c.hdf2, H); add(c.cc, H); add(c.co, NDF * 2 * ORD); add(c.dfp, NDF * 2 * ORD);
     add(c.d3, (size_t)d.fe[2] * C); add(c.d2, (size_t)d.fe[1] * C); add(c.d1, (size_t)d.fe[0] * C); add(c.m, d.fe[0]);
     add(c.spec_tc, (size_t)e.spec_tc_ld); add(c.yspec_tc, (size_t)e.yspec_tc_ld);
     size_t total = 0;
@@ -329,6 +329,9 @@ extern "C" int dpdf_create(const dpdf_spec* spec, const void* weights, size_t nb
         cudaEventCreateWithFlags(&e.br_join[l], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.enc_fork[l], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.enc_join[l], cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e.dfp_stream[l], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.dfp_fork[l], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e.dfp_join[l], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&e.lane_done[l], cudaEventDisableTiming) != cudaSuccess)
       return bail(fail(DPDF_ERR_CUDA, "lane stream creation failed"));
   if (cudaEventCreateWithFlags(&e.lane_fork, cudaEventDisableTiming) != cudaSuccess) return bail(fail(DPDF_ERR_CUDA, "event creation failed"));
@@ -364,6 +367,9 @@ extern "C" int dpdf_destroy(dpdf_engine* h) {
     if (e.br_join[l]) cudaEventDestroy(e.br_join[l]);
     if (e.enc_fork[l]) cudaEventDestroy(e.enc_fork[l]);
     if (e.enc_join[l]) cudaEventDestroy(e.enc_join[l]);
+    if (e.dfp_stream[l]) cudaStreamDestroy(e.dfp_stream[l]);
+    if (e.dfp_fork[l]) cudaEventDestroy(e.dfp_fork[l]);
+    if (e.dfp_join[l]) cudaEventDestroy(e.dfp_join[l]);
     if (e.lane_done[l]) cudaEventDestroy(e.lane_done[l]);
   }
   if (e.lane_fork) cudaEventDestroy(e.lane_fork);
@@ -435,6 +441,8 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     q.dw = sw.dw; q.pw = sw.pw; q.tc_pw = sw.tc_pw; q.bias = sw.b; q.out = out; q.Fin = Fin; q.Fout = Fout; q.stride = stride; q.up = up;
     return q;
   };
+  // latency batch sizes only: at throughput sizes the forked launch just competes for HBM (6.43 -> 6.45 ms at 16 384 streams)
+  const bool dfp_early = e.dfp_early && e.encoder_fork && !e.dfp_ps && std::max(B, e.total_B) < e.overlap_max;
   SepProblem dfc0{};
   dfc0.mode = 1; dfc0.dw = w.df_conv0_w; dfc0.pw = w.df_conv0_pw; dfc0.tc_pw = w.df_conv0_tc_pw; dfc0.bias = w.df_conv0_b;
   dfc0.Fin = NDF; dfc0.Fout = NDF; dfc0.stride = 1; dfc0.up = 1; dfc0.out = c.c0;
@@ -452,6 +460,22 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
       e.pdl_first = true;                                    // first kernel of the forked chain: its predecessor is an event
     }
     RUN("sepconv", sepconv(e, &dfc0, 1, B, sd)); ++n;
+    if (dfp_early) {
+      // The pathway term of the deep-filter coefficients needs nothing but the c0 ring df_conv0 has just pushed: it runs
+      // on a stream of its own beside the DPRNN stack (most SMs idle at latency batch sizes) instead of on the decoder
+      // tail, where it was 40 of the coefficient tail's 50 us at 1024 streams (profiles/r3f_chain_B1024.txt).
+      cudaStream_t sp = st;
+      if (fork) {
+        cudaEventRecord(e.dfp_fork[e.cur_lane], sd);
+        sp = e.dfp_stream[e.cur_lane];
+        cudaStreamWaitEvent(sp, e.dfp_fork[e.cur_lane], 0);
+        e.pdl_first = true;
+      } else {
+        sp = sd;
+      }
+      RUN("df_pathway", launch_df_pathway_early(e, B, sp)); ++n;
+      if (fork) cudaEventRecord(e.dfp_join[e.cur_lane], sp);
+    }
     e.pdl_first = false;
     SepProblem q = sepp(w.df_conv1, c.c0, nullptr, 0, c.c1, NDF, NDF / 2, 2, 1);
     RUN("sepconv", sepconv(e, &q, 1, B, sd)); ++n;
@@ -553,21 +577,26 @@ void enqueue_step(Engine& e, int B, cudaStream_t st) {
     sb = e.br_stream[e.cur_lane];
     cudaStreamWaitEvent(sb, e.br_fork[e.cur_lane], 0);
   }
+  GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc},
+                       {c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1},
+                       {c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
   {
     // The new GRU states are committed to the slot arena beside the decoder tails: nothing reads them before the next hop.
     // In the real chain of a 1024-stream hop (tools/chain_profile.py, profiles/r2L_chain_B1024.txt) the coefficient tail
     // - df_out linear 9 us + pathway conv 44 us - is the LONGER of the two (the three transposed convs + conv0_out add
     // 34 us), so the commit (7 us) rides on the main chain.
-    GRUProblem all[5] = {{c.g0, e.st.h_enc, H, w.enc_gru, c.henc},
-                         {c.x1, e.st.h_erb, 2 * H, w.erb_gru[0], c.herb1}, {c.x2, e.st.h_df, 2 * H, w.df_gru[0], c.hdf1},
-                         {c.herb1, e.st.h_erb + H, 2 * H, w.erb_gru[1], c.herb2}, {c.hdf1, e.st.h_df + H, 2 * H, w.df_gru[1], c.hdf2}};
-    RUN("gru_commit", launch_gru_commit(e, all, 5, B, st)); ++n;
+    // ... unless the pathway conv has left it (dfp_early): then the coefficient tail is a linear and an add, and takes the commit
+    if (!(dfp_early && fork)) { RUN("gru_commit", launch_gru_commit(e, all, 5, B, st)); ++n; }
     if (fork) e.pdl_first = true;                            // first kernel of the forked chain: its predecessor is an event, not a kernel
     GLProblem q = glp(w.df_out, c.cc, H, c.co, NDF * 2 * ORD, 2);
     RUN("gl", launch_gl(e, &q, 1, B, sb)); ++n;
     e.pdl_first = false;
   }
-  if (e.dfp_ps) { RUN("df_pathway", launch_df_pathway_ps(e, B, sb)); }
+  if (dfp_early) {
+    if (!e.timing) cudaStreamWaitEvent(sb, e.dfp_join[e.cur_lane], 0);
+    RUN("df_combine", launch_df_combine(e, B, sb));
+    if (fork) { RUN("gru_commit", launch_gru_commit(e, all, 5, B, sb)); ++n; }
+  } else if (e.dfp_ps) { RUN("df_pathway", launch_df_pathway_ps(e, B, sb)); }
   else { RUN("df_pathway", launch_df_pathway(e, B, sb)); }
   ++n;
   if (fork) cudaEventRecord(e.br_join[e.cur_lane], sb);
@@ -1257,6 +1286,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     drop_graphs(e);
   } else if (strcmp(key, "intra_pdl") == 0) {
     e.intra_pdl = value ? 1 : 0;
+    drop_graphs(e);
+  } else if (strcmp(key, "dfp_early") == 0) {
+    e.dfp_early = value ? 1 : 0;
     drop_graphs(e);
   } else if (strcmp(key, "intra_frag") == 0) {
     e.intra_frag = value ? 1 : 0;

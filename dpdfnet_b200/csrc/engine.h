@@ -49,7 +49,7 @@ struct Scratch {         // all [max_streams][...]
   float *hcat_e, *hcat_d;
   float *emb_e, *cemb, *g0, *henc, *emb;
   float *x1, *herb1, *herb2, *ed, *ed2;
-  float *x2, *hdf1, *hdf2, *cc, *co;
+  float *x2, *hdf1, *hdf2, *cc, *co, *dfp;     // dfp: pathway term of the df coefficients [96][10] (k_df_pathway early form)
   float *d3, *d2, *d1, *m;
   float *spec_tc, *yspec_tc;      // k_dft_tc: spectrum of the hop [spec_tc_ld], masked / filtered spectrum Y [yspec_tc_ld] (zero padded)
 };
@@ -115,6 +115,8 @@ void launch_sepconv_tma(Engine& e, const SepProblem* probs, int nprob, int B, cu
 bool sepconv_tma_available();
 void launch_conv0_out(Engine& e, int B, cudaStream_t st);
 void launch_df_pathway(Engine& e, int B, cudaStream_t st);
+void launch_df_pathway_early(Engine& e, int B, cudaStream_t st);   // pathway term alone -> Scratch::dfp
+void launch_df_combine(Engine& e, int B, cudaStream_t st);         // coefficient ring <- tanh(df_out) + Scratch::dfp
 void launch_df_pathway_ps(Engine& e, int B, cudaStream_t st);
 
 void launch_dprnn_intra(Engine& e, int blk, int B, cudaStream_t st);
@@ -200,6 +202,7 @@ struct Engine {
   int intra_tc_min = 640;         // measured (profiles/r2v_sweep.log, dpdfnet4 ms/hop FFMA2 vs tcgen05): 512 streams 0.763 / 0.800, 768 streams 1.114 / 0.866
   int intra_pdl = 0;              // sweep of block i >= 1 launched as a programmatic dependent of the previous block's post kernel (prologue under its tail)
   int intra_sr = 2;               // k_dprnn_intra_tc "split rows": the D rows of a stream carry the hi | lo operand halves, two MMA passes instead of three; 0 off, 1 whenever D > 1, 2 = with D = 4 only (measured)
+  int dfp_early = 0;              // df pathway conv on a forked stream right behind df_conv0 (needs encoder_fork), k_df_combine + gru_commit on the coefficient tail; measured +0.5..0.8 % hop time (the ERB tail is as long): off
   int intra_frag = 1;             // k_dprnn_intra_tc fragment form where the sweep runs 32 streams per CTA (intra_dup 4): two rows per stream, .16x128b TMEM fragments
   int intra_dup = 0;              // k_dprnn_intra_tc row duplication D (128 / D streams per CTA): 0 = auto (largest D whose sweep fits one wave), 1, 2, 4
   int gru_tc = 2;                 // GRUCell(256) gate GEMMs on tcgen05: 0 never, 1 always, 2 = when B >= gru_tc_min
@@ -236,6 +239,8 @@ struct Engine {
   // post kernel overlapped with the intra sweep: per-lane progress counters [lane][2][2][tiles]
   int decoder_fork = 1;           // run the deep-filter coefficient tail beside the ERB decoder's conv stack (forked stream)
   cudaStream_t br_stream[MAX_LANES] = {};
+  cudaStream_t dfp_stream[MAX_LANES] = {};          // the early df pathway conv (Engine::dfp_early) runs beside the DPRNN stack
+  cudaEvent_t dfp_fork[MAX_LANES] = {}, dfp_join[MAX_LANES] = {};
   cudaEvent_t br_fork[MAX_LANES] = {}, br_join[MAX_LANES] = {};
   int encoder_fork = 1;           // df encoder chain (df_conv0 -> df_conv1) on the forked stream beside erb_conv0..3
   cudaEvent_t enc_fork[MAX_LANES] = {}, enc_join[MAX_LANES] = {};

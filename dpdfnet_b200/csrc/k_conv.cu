@@ -310,12 +310,16 @@ struct DfPathParams {
   const float *w, *pw, *bias;   // [10][5][32], [10][10], [10]
   const float* co;              // [B][96][10] tanh(df_out)
   int B;
+  float* tmp;                   // [B][96][10] pathway term alone (k_df_pathway<.., true> -> k_df_combine)
 };
 
 // One warp = four consecutive bins of a stream; lane = (bin, 4-channel chunk).  Every load of the 5-frame c0 ring
 // is a fully used 128-byte line per bin, weights are broadcast float4 from shared memory, the 8 chunk-lanes of a
 // bin are reduced with xor shuffles.  HBM-bound on the ring (120 KB per stream-frame).
-template <bool RING16>       // c0 ring stored in half precision (option c0_fp16); a template so that the FP32 path costs nothing
+// EARLY = true: only the pathway term is computed and left in p.tmp - it depends on the c0 ring alone, so the launch sits
+// on a forked stream right behind df_conv0 and runs beside the DPRNN stack (which leaves most SMs idle at latency batch
+// sizes) instead of on the critical decoder tail; k_df_combine then adds tanh(df_out) and pushes the coefficient ring.
+template <bool RING16, bool EARLY = false>       // RING16: c0 ring stored in half precision (option c0_fp16); templates so that the FP32 path costs nothing
 __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
   pdl_trigger();
   __shared__ __align__(16) float ws[2 * ORD * 8 * 5 * 4];        // [g][kt][ci/4][o][4]
@@ -388,14 +392,45 @@ __global__ void __launch_bounds__(256) k_df_pathway(DfPathParams p) {
         float u = bs[oo];
 #pragma unroll
         for (int i = 0; i < 10; ++i) u = fmaf(pws[oo * 10 + i], t[i], u);
-        dst[oo] = warm ? 0.f : cop[oo] + fmaxf(u, 0.f);
+        if constexpr (EARLY) p.tmp[((size_t)b * NDF + f) * 10 + oo] = fmaxf(u, 0.f);
+        else dst[oo] = warm ? 0.f : cop[oo] + fmaxf(u, 0.f);
       }
     }
   }
 }
 
+// coefficient ring slot of this hop <- tanh(df_out) + pathway term (k_df_pathway<.., true>); thread = four coefficients
+__global__ void __launch_bounds__(256) k_df_combine(DfPathParams p) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int PER = NDF * 2 * ORD / 4;                     // float4 per stream
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)p.B * PER) return;
+  const int b = idx / PER, r = idx % PER;
+  const int slot = io_slot(p.io, b);
+  const int pos = p.st.pos[slot];
+  const bool warm = (io_flags(p.io, b) & DPDF_FLAG_WARMUP_) != 0;
+  const float4 a = *reinterpret_cast<const float4*>(p.co + (size_t)idx * 4), t = *reinterpret_cast<const float4*>(p.tmp + (size_t)idx * 4);
+  float4* dst = reinterpret_cast<float4*>(p.st.coef_ring + ((size_t)slot * 3 + pos % 3) * NDF * 10) + r;
+  *dst = warm ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(a.x + t.x, a.y + t.y, a.z + t.z, a.w + t.w);
+}
+
+void launch_df_pathway_early(Engine& e, int B, cudaStream_t st) {
+  DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B, e.sc.dfp};
+  const long long ctas = ((long long)B * (NDF / 4) + 7) / 8;
+  const unsigned grid = (unsigned)std::min<long long>(ctas, 4LL * e.num_sms);
+  if (e.st.c0_fp16) launch_k(e, k_df_pathway<true, true>, dim3(grid), dim3(256), 0, st, p);
+  else launch_k(e, k_df_pathway<false, true>, dim3(grid), dim3(256), 0, st, p);
+}
+
+void launch_df_combine(Engine& e, int B, cudaStream_t st) {
+  DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B, e.sc.dfp};
+  const long long total = (long long)B * (NDF * 2 * ORD / 4);
+  launch_k(e, k_df_combine, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, p);
+}
+
 void launch_df_pathway(Engine& e, int B, cudaStream_t st) {
-  DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B};
+  DfPathParams p{e.io_dev, e.st, e.w.dfp_w, e.w.dfp_pw, e.w.dfp_b, e.sc.co, B, nullptr};
   const long long ctas = ((long long)B * (NDF / 4) + 7) / 8;             // one item per warp ...
   const unsigned grid = (unsigned)std::min<long long>(ctas, 4LL * e.num_sms);   // ... or the four resident CTAs per SM (62 registers) walking the items
   if (e.st.c0_fp16) launch_k(e, k_df_pathway<true>, dim3(grid), dim3(256), 0, st, p);

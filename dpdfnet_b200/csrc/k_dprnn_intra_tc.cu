@@ -754,18 +754,21 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
       TL(1);
       const uint32_t pa = lane_base + TM_P + (t & 1) * 192 + 4 * cg;
       uint32_t ghn[4][2], gr[2][2][2], gz[2][2][2], gi[2][2][2];                  // [pair][e][hi row | lo row]
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) tmem_ld_16x128b_nowait(lane_base + TM_HN + 16 * ks + 4 * cg, ghn[ks][0], ghn[ks][1]);   // hn is single buffered: drain first
+      // the sigmoid stage of the first pair needs its r, z pre-activations only: wait for those four loads, then put
+      // everything else in flight under that math (hn is single buffered and is drained before the pair's hand-over)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         tmem_ld_16x128b_nowait(pa + 16 * e, gr[0][e][0], gr[0][e][1]);
         tmem_ld_16x128b_nowait(pa + 64 + 16 * e, gz[0][e][0], gz[0][e][1]);
-        tmem_ld_16x128b_nowait(pa + 128 + 16 * e, gi[0][e][0], gi[0][e][1]);
       }
       tmem_ld_wait();
       TL(2);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {                          // the second pair's pre-activations arrive under the first pair's math
+      for (int e = 0; e < 2; ++e) tmem_ld_16x128b_nowait(pa + 128 + 16 * e, gi[0][e][0], gi[0][e][1]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tmem_ld_16x128b_nowait(lane_base + TM_HN + 16 * ks + 4 * cg, ghn[ks][0], ghn[ks][1]);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
         tmem_ld_16x128b_nowait(pa + 32 + 16 * e, gr[1][e][0], gr[1][e][1]);
         tmem_ld_16x128b_nowait(pa + 64 + 32 + 16 * e, gz[1][e][0], gz[1][e][1]);
         tmem_ld_16x128b_nowait(pa + 128 + 32 + 16 * e, gi[1][e][0], gi[1][e][1]);
@@ -775,7 +778,6 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
       auto f2 = [](uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); };
 #pragma unroll
       for (int pp = 0; pp < 2; ++pp) {
-        if (pp == 1) tmem_ld_wait();
         const int hc0 = ((8 * pp + cg) ^ (srow & 15)) << 4, hc1 = ((8 * pp + 4 + cg) ^ (srow & 15)) << 4;      // staging chunks of the two units
         const float2 hp = make_float2(*reinterpret_cast<const float*>(prow + hc0), *reinterpret_cast<const float*>(prow + hc1));
         // pre-activation = hi-row accumulator + lo-row accumulator (+ bias); sigmoid / tanh with the exponent scales folded in
@@ -786,6 +788,7 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
         const float2 pq = __fmul2_rn(pr, pz);
         const float2 ip = make_float2(rcp_ftz(pq.x), rcp_ftz(pq.y));
         const float2 rr = __fmul2_rn(ip, pz), zz = __fmul2_rn(ip, pr);
+        if (pp == 0) tmem_ld_wait();
         const float2 vin = __fadd2_rn(__fadd2_rn(f2(gi[pp][0][0], gi[pp][1][0]), f2(gi[pp][0][1], gi[pp][1][1])), bp[16 * pp + 64]);
         const float2 vhn = __fadd2_rn(__fadd2_rn(f2(ghn[2 * pp][0], ghn[2 * pp + 1][0]), f2(ghn[2 * pp][1], ghn[2 * pp + 1][1])), bp[16 * pp + 96]);
         const float2 c = __ffma2_rn(rr, vhn, vin);
