@@ -736,7 +736,11 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
     }
   } else {
     // ---- the sweep (gate warps) -----------------------------------------------------------------------------------
-    const uint32_t lane_base = *tmem_slot + ((uint32_t)(qd * 32) << 16);
+    // TMEM addresses are warp-uniform operands: built from shuffled (provably uniform) values they live in uniform
+    // registers, otherwise every tcgen05.ld / st pays a register -> uniform-register move first
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const int cgu = warp_u >> 2;
+    const uint32_t lane_base = __shfl_sync(0xffffffffu, *tmem_slot, 0) + ((uint32_t)((warp_u & 3) * 32) << 16);
     const int nvalid = min(SPC, p.B - b0);
     auto write_out = [&](int s_) {
       const int f = dir ? T - 1 - s_ : s_;
@@ -745,14 +749,26 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
       if (r < nvalid) *reinterpret_cast<float4*>(hg + ((size_t)(b0 + r) * T + f) * 2 * C + dir * C + (tid & 15) * 4) = v;
     };
     const float2 one = make_float2(1.0f, 1.0f);
-    const float2* bp = reinterpret_cast<const float2*>(sb) + cg * 4 + j;          // + 16 p (+ 32 per gate)
+    float2 bias2[2][4];                                      // [pair][gate] of this thread's units: loop invariant
+    {
+      const float2* bp = reinterpret_cast<const float2*>(sb) + cg * 4 + j;        // + 16 p (+ 32 per gate)
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) bias2[pp][gt] = bp[16 * pp + 32 * gt];
+    }
+    // hi-row + lo-row accumulators of the pair's two units: scalar adds whose results the compiler places as an aligned
+    // register pair (a packed add of (hi, hi) + (lo, lo) needs four moves to form its operands first)
+    auto sum2 = [](const uint32_t (&a)[2], const uint32_t (&b)[2]) {
+      return make_float2(__uint_as_float(a[0]) + __uint_as_float(a[1]), __uint_as_float(b[0]) + __uint_as_float(b[1]));
+    };
     for (int t = 0; t < T; ++t) {
       TL(0);
       if (t + 2 < T) load_x(t + 2, xv);                      // in flight during the wait
       mbar_wait(bars + 1, t & 1);
       tc_fence_after();
       TL(1);
-      const uint32_t pa = lane_base + TM_P + (t & 1) * 192 + 4 * cg;
+      const uint32_t pa = lane_base + TM_P + (t & 1) * 192 + 4 * cgu;
       uint32_t ghn[4][2], gr[2][2][2], gz[2][2][2], gi[2][2][2];                  // [pair][e][hi row | lo row]
       // the sigmoid stage of the first pair needs its r, z pre-activations only: wait for those four loads, then put
       // everything else in flight under that math (hn is single buffered and is drained before the pair's hand-over)
@@ -766,7 +782,7 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
 #pragma unroll
       for (int e = 0; e < 2; ++e) tmem_ld_16x128b_nowait(pa + 128 + 16 * e, gi[0][e][0], gi[0][e][1]);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) tmem_ld_16x128b_nowait(lane_base + TM_HN + 16 * ks + 4 * cg, ghn[ks][0], ghn[ks][1]);
+      for (int ks = 0; ks < 4; ++ks) tmem_ld_16x128b_nowait(lane_base + TM_HN + 16 * ks + 4 * cgu, ghn[ks][0], ghn[ks][1]);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         tmem_ld_16x128b_nowait(pa + 32 + 16 * e, gr[1][e][0], gr[1][e][1]);
@@ -775,22 +791,25 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
       }
       unsigned char* srow_w = Ssm + (t & 1) * ST_BUF + srow * 256 + j * 4;
       const unsigned char* prow = Ssm + ((t + 1) & 1) * ST_BUF + srow * 256 + j * 4;      // h_{t-1} of this thread's units (FP32)
-      auto f2 = [](uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); };
-#pragma unroll
-      for (int pp = 0; pp < 2; ++pp) {
-        const int hc0 = ((8 * pp + cg) ^ (srow & 15)) << 4, hc1 = ((8 * pp + 4 + cg) ^ (srow & 15)) << 4;      // staging chunks of the two units
-        const float2 hp = make_float2(*reinterpret_cast<const float*>(prow + hc0), *reinterpret_cast<const float*>(prow + hc1));
-        // pre-activation = hi-row accumulator + lo-row accumulator (+ bias); sigmoid / tanh with the exponent scales folded in
-        const float2 ar = __fadd2_rn(__fadd2_rn(f2(gr[pp][0][0], gr[pp][1][0]), f2(gr[pp][0][1], gr[pp][1][1])), bp[16 * pp]);
-        const float2 az = __fadd2_rn(__fadd2_rn(f2(gz[pp][0][0], gz[pp][1][0]), f2(gz[pp][0][1], gz[pp][1][1])), bp[16 * pp + 32]);
+      // pre-activation = hi-row accumulator + lo-row accumulator (+ bias); sigmoid / tanh with the exponent scales folded in.
+      // Software pipeline: the sigmoid stage of the SECOND pair runs beside the tanh stage of the first (independent MUFU
+      // chains in one basic block), so after the first hand-over only the second pair's tanh stage is left - the math of a
+      // step is a dependent chain (ex2 -> rcp -> ex2 -> rcp), not an issue problem (profiles/r3k_*_rejected.txt).
+      auto sig_stage = [&](int pp, float2& rr, float2& zz) {
+        const float2 ar = __fadd2_rn(sum2(gr[pp][0], gr[pp][1]), bias2[pp][0]);
+        const float2 az = __fadd2_rn(sum2(gz[pp][0], gz[pp][1]), bias2[pp][1]);
         const float2 pr = __fadd2_rn(make_float2(ex2_ftz(fminf(ar.x, 60.f)), ex2_ftz(fminf(ar.y, 60.f))), one);
         const float2 pz = __fadd2_rn(make_float2(ex2_ftz(fminf(az.x, 60.f)), ex2_ftz(fminf(az.y, 60.f))), one);
         const float2 pq = __fmul2_rn(pr, pz);
         const float2 ip = make_float2(rcp_ftz(pq.x), rcp_ftz(pq.y));
-        const float2 rr = __fmul2_rn(ip, pz), zz = __fmul2_rn(ip, pr);
-        if (pp == 0) tmem_ld_wait();
-        const float2 vin = __fadd2_rn(__fadd2_rn(f2(gi[pp][0][0], gi[pp][1][0]), f2(gi[pp][0][1], gi[pp][1][1])), bp[16 * pp + 64]);
-        const float2 vhn = __fadd2_rn(__fadd2_rn(f2(ghn[2 * pp][0], ghn[2 * pp + 1][0]), f2(ghn[2 * pp][1], ghn[2 * pp + 1][1])), bp[16 * pp + 96]);
+        rr = __fmul2_rn(ip, pz);
+        zz = __fmul2_rn(ip, pr);
+      };
+      auto tanh_stage = [&](int pp, const float2 rr, const float2 zz) {
+        const int hc0 = ((8 * pp + cg) ^ (srow & 15)) << 4, hc1 = ((8 * pp + 4 + cg) ^ (srow & 15)) << 4;      // staging chunks of the two units
+        const float2 hp = make_float2(*reinterpret_cast<const float*>(prow + hc0), *reinterpret_cast<const float*>(prow + hc1));
+        const float2 vin = __fadd2_rn(sum2(gi[pp][0], gi[pp][1]), bias2[pp][2]);
+        const float2 vhn = __fadd2_rn(sum2(ghn[2 * pp], ghn[2 * pp + 1]), bias2[pp][3]);
         const float2 c = __ffma2_rn(rr, vhn, vin);
         const float2 pc = __fadd2_rn(make_float2(ex2_ftz(c.x), ex2_ftz(c.y)), one);
         const float2 q = make_float2(rcp_ftz(pc.x), rcp_ftz(pc.y));
@@ -798,27 +817,32 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
         const float2 hv = __ffma2_rn(zz, __fadd2_rn(hp, make_float2(-n.x, -n.y)), n);
         uint32_t hi, lo;
         split2_f16(hv.x, hv.y, hi, lo);
-        tmem_st_16x128b(lane_base + TM_HHI + 16 * pp + 4 * cg, hi, lo);
+        tmem_st_16x128b(lane_base + TM_HHI + 16 * pp + 4 * cgu, hi, lo);
         *reinterpret_cast<float*>(srow_w + hc0) = hv.x;
         *reinterpret_cast<float*>(srow_w + hc1) = hv.y;
-        if (pp == 0 && t > 0) write_out(t - 1);
-        if (pp == 1) {
-          if (t + 2 < T) store_x(t & 1, xv);                 // x_mma(t) (reader of this buffer) completed with the commit
-          TL(3);
-          TL(4);
-          fence_async_smem();                                // generic-proxy smem writes -> visible to the tensor core
-        }
-        tmem_st_wait();
-        if (t + 1 < T) {                                     // hand the pair's K slice over to the issuer, do not wait
-          tc_fence_before();
-          if (pp == 0) {
-            if (cg < 2) asm volatile("bar.arrive 1, 288;" ::: "memory");
-            else asm volatile("bar.arrive 2, 288;" ::: "memory");
-          } else {
-            if (cg < 2) asm volatile("bar.arrive 3, 288;" ::: "memory");
-            else asm volatile("bar.arrive 4, 288;" ::: "memory");
-          }
-        }
+      };
+      float2 rr0, zz0, rr1, zz1;
+      sig_stage(0, rr0, zz0);
+      tmem_ld_wait();
+      sig_stage(1, rr1, zz1);
+      tanh_stage(0, rr0, zz0);
+      tmem_st_wait();
+      if (t + 1 < T) {                                       // hand the first pair's K slices over to the issuer, do not wait
+        tc_fence_before();
+        if (cg < 2) asm volatile("bar.arrive 1, 288;" ::: "memory");
+        else asm volatile("bar.arrive 2, 288;" ::: "memory");
+      }
+      tanh_stage(1, rr1, zz1);
+      if (t > 0) write_out(t - 1);
+      if (t + 2 < T) store_x(t & 1, xv);                     // x_mma(t) (reader of this buffer) completed with the commit
+      TL(3);
+      TL(4);
+      fence_async_smem();                                    // generic-proxy smem writes -> visible to the tensor core
+      tmem_st_wait();
+      if (t + 1 < T) {
+        tc_fence_before();
+        if (cg < 2) asm volatile("bar.arrive 3, 288;" ::: "memory");
+        else asm volatile("bar.arrive 4, 288;" ::: "memory");
       }
     }
   }
