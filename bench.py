@@ -381,8 +381,9 @@ def roofline_blocks(spec, args, kt, B, ms_per_step):
         "bound": "tensor", "kernel": dom, "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dom_tf / peak_tf,
         "issued_frac": 3.0 * dom_tf / peak_tf, "algorithmic_macs_per_stream_launch": per_macs,
         "note": "FP32-equivalent algorithmic FLOPs; every MAC is issued as 3 FP16 tensor MACs (hi*hi + lo*hi + hi*lo); peak = measured dense bf16 burst. "
-                "issued_frac counts those 3 passes only: below 3 073 streams the df-branch sweep also duplicates every stream over D = 2 or 4 rows of "
-                "the M = 128 tile (same MMAs, identical rows), tensor work that buys latency and is not counted here"}
+                "issued_frac counts those 3 passes only: below 3 073 streams the df-branch sweep spreads every stream over D = 2 or 4 rows of "
+                "the M = 128 tile (same MMAs, identical rows), tensor work that buys latency and is not counted here; up to 1 792 streams it runs "
+                "in fragment form instead - 32 streams on 64 of the 128 rows (hi | lo operand halves), TWO passes per product"}
     roof_s = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
               "algorithmic_bytes_per_stream_frame": step_bytes}
     return roof, roof_t, roof_s
@@ -648,7 +649,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-ladder", action="store_true", help="skip the sustained-streams batch ladder")
     ap.add_argument("--no-extras", action="store_true", help="cfg1 only: skip the compact cfg2..cfg4 results")
-    ap.add_argument("--ladder", type=int, nargs="*", default=[8192, 16384, 20480, 22528, 23552, 24576])
+    ap.add_argument("--ladder", type=int, nargs="*", default=[8192, 16384, 20480, 22528, 23552, 24576, 25600])
     ap.add_argument("--stream-ladder", type=int, nargs="*", default=[1024, 2048, 3072, 4096, 4608, 5120, 5632])
     ap.add_argument("--stream-ticks", type=int, default=300)
     ap.add_argument("--many-ladder", type=int, nargs="*", default=[256, 1024], help="StreamEnhancer objects per process_many tick")

@@ -132,7 +132,7 @@ static int bind_weights(Engine& e) {
       x.tc_fc2_w = W(q + ".tc.fc2_w", C * C);
       x.tc_intra = W(q + ".tc.intra", 2 * 4 * 192 * C / 2);
       x.tc_intra_bias = W(q + ".tc.intra_bias", 2 * 4 * C);
-      if (br) {                                              // optional (blobs packed before the fragment form existed): absent = form off
+      {                                                      // optional (blobs packed before the fragment form existed): absent = form off
         auto it = e.wtable.find(q + ".tc.intra_f");
         x.tc_intra_f = it != e.wtable.end() && it->second.second == (size_t)(2 * 4 * 192 * C / 2) ? e.weights_dev + it->second.first : nullptr;
       }
@@ -673,12 +673,19 @@ static void drop_graphs(Engine& e) {
 // The overlapped post kernel and lanes exclude each other: post CTAs waiting for their sweep would
 // hold the SMs another lane's sweep needs.  Measured (profiles/r01O_lanes.log): one chain + overlap wins below 4096
 // streams, eight free-running lanes without overlap above.
+// Round 2: with the fragment-form sweep (k_dprnn_intra_tc.cu:intra_sweep_f, 32-stream CTAs, 70 us per launch) the
+// overlapped post kernel cannot keep up with its sweep any more and its spinning tiles only hold SMs: 128-stream lanes
+// without overlap win wherever that form runs (profiles/r3p_*, r3q_*, r3r_*: 1024 streams 0.743 -> 0.653 ms per hop, lock-step
+// p50 0.748 -> 0.717 ms; Engine::overlap = 2 forces the overlap there too).
 static bool overlap_applies(const Engine& e, int B) {
-  return e.overlap && e.post_tc && (e.intra_tc == 1 || (e.intra_tc == 2 && B >= e.intra_tc_min)) && B < e.overlap_max && e.lanes <= 1;
+  const bool tc = e.post_tc && (e.intra_tc == 1 || (e.intra_tc == 2 && B >= e.intra_tc_min));
+  if (!e.overlap || !tc || B >= e.overlap_max || e.lanes > 1) return false;
+  if (e.overlap == 1 && e.lanes != 1 && e.intra_frag && intra_tc_dup(e, B) == 4) return false;
+  return true;
 }
 static int lanes_for(const Engine& e, int B) {
   if (overlap_applies(e, B)) return 1;
-  int L = e.lanes > 0 ? e.lanes : (B >= 2048 ? 8 : (B >= 1024 ? 4 : 1));   // measured: profiles/r01B_lanes.log
+  int L = e.lanes > 0 ? e.lanes : (B >= 640 ? 8 : 1);      // measured: profiles/r01B_lanes.log, r3q_sweep_overlap_1024.log
   L = std::min(L, Engine::MAX_LANES);
   while (L > 1 && B / L < 128) --L;
   return std::max(L, 1);
@@ -1290,6 +1297,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "dfp_early") == 0) {
     e.dfp_early = value ? 1 : 0;
     drop_graphs(e);
+  } else if (strcmp(key, "intra_frag_erb") == 0) {
+    e.intra_frag_erb = value ? 1 : 0;
+    drop_graphs(e);
   } else if (strcmp(key, "intra_frag") == 0) {
     e.intra_frag = value ? 1 : 0;
     drop_graphs(e);
@@ -1329,7 +1339,7 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     e.pdl = value;
     drop_graphs(e);
   } else if (strcmp(key, "overlap") == 0 || strcmp(key, "overlap_max") == 0) {
-    if (key[7] == 0) e.overlap = value ? 1 : 0;
+    if (key[7] == 0) e.overlap = value < 0 ? 0 : (value > 2 ? 2 : value);
     else e.overlap_max = value;
     drop_graphs(e);
   } else if (strcmp(key, "free_lanes") == 0) {

@@ -95,7 +95,7 @@ struct IntraTcParams {
   float* hcat[2];         // [B][Fp][128]
   int Fp[2];
   const float* wimg[2];   // [2 dirs][W_ih hi | W_ih lo | W_hh hi | W_hh lo] FP16 operand images
-  const float* wimg_f;    // df branch, fragment form: the same with the K axis of W_hh in the order of intra_sweep_f (weights.py: tc.intra_f)
+  const float* wimg_f[2]; // fragment form: the same with the K axis of W_hh in the order of intra_sweep_f (weights.py: tc.intra_f)
   const float* bias[2];   // [2][4][64], exponent scales folded in (weights.py: tc.intra_bias)
   int tiles[2];           // stream tiles of the sweep per branch: ceil(B / (128 / D)) with the branch's row duplication D
   int B;
@@ -578,6 +578,7 @@ __device__ __forceinline__ void tmem_st_16x128b(uint32_t taddr, uint32_t r0, uin
 // shuffle at all: thread (i, j) packs its units of slices 2p and 2p + 1 (16 (2p + e) + 4 cg + j, e = 0, 1) into ONE operand
 // column 16 p + 4 cg + j (two K halves), the hi word to row i and the lo word to row 8 + i.  The recurrent matrix is
 // packed with its K axis in that order (weights.py: tc.intra_f).  The gate math of a pair runs on packed f32x2 lanes.
+template <int BR>      // branch: 0 = df, 1 = erb (worth it for the 48 kHz models only, whose erb sweep has 40 positions against 8)
 __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int dir, const int tile) {
   constexpr int SPC = 32;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -592,10 +593,10 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
   const int qd = warp & 3, cg = warp >> 2;
   const int si = lane >> 2, j = lane & 3;                    // stream of the quadrant, unit of the cg group
   const int srow = qd * 8 + si;                              // the stream's row in the staging tiles
-  const int T = p.Fp[0];
+  const int T = p.Fp[BR];
   const int b0 = tile * SPC;
-  const float* __restrict__ xg = p.x[0];
-  float* __restrict__ hg = p.hcat[0];
+  const float* __restrict__ xg = p.x[BR];
+  float* __restrict__ hg = p.hcat[BR];
 
   if (tid == 0) {
     mbar_init(bars, 1);
@@ -605,14 +606,14 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   if (tid < 256) {                                           // biases of a pair's two units side by side: [gate][p][cg][j][e]
     const int u = tid & 63, ks = u >> 4;
-    sb[(tid >> 6) * C + (((ks >> 1) * 4 + ((u >> 2) & 3)) * 4 + (u & 3)) * 2 + (ks & 1)] = __ldg(p.bias[0] + dir * 4 * C + tid);
+    sb[(tid >> 6) * C + (((ks >> 1) * 4 + ((u >> 2) & 3)) * 4 + (u & 3)) * 2 + (ks & 1)] = __ldg(p.bias[BR] + dir * 4 * C + tid);
   }
   for (int i = tid; i < ST_BUF / 16; i += ITC_NT) reinterpret_cast<uint4*>(Ssm + ST_BUF)[i] = make_uint4(0u, 0u, 0u, 0u);   // h_{-1} = 0
   for (int i = tid; i < 4 * A_IMG / 16; i += ITC_NT) reinterpret_cast<uint4*>(Xsm)[i] = make_uint4(0u, 0u, 0u, 0u);        // idle operand rows stay 0
-  auto progress_ptr = [&]() -> int* { return p.progress ? p.progress + dir * p.tiles[0] + tile : nullptr; };
+  auto progress_ptr = [&]() -> int* { return p.progress ? p.progress + (BR ? 2 * p.tiles[0] + dir * p.tiles[1] : dir * p.tiles[0]) + tile : nullptr; };
   __syncthreads();                                           // barriers initialised
   if (tid == 0) {
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wimg_f) + (size_t)dir * 4 * W_IMG;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wimg_f[BR]) + (size_t)dir * 4 * W_IMG;
     mbar_expect_tx(bars, 4 * W_IMG);
 #pragma unroll
     for (int i = 0; i < 4; ++i) bulk_g2s(Wsm + i * W_IMG, src + (size_t)i * W_IMG, W_IMG, bars);
@@ -867,7 +868,7 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
 // Grid = df CTAs (2 directions x tiles[0]) followed by erb CTAs.  The erb sweep has F'e = 8 positions against the df
 // sweep's 48, so it is never the critical path: it keeps full 128-stream tiles (DERB = 1) while the df branch is
 // split DDF ways, which leaves more SMs to the overlapped post kernel than duplicating both branches.
-template <int DDF, int DERB, int FORM = 0>      // FORM of the df sweep: 0 = D copies of a row, 1 = split rows, 2 = fragment form (32 streams)
+template <int DDF, int DERB, int FORM = 0, int FORM_E = 0>      // FORM of the df / erb sweep: 0 = D copies of a row, 1 = split rows, 2 = fragment form (32 streams)
 #ifdef ITC_MAXNREG
 __global__ void __maxnreg__(ITC_MAXNREG) k_dprnn_intra_tc(const __grid_constant__ IntraTcParams p) {
 #else
@@ -877,10 +878,12 @@ __global__ void __launch_bounds__(ITC_NT, 1) k_dprnn_intra_tc(const __grid_const
   // two inlined copies of the sweep even for DDF == DERB: the branch index is then a compile-time constant in each
   // (one generic copy costs the gate warps live registers: 56 instead of 16 bytes of spills)
   if (item < ndf) {
-    if constexpr (FORM == 2) intra_sweep_f(p, item / p.tiles[0], item % p.tiles[0]);
+    if constexpr (FORM == 2) intra_sweep_f<0>(p, item / p.tiles[0], item % p.tiles[0]);
     else intra_sweep<DDF, FORM == 1>(p, 0, item / p.tiles[0], item % p.tiles[0]);
+  } else {
+    if constexpr (FORM_E == 2) intra_sweep_f<1>(p, (item - ndf) / p.tiles[1], (item - ndf) % p.tiles[1]);
+    else intra_sweep<DERB>(p, 1, (item - ndf) / p.tiles[1], (item - ndf) % p.tiles[1]);
   }
-  else intra_sweep<DERB>(p, 1, (item - ndf) / p.tiles[1], (item - ndf) % p.tiles[1]);
 }
 
 // Row duplication factor of the df-branch sweep for a step of B streams (Engine::intra_dup = 0: auto); the erb branch
@@ -892,9 +895,21 @@ int intra_tc_dup(const Engine& e, int B) {
   if (e.intra_dup == 1 || e.intra_dup == 2 || e.intra_dup == 4) return e.intra_dup;
   const int Bt = std::max(B, e.total_B);                     // lanes run their sweeps side by side
   auto ctas = [&](int D) { return 2 * ((Bt * D + 127) / 128) + 2 * ((Bt + 127) / 128); };
-  if (ctas(4) <= e.num_sms * 2 / 3) return 4;
+  // the fragment form's 32-stream CTAs (intra_frag) win for as long as the sweep fits ONE wave (profiles/r3n_*: 1280 / 1536 /
+  // 1792 streams 0.828 / 0.914 / 1.013 ms per hop against 0.895 / 0.952 / 1.021 with D = 2)
+  if (ctas(4) <= (e.intra_frag ? e.num_sms : e.num_sms * 2 / 3)) return 4;
   if (ctas(2) <= e.num_sms) return 2;
   return 1;
+}
+
+// Row count per stream of the ERB-branch sweep: 1, or 4 = fragment form (32 streams per CTA) for the 48 kHz models, whose erb
+// sweep has 40 positions - with 128-stream tiles (5 700 cycles per step) it outlasts the df sweep's 48 fragment-form steps -
+// while both branches' CTAs still fit one wave.
+int intra_tc_dup_erb(const Engine& e, int B) {
+  if (!e.intra_frag || !e.intra_frag_erb || e.d.fe[3] < 16 || intra_tc_dup(e, B) != 4) return 1;
+  if (e.d.N == 0 || !e.w.dprnn_df[0].tc_intra_f || !e.w.dprnn_erb[0].tc_intra_f) return 1;      // blob packed before the form existed
+  const int Bt = std::max(B, e.total_B);
+  return 4 * ((Bt * 4 + 127) / 128) <= e.num_sms ? 4 : 1;
 }
 
 void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
@@ -909,14 +924,17 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.wimg[1] = e.w.dprnn_erb[blk].tc_intra; p.bias[1] = e.w.dprnn_erb[blk].tc_intra_bias;
   p.B = B;
   const int D = intra_tc_dup(e, B);
+  const int DE = intra_tc_dup_erb(e, B);
   p.tiles[0] = (B * D + 127) / 128;
-  p.tiles[1] = (B + 127) / 128;
+  p.tiles[1] = (B * DE + 127) / 128;
   p.progress = e.overlap_now ? e.progress_dev + (size_t)e.cur_lane * 4 * e.progress_tiles : nullptr;
   p.err = e.err_dev;
   const dim3 grid(2 * (p.tiles[0] + p.tiles[1]));
   const bool sr = e.intra_sr == 1 ? D > 1 : (e.intra_sr == 2 && D == 4);    // auto: where the step is tensor bound (profiles/r3b_*)
-  p.wimg_f = e.w.dprnn_df[blk].tc_intra_f;
-  if (D == 4 && e.intra_frag && p.wimg_f) launch_k(e, k_dprnn_intra_tc<4, 1, 2>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  p.wimg_f[0] = e.w.dprnn_df[blk].tc_intra_f;
+  p.wimg_f[1] = e.w.dprnn_erb[blk].tc_intra_f;
+  if (D == 4 && e.intra_frag && p.wimg_f[0] && DE == 4 && p.wimg_f[1]) launch_k(e, k_dprnn_intra_tc<4, 4, 2, 2>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  else if (D == 4 && e.intra_frag && p.wimg_f[0]) launch_k(e, k_dprnn_intra_tc<4, 1, 2>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else if (D == 4 && sr) launch_k(e, k_dprnn_intra_tc<4, 1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else if (D == 2 && sr) launch_k(e, k_dprnn_intra_tc<2, 1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else if (D == 4) launch_k(e, k_dprnn_intra_tc<4, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
@@ -931,6 +949,7 @@ void init_dprnn_intra_tc_kernels() {
   cudaFuncSetAttribute(k_dprnn_intra_tc<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
   cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
   cudaFuncSetAttribute(k_dprnn_intra_tc<4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
+  cudaFuncSetAttribute(k_dprnn_intra_tc<4, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INTRA_TC_SMEM);
 }
 
 }  // namespace dpdf

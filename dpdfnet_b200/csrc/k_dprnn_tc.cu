@@ -67,7 +67,8 @@ struct PostTcParams {
                           // the branches, which have different weights; the padding tile has no valid rows)
   const int* progress;    // sweep counters [df: 2 dirs x ptiles | erb: 2 dirs x stiles], nullptr = row-major tiles of a finished sweep
   int stiles;             // ceil(B / 128)
-  int dup, ptiles;        // the df sweep's CTAs own 128 / dup streams each: ptiles = ceil(B * dup / 128) counters per direction (erb: dup = 1)
+  int dup, ptiles;        // the df sweep's CTAs own 128 / dup streams each: ptiles = ceil(B * dup / 128) counters per direction
+  int dup_e, ptiles_e;    // the same for the erb sweep (1, or 4 in fragment form: intra_tc_dup_erb)
   int* ctr;               // k_dprnn_post_res: [0] next df tile, [1] next erb tile, [2] CTAs that have finished (the last one zeroes all three)
   int ctas_erb;           // k_dprnn_post_res: CTAs [0, ctas_erb) serve the erb branch, the others the df branch
   int pf_dist;            // row-major mode: warm L2 with the inputs of tile blockIdx.x + pf_dist (0 = off); CTAs are dispatched in
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 2 * TC_NT : TC_NT, MODE == 2 ? 1 :
     const int stile = (tile - (bi ? 0 : p.tiles1)) % p.stiles, T = q.Fp;
     if (tid == 0 && valid > 0) {
       // the sweep CTAs this tile's 128 streams come from: dup per direction (branch index as in the intra kernel: 0 = df, 1 = erb)
-      const int dup = bi ? 1 : p.dup, pt = bi ? p.stiles : p.ptiles;
+      const int dup = bi ? p.dup_e : p.dup, pt = bi ? p.ptiles_e : p.ptiles;
       const volatile int* fw = p.progress + (bi ? 2 * p.ptiles : 0) + stile * dup;
       const volatile int* bw = fw + pt;
       const int nsrc = min(dup, pt - stile * dup);
@@ -1015,6 +1016,8 @@ void launch_dprnn_post_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.stiles = (B + 127) / 128;
   p.dup = intra_tc_dup(e, B);
   p.ptiles = (B * p.dup + 127) / 128;
+  p.dup_e = intra_tc_dup_erb(e, B);
+  p.ptiles_e = (B * p.dup_e + 127) / 128;
   p.tiles1 = even(p.stiles * e.d.fe[3]);
   p.tiles0 = even(p.stiles * (NDF / 2));
   cfg.gridDim = dim3((unsigned)(p.tiles0 + p.tiles1));

@@ -339,7 +339,7 @@ def pack_tensors(spec: ModelSpec, sd: Mapping[str, np.ndarray]) -> "OrderedDict[
             gscale = np.repeat(np.array([-LOG2E, -LOG2E, 2.0 * LOG2E]), C).astype(np.float32)[:, None]
             t[f"{q}.tc.intra"] = np.concatenate([
                 umma_operand16(sd[f"{p}.intra_gru.{m}_l0{sfx}"] * gscale) for sfx in ("", "_reverse") for m in ("weight_ih", "weight_hh")])
-            if br == "df":
+            if True:
                 # fragment form of the sweep (k_dprnn_intra_tc.cu:intra_sweep_f): the thread of unit (cg, j) packs its units
                 # of K slices 2p and 2p + 1 into ONE operand column 16 p + 4 cg + j, so K element k = 2 c + e of the
                 # recurrent product is hidden unit 16 (2 p + e) + 4 cg + j; W_ih is unchanged

@@ -157,7 +157,7 @@ def test_intra_tc_multi_tile(torch_cuda, name, B):
 
 
 @pytest.mark.parametrize("overlap", [0, 1])
-@pytest.mark.parametrize("name,B", [("dpdfnet2", 200), ("dpdfnet4", 330)])
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 200), ("dpdfnet4", 330), ("dpdfnet2_48khz_hr", 70)])
 def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
     """tcgen05 intra-GRU kernel with 128 / D streams per CTA (D rows of the MMA tile per stream, the gate math split
     over the D partner threads): D = 1, 2, 4 run the same arithmetic, so they must agree bit for bit, on ragged last
@@ -168,7 +168,7 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
     rng = np.random.default_rng(31)
     pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
     outs = {}
-    for D in (1, 2, 4, 0, "2sr", "4sr", "4f"):
+    for D in (1, 2, 4, 0, "2sr", "4sr", "4f", "4fe"):
         eng = _engine(name, 4, B)
         eng.set_option("intra_tc", 1)
         eng.set_option("overlap", overlap)
@@ -180,7 +180,8 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
         # of a stream's four gate threads its own column of both rows, K axis of W_hh permuted on the host
         if D != 0:                                          # 0: the engine's own choice of form
             eng.set_option("intra_sr", 1 if D in ("2sr", "4sr") else 0)
-            eng.set_option("intra_frag", 1 if D == "4f" else 0)
+            eng.set_option("intra_frag", 1 if D in ("4f", "4fe") else 0)
+            eng.set_option("intra_frag_erb", 1 if D == "4fe" else 0)        # erb sweep in fragment form too (48 kHz models only)
         eng.set_option("intra_dup", int(D[0]) if isinstance(D, str) else D)
         outs[D] = (eng.run_pcm_host(pcm), eng.debug_tensor("xd", B), eng.state_export(B - 1))
         eng.close()
@@ -189,14 +190,14 @@ def test_intra_tc_row_duplication(torch_cuda, name, B, overlap):
             assert np.array_equal(a, b), D
     for a, b in zip(outs[0], outs[1]):                      # the auto choice may be a split-row form
         assert np.abs(a - b).max() < 2e-5
-    for D in ("2sr", "4sr", "4f"):
+    for D in ("2sr", "4sr", "4f", "4fe"):
         assert np.abs(outs[D][0] - outs[1][0]).max() < 2e-6, D
         assert np.abs(outs[D][1] - outs[1][1]).max() < 2e-5, D
         assert np.abs(outs[D][2] - outs[1][2]).max() < 2e-5, D
     ora = _oracle(name, 4, B)
     ref = np.concatenate([ora.step_pcm(pcm[:, t * hop:(t + 1) * hop]) for t in range(T)], 1)
     N = get_spec(name).n_blocks
-    for D in (4, "2sr", "4sr", "4f"):
+    for D in (4, "2sr", "4sr", "4f", "4fe"):
         assert np.abs(outs[D][0] - ref).max() < WAVE_TOL, D
         assert np.abs(outs[D][1] - np.asarray(ora.dbg[f"xd{N - 1}"]).reshape(B, -1)).max() < 2e-4, D
     with pytest.raises(ValueError):

@@ -29,7 +29,7 @@ int main(int argc, char** argv) {
   cudaMemset(tl, 0, T * 12 * 8);
   IntraTcParams p{};
   p.x[0] = p.x[1] = x; p.hcat[0] = p.hcat[1] = hcat; p.Fp[0] = T; p.Fp[1] = 8;
-  p.wimg[0] = p.wimg[1] = w; p.wimg_f = w; p.bias[0] = p.bias[1] = bias; p.B = B; p.tiles[0] = (B * ITC_DUP + 127) / 128; p.tiles[1] = (B + 127) / 128;
+  p.wimg[0] = p.wimg[1] = w; p.wimg_f[0] = p.wimg_f[1] = w; p.bias[0] = p.bias[1] = bias; p.B = B; p.tiles[0] = (B * ITC_DUP + 127) / 128; p.tiles[1] = (B + 127) / 128;
 #ifdef ITC_TIMELINE
   p.tl = tl;
 #endif

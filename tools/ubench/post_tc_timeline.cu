@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../../dpdfnet_b200/csrc/k_dprnn_tc.cu"
-namespace dpdf { int intra_tc_dup(const Engine&, int) { return 1; } }   // the launcher (unused here) refers to it
+namespace dpdf { int intra_tc_dup(const Engine&, int) { return 1; } int intra_tc_dup_erb(const Engine&, int) { return 1; } }   // the launcher (unused here) refers to it
 
 int main(int argc, char** argv) {
   using namespace dpdf;
