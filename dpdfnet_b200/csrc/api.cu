@@ -685,7 +685,8 @@ static bool overlap_applies(const Engine& e, int B) {
 }
 static int lanes_for(const Engine& e, int B) {
   if (overlap_applies(e, B)) return 1;
-  int L = e.lanes > 0 ? e.lanes : (B >= 640 ? 8 : 1);      // measured: profiles/r01B_lanes.log, r3q_sweep_overlap_1024.log
+  // measured: profiles/r01B_lanes.log, r3q_sweep_overlap_1024.log, r3v_sweep_frag_lanes_big.log
+  int L = e.lanes > 0 ? e.lanes : (B < 640 ? 1 : ((B >= 2560 && e.intra_frag && intra_tc_dup(e, B) == 4) ? 4 : 8));
   L = std::min(L, Engine::MAX_LANES);
   while (L > 1 && B / L < 128) --L;
   return std::max(L, 1);
@@ -1296,6 +1297,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     drop_graphs(e);
   } else if (strcmp(key, "dfp_early") == 0) {
     e.dfp_early = value ? 1 : 0;
+    drop_graphs(e);
+  } else if (strcmp(key, "frag_max") == 0) {
+    e.frag_max = value;
     drop_graphs(e);
   } else if (strcmp(key, "intra_frag_erb") == 0) {
     e.intra_frag_erb = value ? 1 : 0;

@@ -204,6 +204,7 @@ struct Engine {
   int intra_pdl = 0;              // sweep of block i >= 1 launched as a programmatic dependent of the previous block's post kernel (prologue under its tail)
   int intra_sr = 2;               // k_dprnn_intra_tc "split rows": the D rows of a stream carry the hi | lo operand halves, two MMA passes instead of three; 0 off, 1 whenever D > 1, 2 = with D = 4 only (measured)
   int dfp_early = 0;              // df pathway conv on a forked stream right behind df_conv0 (needs encoder_fork), k_df_combine + gru_commit on the coefficient tail; measured +0.5..0.8 % hop time (the ERB tail is as long): off
+  int frag_max = 6144;            // largest step (streams, all lanes) whose sweeps run in fragment form
   int intra_frag_erb = 1;         // ... and for the erb branch of the 48 kHz models while both sweeps fit one wave (intra_tc_dup_erb)
   int intra_frag = 1;             // k_dprnn_intra_tc fragment form where the sweep runs 32 streams per CTA (intra_dup 4): two rows per stream, .16x128b TMEM fragments
   int intra_dup = 0;              // k_dprnn_intra_tc row duplication D (128 / D streams per CTA): 0 = auto (largest D whose sweep fits one wave), 1, 2, 4

@@ -895,9 +895,14 @@ int intra_tc_dup(const Engine& e, int B) {
   if (e.intra_dup == 1 || e.intra_dup == 2 || e.intra_dup == 4) return e.intra_dup;
   const int Bt = std::max(B, e.total_B);                     // lanes run their sweeps side by side
   auto ctas = [&](int D) { return 2 * ((Bt * D + 127) / 128) + 2 * ((Bt + 127) / 128); };
-  // the fragment form's 32-stream CTAs (intra_frag) win for as long as the sweep fits ONE wave (profiles/r3n_*: 1280 / 1536 /
-  // 1792 streams 0.828 / 0.914 / 1.013 ms per hop against 0.895 / 0.952 / 1.021 with D = 2)
-  if (ctas(4) <= (e.intra_frag ? e.num_sms : e.num_sms * 2 / 3)) return 4;
+  // The fragment form's 32-stream CTAs (intra_frag) win well beyond one wave of them, because the step then runs as lanes
+  // (api.cu:lanes_for) whose sweeps are separate launches that rarely coincide (profiles/r3n_*, r3v_*: 2048 / 3072 / 4096
+  // streams 1.01 / 1.44 / 1.83 ms per hop against 1.12 / 1.52 / 1.91 with D = 2 / 1 and the overlapped post kernel, r3w_*: 5120 /
+  // 6144 streams 2.24 / 2.64 against 2.40 / 2.75; at 8192 streams the 128-stream tiles are back in front, 3.36 against 3.49 ms).
+  // (48 kHz models: their separable convs keep the SMs busier, the cross-over is lower - StreamGroup ticks of dpdfnet8_48khz_hr
+  // at 4096 / 4608 / 5120 streams 7.4 / 8.9 / 10.4 ms in fragment form against 7.8 / 8.6 / 9.2, profiles/r3X_bench.json)
+  if (e.intra_frag && Bt <= (e.d.hr48 ? std::min(e.frag_max, 4096) : e.frag_max)) return 4;
+  if (ctas(4) <= e.num_sms * 2 / 3) return 4;
   if (ctas(2) <= e.num_sms) return 2;
   return 1;
 }
@@ -908,8 +913,7 @@ int intra_tc_dup(const Engine& e, int B) {
 int intra_tc_dup_erb(const Engine& e, int B) {
   if (!e.intra_frag || !e.intra_frag_erb || e.d.fe[3] < 16 || intra_tc_dup(e, B) != 4) return 1;
   if (e.d.N == 0 || !e.w.dprnn_df[0].tc_intra_f || !e.w.dprnn_erb[0].tc_intra_f) return 1;      // blob packed before the form existed
-  const int Bt = std::max(B, e.total_B);
-  return 4 * ((Bt * 4 + 127) / 128) <= e.num_sms ? 4 : 1;
+  return std::max(B, e.total_B) <= e.frag_max / 3 ? 4 : 1;    // profiles/r3w_*: dpdfnet8_48khz_hr 2048 streams 3.24 -> 3.02 ms, 4096 streams 5.71 -> 5.79
 }
 
 void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {

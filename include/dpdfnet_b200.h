@@ -138,7 +138,7 @@ int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the la
  * "decoder_fork" 0/1 decoder tails on forked streams; "intra_tc" / "sep_tc" / "gru_tc" 0 FFMA2 / 1 tcgen05 / 2 by batch
  * size (+ "intra_tc_min"); "intra_dup" 0 auto / 1 / 2 / 4 rows per stream in the tcgen05 intra-GRU tile (128 / D streams
  * per CTA); "intra_frag" 0/1 fragment form of that kernel where it runs 32 streams per CTA (two rows per stream, .16x128b
- * TMEM fragments; on); "intra_sr" 0 / 1 / 2 split rows (hi | lo operand halves in the D rows of a stream, two MMA passes) never /
+ * TMEM fragments; on, up to "frag_max" = 6 144 streams per step); "intra_sr" 0 / 1 / 2 split rows (hi | lo operand halves in the D rows of a stream, two MMA passes) never /
  * whenever D > 1 / with D = 4 only when the fragment form is off (default 2); "dfp_early" 0/1 df pathway conv on a forked
  * stream behind df_conv0 + k_df_combine (measured slower, off); "sep_tma" 0/1 tensor-core separable convs as the persistent TMA-fed kernel; "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel; "c0_fp16" 0/1 c0 ring stored in half precision (switch only on freshly reset streams); "ana_nb" / "syn_sb" caps on the
  * streams per CTA of the analysis / synthesis kernels ("ana_force" / "syn_force" force a count, experiments only); "post_pf" L2 prefetch distance of the post kernel; "dfp_ps" 0/1

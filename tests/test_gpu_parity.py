@@ -325,6 +325,32 @@ def test_dft_on_tensor_cores(torch_cuda, name, B):
     assert np.abs(outs[1][0][:8] - ref).max() < WAVE_TOL
 
 
+@pytest.mark.parametrize("name,B", [("dpdfnet2", 300), ("dpdfnet2_48khz_hr", 70)])
+def test_schedule_options_do_not_change_the_arithmetic(torch_cuda, name, B):
+    """Options that only move kernels around - the df pathway conv on a forked stream behind df_conv0 with k_df_combine on
+    the tail (dfp_early), the overlapped post kernel forced on where lanes are the default (overlap = 2), lanes, the GRU
+    cells' unit chunk - must reproduce the default schedule bit for bit, state included, warm-up frames included."""
+    T = 5
+    hop = get_spec(name).hop
+    rng = np.random.default_rng(77)
+    pcm = (rng.standard_normal((B, T * hop)) * 0.1).astype(np.float32)
+    flags = np.zeros(B, np.int32)
+    flags[::3] = 1                                                  # DPDF_FLAG_WARMUP rows: the coefficient ring gets zeros
+    outs = []
+    for opts in ({}, {"dfp_early": 1}, {"dfp_early": 1, "lanes": 2}, {"overlap": 2}, {"lanes": 1, "overlap": 0}, {"gru_uc": 64}):
+        eng = _engine(name, 9, B)
+        for k in ("intra_tc", "post_tc", "sep_tc", "gru_tc"):
+            eng.set_option(k, 1)
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        a = np.concatenate([eng.step_pcm_host(pcm[:, t * hop:(t + 1) * hop], flags=flags if t == 0 else None) for t in range(T)], 1)
+        outs.append((a, eng.state_export(B - 1), eng.state_export(0)))
+        eng.close()
+    for o in outs[1:]:
+        for x, y in zip(o, outs[0]):
+            assert np.array_equal(x, y)
+
+
 @pytest.mark.parametrize("intra_tc", [0, 1])
 def test_lanes_match_single_chain(torch_cuda, intra_tc):
     """A batched step split into lanes (row ranges running as forked kernel chains inside one CUDA graph) must give
