@@ -686,7 +686,8 @@ static bool overlap_applies(const Engine& e, int B) {
 static int lanes_for(const Engine& e, int B) {
   if (overlap_applies(e, B)) return 1;
   // measured: profiles/r01B_lanes.log, r3q_sweep_overlap_1024.log, r3v_sweep_frag_lanes_big.log
-  int L = e.lanes > 0 ? e.lanes : (B < 640 ? 1 : ((B >= 2560 && e.intra_frag && intra_tc_dup(e, B) == 4) ? 4 : 8));
+  // r4b_sweep_intra_tc_tiny.log (256 / 384 / 512 / 640 streams: one lane 0.58 / 0.60 / 0.65 / 0.68 ms per hop, 128-stream lanes 0.51 / 0.54 / 0.56 / 0.59)
+  int L = e.lanes > 0 ? e.lanes : (B < 256 ? 1 : ((B >= 2560 && e.intra_frag && intra_tc_dup(e, B) == 4) ? 4 : 8));
   L = std::min(L, Engine::MAX_LANES);
   while (L > 1 && B / L < 128) --L;
   return std::max(L, 1);

@@ -200,7 +200,7 @@ struct Engine {
   int use_graph = 1;
   int intra_bt = 0;               // 0 = auto
   int intra_tc = 2;               // intra-frame GRU on tcgen05 (FP16 split): 0 never, 1 always, 2 = when B >= intra_tc_min
-  int intra_tc_min = 640;         // measured (profiles/r2v_sweep.log, dpdfnet4 ms/hop FFMA2 vs tcgen05): 512 streams 0.763 / 0.800, 768 streams 1.114 / 0.866
+  int intra_tc_min = 1;           // with the fragment form (32-stream CTAs) the tcgen05 sweep wins at every batch size (profiles/r4a_*, r4b_*, dpdfnet4 ms/hop FFMA2 / tcgen05: 4 streams 0.595 / 0.491, 64: 0.616 / 0.514, 512: 0.738 / 0.585; dpdfnet8_48khz_hr 512: 1.96 / 1.25); before it the cross-over was 640 streams (profiles/r2v_sweep.log)
   int intra_pdl = 0;              // sweep of block i >= 1 launched as a programmatic dependent of the previous block's post kernel (prologue under its tail)
   int intra_sr = 2;               // k_dprnn_intra_tc "split rows": the D rows of a stream carry the hi | lo operand halves, two MMA passes instead of three; 0 off, 1 whenever D > 1, 2 = with D = 4 only (measured)
   int dfp_early = 0;              // df pathway conv on a forked stream right behind df_conv0 (needs encoder_fork), k_df_combine + gru_commit on the coefficient tail; measured +0.5..0.8 % hop time (the ERB tail is as long): off
