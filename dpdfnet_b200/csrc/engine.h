@@ -209,7 +209,7 @@ struct Engine {
   int intra_frag = 1;             // k_dprnn_intra_tc fragment form where the sweep runs 32 streams per CTA (intra_dup 4): two rows per stream, .16x128b TMEM fragments
   int intra_dup = 0;              // k_dprnn_intra_tc row duplication D (128 / D streams per CTA): 0 = auto (largest D whose sweep fits one wave), 1, 2, 4
   int gru_tc = 2;                 // GRUCell(256) gate GEMMs on tcgen05: 0 never, 1 always, 2 = when B >= gru_tc_min
-  int gru_tc_min = 256;
+  int gru_tc_min = 1;             // since the recurrent half runs ahead of the grid dependency and the MMAs issue under elect.sync the tcgen05 cells win at every batch size (profiles/r4d_*: 1 / 64 / 192 streams 0.463 / 0.515 / 0.562 -> 0.381 / 0.432 / 0.487 ms per hop; 256 before)
   int dft_tc = 2;                 // framed DFT / inverse DFT + OLA on tcgen05 (k_dft_tc.cu): 0 never, 1 always, 2 = when B >= dft_tc_min
   int dft_tc_min = 512;
   int spec_tc_ld = 0, yspec_tc_ld = 0;       // floats per stream of the two scratch rows
