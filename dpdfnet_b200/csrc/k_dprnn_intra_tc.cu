@@ -689,7 +689,7 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
         umma_f16(d, da + ks * 16, dbl + ks * 16, idesc_f16(128, 192), 1);
       }
     };
-    auto h_mma_slice = [&](int t, int kk) {                  // K slice kk = operand columns [8 kk, 8 kk + 8)
+    auto h_mma_slice = [&](int t, int kk, bool first) {      // K slice kk = operand columns [8 kk, 8 kk + 8); first of the step: hn is overwritten
       const uint32_t whi = w_base + 2 * W_IMG + kk * 256, wlo = w_base + 3 * W_IMG + kk * 256;
       const uint64_t rz_h = DESC0 | (whi >> 4), rz_l = DESC0 | (wlo >> 4);
       const uint64_t n_h = DESC0 | ((whi + 16 * 1024) >> 4), n_l = DESC0 | ((wlo + 16 * 1024) >> 4);
@@ -697,29 +697,32 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
       const uint32_t drz = tmem + TM_P + (t & 1) * 192, dn = tmem + TM_HN;
       umma_f16_ts(drz, a, rz_h, idesc_f16(128, 128), 1);
       umma_f16_ts(drz, a, rz_l, idesc_f16(128, 128), 1);
-      umma_f16_ts(dn, a, n_h, idesc_f16(128, 64), kk > 0);
+      umma_f16_ts(dn, a, n_h, idesc_f16(128, 64), first ? 0u : 1u);
       umma_f16_ts(dn, a, n_l, idesc_f16(128, 64), 1);
     };
     if (elect_one()) {
       mbar_wait(bars, 0);
       x_mma(0);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) h_mma_slice(0, kk);
+      for (int kk = 0; kk < 4; ++kk) h_mma_slice(0, kk, kk == 0);
       umma_commit(bars + 1);
       if (T > 1) x_mma(1);
     }
     for (int t = 0; t + 1 < T; ++t) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        // K slice kk = pair kk >> 1 of the eight gate warps with cg >> 1 == (kk & 1): they and this warp meet on barrier 1 + kk
+      for (int i = 0; i < 4; ++i) {
+        // K slice kk = pair kk >> 1 of the eight gate warps with cg >> 1 == (kk & 1): they and this warp meet on barrier 1 + kk.
+        // Of a pair's two slices the one of warps 8..15 is taken FIRST: those warps do not stage x, arrive earlier, and their
+        // four MMAs then run while warps 0..7 finish - only one slice's MMAs stay behind the last arrive of a step.
+        const int kk = i ^ 1;
         if (kk == 0) asm volatile("bar.sync 1, 288;" ::: "memory");
         if (kk == 1) asm volatile("bar.sync 2, 288;" ::: "memory");
         if (kk == 2) asm volatile("bar.sync 3, 288;" ::: "memory");
         if (kk == 3) asm volatile("bar.sync 4, 288;" ::: "memory");
-        if (kk == 3) TL(5);
+        if (i == 3) TL(5);
         if (elect_one()) {
           tc_fence_after();
-          h_mma_slice(t + 1, kk);
+          h_mma_slice(t + 1, kk, i == 0);
         }
         __syncwarp();
       }
@@ -833,9 +836,11 @@ __device__ __forceinline__ void intra_sweep_f(const IntraTcParams& p, const int 
         if (cg < 2) asm volatile("bar.arrive 1, 288;" ::: "memory");
         else asm volatile("bar.arrive 2, 288;" ::: "memory");
       }
-      tanh_stage(1, rr1, zz1);
+      // the chores sit between the hand-over and the second pair's tanh stage: their loads, conversions and stores fill the
+      // issue slots that chain leaves (after it they were a serial tail in front of the last arrive)
       if (t > 0) write_out(t - 1);
       if (t + 2 < T) store_x(t & 1, xv);                     // x_mma(t) (reader of this buffer) completed with the commit
+      tanh_stage(1, rr1, zz1);
       TL(3);
       TL(4);
       fence_async_smem();                                    // generic-proxy smem writes -> visible to the tensor core
