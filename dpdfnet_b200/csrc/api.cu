@@ -689,11 +689,12 @@ static int lanes_for(const Engine& e, int B) {
   // r4b_sweep_intra_tc_tiny.log (256 / 384 / 512 / 640 streams: one lane 0.58 / 0.60 / 0.65 / 0.68 ms per hop, 128-stream lanes 0.51 / 0.54 / 0.56 / 0.59)
   int L = e.lanes > 0 ? e.lanes : (B < 256 ? 1 : ((B >= 2560 && e.intra_frag && intra_tc_dup(e, B) == 4) ? 4 : 8));
   L = std::min(L, Engine::MAX_LANES);
-  while (L > 1 && B / L < 128) --L;
+  while (L > 1 && B / L < e.lane_min) --L;
   return std::max(L, 1);
 }
-static void lane_range(int B, int L, int l, int* r0, int* n) {
-  const int per = ((B + L - 1) / L + 127) / 128 * 128;          // lane sizes are multiples of the 128-stream MMA tile
+static void lane_range(const Engine& e, int B, int L, int l, int* r0, int* n) {
+  const int g = e.lane_min;
+  const int per = ((B + L - 1) / L + g - 1) / g * g;              // lane sizes are multiples of the 128-stream MMA tile (Engine::lane_min)
   *r0 = std::min(B, l * per);
   *n = std::min(B, (l + 1) * per) - *r0;
 }
@@ -710,7 +711,7 @@ static void enqueue_lanes(Engine& e, int B, cudaStream_t st, bool fork) {
   if (fork && L > 1) cudaEventRecord(e.lane_fork, st);
   for (int l = 0; l < L; ++l) {
     int r0, n;
-    lane_range(B, L, l, &r0, &n);
+    lane_range(e, B, L, l, &r0, &n);
     if (n <= 0) continue;
     for (size_t i = 0; i < base.size(); ++i) *e.sc_items[i].first = base[i] + (size_t)r0 * e.sc_items[i].second;
     e.io_dev = e.io_lanes + l;
@@ -770,7 +771,7 @@ static int run_hops_free(Engine& e, int B, int T, cudaStream_t st) {
   e.total_B = B;
   for (int l = 0; l < L && rc == 0; ++l) {
     int r0, n;
-    lane_range(B, L, l, &r0, &n);
+    lane_range(e, B, L, l, &r0, &n);
     if (n <= 0) continue;
     auto it = e.lane_graphs.find(B * Engine::MAX_LANES + l);
     if (it == e.lane_graphs.end()) {
@@ -817,7 +818,7 @@ static int set_io(Engine& e, const float* in, long long in_stride, float* out, l
   const long long rin = mode == 1 ? (long long)e.d.F * 2 : in_stride, rout = mode == 1 ? (long long)e.d.F * 2 : out_stride;
   for (int l = 0; l < L; ++l) {
     int r0, n;
-    lane_range(B, L, l, &r0, &n);
+    lane_range(e, B, L, l, &r0, &n);
     io[l].in = in + (size_t)r0 * rin; io[l].out = out + (size_t)r0 * rout;
     io[l].in_stride = in_stride; io[l].out_stride = out_stride;
     io[l].slot_ids = slot_ids ? slot_ids + r0 : nullptr; io[l].flags = flags ? flags + r0 : nullptr;
@@ -1298,6 +1299,10 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
     drop_graphs(e);
   } else if (strcmp(key, "dfp_early") == 0) {
     e.dfp_early = value ? 1 : 0;
+    drop_graphs(e);
+  } else if (strcmp(key, "lane_min") == 0) {
+    if (value < 32 || value % 32) return fail(DPDF_ERR_INVALID, "lane_min must be a positive multiple of 32");
+    e.lane_min = value;
     drop_graphs(e);
   } else if (strcmp(key, "frag_max") == 0) {
     e.frag_max = value;

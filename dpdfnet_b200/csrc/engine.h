@@ -191,7 +191,8 @@ struct Engine {
   // inside one CUDA graph, so the latency-bound kernels of one lane (the sequential intra-frame GRU sweep occupies
   // 32 SMs per 1024 streams) overlap with the throughput kernels of the others.  Lanes share the state arena (slots
   // are global) and use disjoint row ranges of the scratch arena.
-  static constexpr int MAX_LANES = 8;
+  static constexpr int MAX_LANES = 16;
+  int lane_min = 128;             // smallest lane (streams); lanes are multiples of it
   int lanes = 0;                  // 0 = auto by batch size
   int total_B = 0;                // batch of the whole step while its lanes are enqueued (kernel-variant choice)
   std::vector<std::pair<float**, size_t>> sc_items;   // scratch pointer members and their floats per stream
