@@ -1300,6 +1300,9 @@ extern "C" int dpdf_set_option(dpdf_engine* h, const char* key, int32_t value) {
   } else if (strcmp(key, "dfp_early") == 0) {
     e.dfp_early = value ? 1 : 0;
     drop_graphs(e);
+  } else if (strcmp(key, "sweep_prio") == 0) {
+    e.sweep_prio = value;
+    drop_graphs(e);
   } else if (strcmp(key, "lane_min") == 0) {
     if (value < 32 || value % 32) return fail(DPDF_ERR_INVALID, "lane_min must be a positive multiple of 32");
     e.lane_min = value;

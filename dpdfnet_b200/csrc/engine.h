@@ -192,6 +192,8 @@ struct Engine {
   // 32 SMs per 1024 streams) overlap with the throughput kernels of the others.  Lanes share the state arena (slots
   // are global) and use disjoint row ranges of the scratch arena.
   static constexpr int MAX_LANES = 16;
+  int sweep_prio = 0;             // launch priority of the sweep kernels (0 = default, v = -v): a sweep CTA needs a whole SM, lanes' small kernels fragment them
+  int prio_now = 0;               // priority of the launch being enqueued (launch_k)
   int lane_min = 128;             // smallest lane (streams); lanes are multiples of it
   int lanes = 0;                  // 0 = auto by batch size
   int total_B = 0;                // batch of the whole step while its lanes are enqueued (kernel-variant choice)
@@ -285,11 +287,19 @@ template <typename... KArgs, typename... Args>
 inline void launch_k(const Engine& e, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
   cfg.attrs = attr;
-  cfg.numAttrs = (e.pdl_now && !e.pdl_first) ? 1 : 0;
+  cfg.numAttrs = 0;
+  if (e.pdl_now && !e.pdl_first) {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    ++cfg.numAttrs;
+  }
+  if (e.prio_now) {                                        // kernel-node priority (Engine::sweep_prio): lower value = scheduled first
+    attr[cfg.numAttrs].id = cudaLaunchAttributePriority;
+    attr[cfg.numAttrs].val.priority = -e.prio_now;
+    ++cfg.numAttrs;
+  }
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

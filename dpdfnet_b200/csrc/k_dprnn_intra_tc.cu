@@ -940,6 +940,7 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   p.err = e.err_dev;
   const dim3 grid(2 * (p.tiles[0] + p.tiles[1]));
   const bool sr = e.intra_sr == 1 ? D > 1 : (e.intra_sr == 2 && D == 4);    // auto: where the step is tensor bound (profiles/r3b_*)
+  e.prio_now = e.sweep_prio;
   p.wimg_f[0] = e.w.dprnn_df[blk].tc_intra_f;
   p.wimg_f[1] = e.w.dprnn_erb[blk].tc_intra_f;
   if (D == 4 && e.intra_frag && p.wimg_f[0] && DE == 4 && p.wimg_f[1]) launch_k(e, k_dprnn_intra_tc<4, 4, 2, 2>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
@@ -949,6 +950,7 @@ void launch_dprnn_intra_tc(Engine& e, int blk, int B, cudaStream_t st) {
   else if (D == 4) launch_k(e, k_dprnn_intra_tc<4, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else if (D == 2) launch_k(e, k_dprnn_intra_tc<2, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
   else launch_k(e, k_dprnn_intra_tc<1, 1>, grid, dim3(ITC_NT), INTRA_TC_SMEM, st, p);
+  e.prio_now = 0;
 }
 
 void init_dprnn_intra_tc_kernels() {

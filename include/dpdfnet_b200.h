@@ -140,7 +140,8 @@ int dpdf_kernel_launches(const dpdf_engine* e);    /* kernels launched by the la
  * per CTA); "intra_frag" 0/1 fragment form of that kernel where it runs 32 streams per CTA (two rows per stream, .16x128b
  * TMEM fragments; on, up to "frag_max" = 6 144 streams per step); "intra_sr" 0 / 1 / 2 split rows (hi | lo operand halves in the D rows of a stream, two MMA passes) never /
  * whenever D > 1 / with D = 4 only when the fragment form is off (default 2); "dfp_early" 0/1 df pathway conv on a forked
- * stream behind df_conv0 + k_df_combine (measured slower, off); "sep_tma" 0/1 tensor-core separable convs as the persistent TMA-fed kernel; "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel; "c0_fp16" 0/1 c0 ring stored in half precision (switch only on freshly reset streams); "ana_nb" / "syn_sb" caps on the
+ * stream behind df_conv0 + k_df_combine (measured slower, off); "lane_min" smallest lane in streams (128), "sweep_prio" launch
+ * priority of the sweep kernels (measured neutral, 0); "sep_tma" 0/1 tensor-core separable convs as the persistent TMA-fed kernel; "post_tc" 0/1; "intra_bt" 0/8/16/32 stream tile of the FFMA2 intra-GRU kernel; "c0_fp16" 0/1 c0 ring stored in half precision (switch only on freshly reset streams); "ana_nb" / "syn_sb" caps on the
  * streams per CTA of the analysis / synthesis kernels ("ana_force" / "syn_force" force a count, experiments only); "post_pf" L2 prefetch distance of the post kernel; "dfp_ps" 0/1
  * df pathway conv as pending partial sums (switch only on freshly reset streams); "pdl" 0 / 1 chain every kernel of a
  * hop with programmatic dependent launches / 2 every segment but the DPRNN stack; "tail_pdl" 0/1 the dense tail only; "intra_pdl" 0/1 the sweep of block i >= 1 as a programmatic dependent of the previous
