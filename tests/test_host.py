@@ -126,3 +126,30 @@ def test_packed_blob_carries_tensor_core_images():
             assert t[f"{q}.tc.gates"].size == 6 * 64 * 64 and t[f"{q}.tc.fc_w"].size == 2 * 64 * 64
             b, tb = t[f"{q}.intra.bias"].reshape(2, 4, 64), t[f"{q}.tc.intra_bias"].reshape(2, 4, 64)
             assert np.allclose(tb[:, :2], -LOG2E * b[:, :2], rtol=1e-6) and np.allclose(tb[:, 2:], 2 * LOG2E * b[:, 2:], rtol=1e-6)
+
+
+def test_fragment_form_images_permute_only_the_recurrent_k_axis():
+    """tc.intra_f (k_dprnn_intra_tc.cu:intra_sweep_f): W_ih images identical to tc.intra; W_hh images hold, at K element
+    k = 2 c + e of operand column c = 16 p + 4 cg + j, hidden unit 16 (2 p + e) + 4 cg + j - the two units one gate thread
+    packs into that column - for both branches and both directions."""
+    from dpdfnet_b200.spec import get_spec
+    from dpdfnet_b200.weights import pack_tensors, random_checkpoint
+    spec = get_spec("dpdfnet2_48khz_hr")
+    t = pack_tensors(spec, random_checkpoint(spec, 4))
+    W = 192 * 64                                            # halves per image
+
+    def unimage(img16):                                     # K-major SWIZZLE_NONE image -> [192, 64]
+        return img16.reshape(192 // 8, 64 // 8, 8, 8).transpose(0, 2, 1, 3).reshape(192, 64)
+
+    for br in ("erb", "df"):
+        for i in range(spec.n_blocks):
+            a = t[f"enc.dprnn_{br}.{i}.tc.intra"].view(np.float16).reshape(2, 4, W)
+            f = t[f"enc.dprnn_{br}.{i}.tc.intra_f"].view(np.float16).reshape(2, 4, W)
+            assert np.array_equal(a[:, :2], f[:, :2])                             # W_ih hi | lo untouched
+            for d in range(2):
+                for im in (2, 3):                                                 # W_hh hi, lo
+                    plain, perm = unimage(a[d, im]), unimage(f[d, im])
+                    for c in range(32):
+                        p, cg, j = c >> 4, (c >> 2) & 3, c & 3
+                        for e in range(2):
+                            assert np.array_equal(perm[:, 2 * c + e], plain[:, 16 * (2 * p + e) + 4 * cg + j])
