@@ -649,7 +649,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-ladder", action="store_true", help="skip the sustained-streams batch ladder")
     ap.add_argument("--no-extras", action="store_true", help="cfg1 only: skip the compact cfg2..cfg4 results")
-    ap.add_argument("--ladder", type=int, nargs="*", default=[8192, 16384, 20480, 22528, 23552, 24576, 25600])
+    ap.add_argument("--ladder", type=int, nargs="*", default=[8192, 16384, 20480, 22528, 23552, 24576, 25600, 26624])
     ap.add_argument("--stream-ladder", type=int, nargs="*", default=[1024, 2048, 3072, 4096, 4608, 5120, 5632])
     ap.add_argument("--stream-ticks", type=int, default=300)
     ap.add_argument("--many-ladder", type=int, nargs="*", default=[256, 1024], help="StreamEnhancer objects per process_many tick")

@@ -687,7 +687,10 @@ static int lanes_for(const Engine& e, int B) {
   if (overlap_applies(e, B)) return 1;
   // measured: profiles/r01B_lanes.log, r3q_sweep_overlap_1024.log, r3v_sweep_frag_lanes_big.log
   // r4b_sweep_intra_tc_tiny.log (256 / 384 / 512 / 640 streams: one lane 0.58 / 0.60 / 0.65 / 0.68 ms per hop, 128-stream lanes 0.51 / 0.54 / 0.56 / 0.59)
-  int L = e.lanes > 0 ? e.lanes : (B < 256 ? 1 : ((B >= 2560 && e.intra_frag && intra_tc_dup(e, B) == 4) ? 4 : 8));
+  // r4O / r4P / r4Q: beyond the fragment form's range two lanes beat eight (7168 / 8192 / 16384 / 24576 streams 3.03 / 3.36 / 6.44 /
+  // 9.62 -> 2.95 / 3.25 / 6.27 / 9.35 ms per hop)
+  const bool frag = e.intra_frag && intra_tc_dup(e, B) == 4;
+  int L = e.lanes > 0 ? e.lanes : (B < 256 ? 1 : (frag ? (B >= 2560 ? 4 : 8) : 2));
   L = std::min(L, Engine::MAX_LANES);
   while (L > 1 && B / L < e.lane_min) --L;
   return std::max(L, 1);
